@@ -1,0 +1,205 @@
+/*
+ * ldm_b200.h -- C ABI of the B200-native DDPM denoising hot path.
+ *
+ * The reference (JohanLundberg12/latent-diffusion-models) is pure Python/PyTorch
+ * and has no FFI of its own; its "operator API" for this path is the duck-typed
+ * Python protocol of src/UNet.py and src/DDPM.py.  Every entry point below
+ * replaces the PyTorch library calls behind one reference function and cites it
+ * (file:line relative to the reference tree).  INTEGRATION.md shows the ctypes
+ * binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch types.
+ *   - every function returns 0 on success, <0 on error; ldm_last_error() gives the
+ *     thread-local message.  Nothing throws or aborts across the boundary.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.
+ *   - every launch goes to the caller's `stream` (a cudaStream_t passed as void*);
+ *     no hidden synchronisation, no host reads of device data, no allocation after
+ *     *_create / *_load_params (so the calls are CUDA-graph capturable).
+ *   - reference-facing tensors are fp32 NCHW contiguous, indices are int64
+ *     (what src/DDPM.py and src/UNet.py exchange).  Internally activations are
+ *     NHWC in the handle's compute dtype.
+ */
+#ifndef LDM_B200_H_
+#define LDM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDM_B200_ABI_VERSION 1
+
+/* compute precision of a UNet handle */
+enum ldm_dtype {
+  LDM_F32 = 0,  /* fp32 activations, FFMA implicit-GEMM convs: parity path (<=1e-4 rel.)   */
+  LDM_BF16 = 1  /* bf16 NHWC activations, tcgen05/TMEM/TMA implicit-GEMM convs (<=2e-2 rel.) */
+};
+
+/* ---- library ---------------------------------------------------------------------- */
+int ldm_abi_version(void);
+const char* ldm_last_error(void);
+/* number of kernels this library has launched since load / last reset (all handles). */
+int64_t ldm_launch_count(void);
+void ldm_reset_launch_count(void);
+
+/* ---- UNet eps-model: replaces src/UNet.py:293-389 (UNet.__init__ / UNet.forward) -- */
+typedef struct ldm_unet ldm_unet;
+
+typedef struct ldm_unet_desc {
+  int32_t in_channels;        /* src/UNet.py:296 */
+  int32_t out_channels;       /* src/UNet.py:297 */
+  int32_t channels;           /* src/UNet.py:298 (default 64)                        */
+  int32_t n_levels;           /* len(channel_multipliers), src/UNet.py:299           */
+  int32_t channel_multipliers[8];
+  int32_t with_time_emb;      /* src/UNet.py:300                                      */
+  int32_t num_classes;        /* src/UNet.py:301; 0 = None                            */
+  int32_t image_size;         /* H = W of x_noisy; must be divisible by 2^n_levels    */
+  int32_t dtype;              /* enum ldm_dtype                                       */
+  int32_t conv_impl;          /* 0 = default for dtype (bf16: tcgen05), 1 = force FFMA (debug/A-B) */
+} ldm_unet_desc;
+
+int ldm_unet_create(const ldm_unet_desc* desc, ldm_unet** out);
+void ldm_unet_destroy(ldm_unet* h);
+
+/* Number of state_dict tensors and their canonical order / names / element counts
+ * (order == reference state_dict order). */
+int ldm_unet_num_params(const ldm_unet* h);
+const char* ldm_unet_param_name(const ldm_unet* h, int index);
+int64_t ldm_unet_param_numel(const ldm_unet* h, int index);
+
+/* (Re)pack all parameters from the caller's fp32 state_dict tensors (device pointers,
+ * canonical order, PyTorch layouts: conv OIHW, ConvTranspose IOHW, Linear [out,in]).
+ * Replaces nn.Module.load_state_dict for the packed copies (src/utils.py:36-45). */
+int ldm_unet_load_params(ldm_unet* h, const float* const* params, int n_params, void* stream);
+
+/* Workspace the caller must provide to forward for a batch of `batch` rows. */
+int64_t ldm_unet_workspace_bytes(const ldm_unet* h, int batch);
+
+/* eps = UNet(x_noisy, t, y)  -- src/UNet.py:361-389.
+ *   x      [batch, Cin, S, S] fp32 NCHW          out [batch, Cout, S, S] fp32 NCHW
+ *   t      [batch] int64, or NULL with t_dev_scalar: one int64 on the device broadcast to all rows
+ *   y      int64 labels: y_len == batch, or y_len == 1 (broadcast, src/UNet.py:375-376), or NULL/0 = None
+ *   y_rows applies labels only to rows [0, y_rows) (classifier-free-guidance batching: rows
+ *          [0,B) conditional, [B,2B) unconditional); pass `batch` for the plain call.        */
+int ldm_unet_forward(ldm_unet* h, const float* x, const int64_t* t, const int64_t* t_dev_scalar,
+                     const int64_t* y, int y_len, int y_rows, int batch, float* out,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Debug/parity tap: subsequent forwards also copy the named internal NHWC activation to fp32 NCHW
+ * `out_nchw` (device, `out_numel` elements); name NULL or out NULL clears the tap.
+ * names: "initial", "enc{i}.res", "enc{i}.attn", "bottleneck", "dec{i}", "final.res", "temb". */
+int ldm_unet_set_tap(ldm_unet* h, const char* name, float* out_nchw, int64_t out_numel);
+
+/* ---- diffusion process: replaces src/DDPM.py --------------------------------------- */
+
+/* q_sample: x_t = sqrt(abar[t_b]) x0 + sqrt(1-abar[t_b]) eps      (src/DDPM.py:46-68)
+ * eps==NULL: eps is drawn in-kernel (Philox4x32-10, key seed, counter = global element) and
+ * written to eps_out (src/DDPM.py:63-64, torch.randn_like).  n_per_sample = C*H*W.         */
+int ldm_q_sample(const float* x0, const int64_t* t, const float* alpha_bar, int n_steps,
+                 const float* eps, float* eps_out, float* xt, int batch, int64_t n_per_sample,
+                 uint64_t seed, uint64_t sample_offset, void* stream);
+
+/* p_sample with fused classifier-free guidance (src/DDPM.py:71-96 and :120-124):
+ *   eps  = eps_uncond ? eps_uncond + cfg_scale*(eps_cond - eps_uncond) : eps_cond
+ *   mean = alpha_t^-1/2 (x_t - (1-alpha_t)/sqrt(1-abar_t) eps)
+ *   out  = t==0 ? mean : mean + sqrt(beta_t) z
+ * t is read from the device: t_dev holds t_len int64 (1 = batch-constant, or `batch` per-sample values:
+ * alpha/alpha_bar are gathered per sample, the t==0 branch follows t_dev[0] as in the reference, :74-85).
+ * z = noise if given, else in-kernel Philox keyed by (seed, sample_offset+b, t).
+ * coef is the [n_steps,4] fp32 table built by ldm_build_coef_table.  In-place (out==xt) allowed. */
+int ldm_p_sample(const float* xt, const float* eps_cond, const float* eps_uncond, float cfg_scale,
+                 const int64_t* t_dev, int t_len, const float* coef, int n_steps, const float* noise,
+                 uint64_t seed, uint64_t sample_offset, float* out, int batch, int64_t n_per_sample,
+                 void* stream);
+
+/* coef[t] = { alpha_t^-1/2, (1-alpha_t)/sqrt(1-abar_t), sqrt(beta_t), 0 } from the reference's
+ * fp32 schedule tensors (src/DDPM.py:31-43), computed on the device in fp32. */
+int ldm_build_coef_table(const float* beta, const float* alpha, const float* alpha_bar, int n_steps,
+                         float* coef, void* stream);
+
+/* Standard normal fill (x_T ~ N(0,I), src/DDPM.py:108) with the sampler's Philox keying:
+ * element e of sample (sample_offset+b) at stream `stream_id` -- invariant to batch sharding. */
+int ldm_randn(float* out, int batch, int64_t n_per_sample, uint64_t seed, uint64_t sample_offset,
+              uint64_t stream_id, void* stream);
+
+/* ---- sampler: replaces the loop of Diffusion.sample, src/DDPM.py:98-130 ------------- */
+typedef struct ldm_sampler ldm_sampler;
+
+typedef struct ldm_sampler_desc {
+  int32_t batch;          /* images per call on this GPU                                  */
+  int32_t n_steps;        /* T (src/DDPM.py:23)                                           */
+  float cfg_scale;        /* >0: cond+uncond batched as one 2B pass (src/DDPM.py:119-124) */
+  int32_t y_len;          /* 0 (None), 1 (broadcast) or batch                             */
+  int32_t use_graph;      /* 1: capture one step as a CUDA graph and replay T times       */
+} ldm_sampler_desc;
+
+int ldm_sampler_create(ldm_unet* unet, const ldm_sampler_desc* desc, ldm_sampler** out);
+void ldm_sampler_destroy(ldm_sampler* s);
+int64_t ldm_sampler_workspace_bytes(const ldm_sampler* s);
+
+/* Runs the whole reverse process on `stream`:
+ *   x      [batch,C,S,S] fp32 NCHW: holds x_T on entry when x_is_init!=0 (fixed-noise parity),
+ *          otherwise it is filled with N(0,I) from (seed, sample_offset); holds x_0 on return.
+ *   y      int64[y_len] device labels (or NULL)
+ *   coef   [n_steps,4] table (ldm_build_coef_table)
+ *   noise  optional [n_steps, batch, C,S,S] fp32 injected per-step noise indexed by t (parity), else NULL
+ *   first_step / num_steps: run timesteps t = first_step, first_step-1, ... (num_steps of them);
+ *          pass n_steps-1 / n_steps for the full trajectory.
+ * No host synchronisation inside; the caller syncs the stream. */
+int ldm_sampler_run(ldm_sampler* s, float* x, int x_is_init, const int64_t* y, const float* coef,
+                    const float* noise, uint64_t seed, uint64_t sample_offset,
+                    int first_step, int num_steps, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+
+/* ---- kernel-level entry points (unit parity tests and ncu targets) ------------------
+ * NHWC tensors; `dtype` selects float or bf16 element type; ld* = pixel stride in elements. */
+
+/* GroupNorm(+SiLU)(+residual): y = [silu](gn(x)) [+ res]  -- src/UNet.py:52-58,106,147,20 */
+int ldm_group_norm(const void* x, int ldx, void* y, int ldy, const void* res, int ldres,
+                   const float* gamma, const float* beta, int batch, int hw, int channels, int groups,
+                   float eps, int silu, int dtype, void* workspace, void* stream);
+int64_t ldm_group_norm_workspace_bytes(int batch, int groups);
+
+/* 3x3 (pad 1) / 1x1 convolution as implicit GEMM -- src/UNet.py:54,82,119,145 (F.conv2d).
+ *   w_packed: [Cout][taps*Cin (+Cin2)] in `dtype` (see ldm_pack_conv_weight); bias fp32 or NULL
+ *   x2/cin2 : optional second 1x1 source K-concatenated after the taps (fused ResNetBlock shortcut, :99)
+ *   rowvec  : optional fp32 [batch][ld_rowvec] added per sample and output channel (time embedding, :88-93)
+ *   res     : optional residual tensor added in the epilogue (identity shortcut, :99)
+ *   impl    : 0 default (bf16: tcgen05, f32: FFMA), 1 force FFMA                              */
+int ldm_conv2d(const void* x, int ldx, int cin, const void* x2, int ldx2, int cin2,
+               const void* w_packed, const float* bias, const float* rowvec, int ld_rowvec,
+               const void* res, int ldres, void* y, int ldy, int cout,
+               int batch, int height, int width, int ksize, int dtype, int impl, void* stream);
+/* OIHW fp32 -> packed [Cout][kh][kw][Cin] (+ optional OI11 second source appended along K) */
+int ldm_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize,
+                         const float* w2_oi11, int cin2, void* w_packed, int dtype, void* stream);
+
+/* ConvTranspose2d(kernel 2, stride 2) -- src/UNet.py:231-233 (F.conv_transpose2d): a [B*H*W, 4*Cout] GEMM
+ * whose epilogue scatters quadrant (dy,dx) to pixel (2h+dy, 2w+dx); y is [B,2H,2W,*] with pixel stride ldy
+ * (so it can write straight into the first Cout channels of the decoder's concat buffer, :245).
+ *   w_packed: [(dy,dx,co)][Cin] from ldm_pack_conv_transpose_weight (PyTorch layout IOHW [Cin][Cout][2][2]) */
+int ldm_conv_transpose2x2(const void* x, int ldx, int cin, const void* w_packed, const float* bias, void* y,
+                          int ldy, int cout, int batch, int height, int width, int dtype, int impl, void* stream);
+int ldm_pack_conv_transpose_weight(const float* w_iohw, int cin, int cout, void* w_packed, int dtype,
+                                   void* stream);
+
+/* MaxPool2d(2,2) -- src/UNet.py:183,207 */
+int ldm_max_pool2x2(const void* x, int ldx, void* y, int ldy, int batch, int height, int width, int channels,
+                    int dtype, void* stream);
+
+/* LinearAttention core (src/UNet.py:149-163): qkv [B,N,384] -> out [B,N,128] */
+int ldm_linear_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, void* stream);
+/* Attention core (src/UNet.py:122-135): qkv [B,N,384] -> out [B,N,128], N <= 256 */
+int ldm_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, void* stream);
+
+/* layout converters used by the tests: fp32 NCHW <-> NHWC(dtype) */
+int ldm_nchw_to_nhwc(const float* x, void* y, int batch, int channels, int hw, int dtype, void* stream);
+int ldm_nhwc_to_nchw(const void* x, int ldx, float* y, int batch, int channels, int hw, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDM_B200_H_ */

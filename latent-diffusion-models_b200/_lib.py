@@ -1,0 +1,119 @@
+"""ctypes binding of libldm_b200.so (the C ABI declared in include/ldm_b200.h).
+
+There is no CPU fallback: every entry point raises if the CUDA library is missing or a call fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libldm_b200.so")
+_lib: Optional[C.CDLL] = None
+
+F32, BF16 = 0, 1
+DTYPES = {"fp32": F32, "f32": F32, "float32": F32, "bf16": BF16, "bfloat16": BF16}
+
+c_i64p = C.POINTER(C.c_int64)
+vp = C.c_void_p
+
+
+class UNetDesc(C.Structure):
+    _fields_ = [("in_channels", C.c_int32), ("out_channels", C.c_int32), ("channels", C.c_int32),
+                ("n_levels", C.c_int32), ("channel_multipliers", C.c_int32 * 8),
+                ("with_time_emb", C.c_int32), ("num_classes", C.c_int32), ("image_size", C.c_int32),
+                ("dtype", C.c_int32), ("conv_impl", C.c_int32)]
+
+
+class SamplerDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("n_steps", C.c_int32), ("cfg_scale", C.c_float),
+                ("y_len", C.c_int32), ("use_graph", C.c_int32)]
+
+
+# name -> (restype, argtypes); mirrors include/ldm_b200.h one to one
+SIGNATURES = {
+    "ldm_abi_version": (C.c_int, []),
+    "ldm_last_error": (C.c_char_p, []),
+    "ldm_launch_count": (C.c_int64, []),
+    "ldm_reset_launch_count": (None, []),
+    "ldm_unet_create": (C.c_int, [C.POINTER(UNetDesc), C.POINTER(vp)]),
+    "ldm_unet_destroy": (None, [vp]),
+    "ldm_unet_num_params": (C.c_int, [vp]),
+    "ldm_unet_param_name": (C.c_char_p, [vp, C.c_int]),
+    "ldm_unet_param_numel": (C.c_int64, [vp, C.c_int]),
+    "ldm_unet_load_params": (C.c_int, [vp, C.POINTER(vp), C.c_int, vp]),
+    "ldm_unet_workspace_bytes": (C.c_int64, [vp, C.c_int]),
+    "ldm_unet_forward": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int64, vp]),
+    "ldm_unet_set_tap": (C.c_int, [vp, C.c_char_p, vp, C.c_int64]),
+    "ldm_q_sample": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int64, C.c_uint64, C.c_uint64, vp]),
+    "ldm_p_sample": (C.c_int, [vp, vp, vp, C.c_float, vp, C.c_int, vp, C.c_int, vp, C.c_uint64, C.c_uint64, vp,
+                               C.c_int, C.c_int64, vp]),
+    "ldm_build_coef_table": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
+    "ldm_randn": (C.c_int, [vp, C.c_int, C.c_int64, C.c_uint64, C.c_uint64, C.c_uint64, vp]),
+    "ldm_sampler_create": (C.c_int, [vp, C.POINTER(SamplerDesc), C.POINTER(vp)]),
+    "ldm_sampler_destroy": (None, [vp]),
+    "ldm_sampler_workspace_bytes": (C.c_int64, [vp]),
+    "ldm_sampler_run": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, vp,
+                                  C.c_int64, vp]),
+    "ldm_group_norm": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_float, C.c_int, C.c_int, vp, vp]),
+    "ldm_group_norm_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
+    "ldm_conv2d": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, vp,
+                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_pack_conv_weight": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp]),
+    "ldm_conv_transpose2x2": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_pack_conv_transpose_weight": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp]),
+    "ldm_max_pool2x2": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_linear_attention": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_attention": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_nchw_to_nhwc": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_nhwc_to_nchw": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+}
+
+
+class LdmError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raises (no fallback) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LdmError(f"{LIB_PATH} is missing: run `python __graft_entry__.py` to build the sm_100a kernels; "
+                       "there is no CPU or PyTorch fallback for this path")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ldm_abi_version() != 1:
+        raise LdmError("libldm_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise LdmError(load().ldm_last_error().decode(errors="replace"))
+
+
+def launch_count() -> int:
+    return int(load().ldm_launch_count())
+
+
+def reset_launch_count() -> None:
+    load().ldm_reset_launch_count()
+
+
+def ptr(t) -> Optional[int]:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,468 @@
+// Memory-bound kernels of the DDPM hot path: layout converters, max-pool, the fused
+// p_sample / q_sample updates, the time-embedding MLP and the tiny first/last convolutions.
+// All are HBM-bound: 16-byte vector accesses, one read + one write of every live tensor.
+#include "kernels.h"
+
+// ------------------------------------------------------------------ layout converters (tests, taps)
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int C, int HW,
+                                    int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  int64_t r = i / C;
+  int p = (int)(r % HW);
+  int64_t b = r / HW;
+  y[i] = from_float<T>(x[(b * C + c) * HW + p]);
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, int ldx, float* __restrict__ y, int C, int HW,
+                                    int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int p = (int)(i % HW);
+  int64_t r = i / HW;
+  int c = (int)(r % C);
+  int64_t b = r / C;
+  y[i] = to_float(x[(b * HW + p) * (int64_t)ldx + c]);
+}
+int k_nchw_to_nhwc(const float* x, void* y, int batch, int channels, int hw, int dtype, cudaStream_t st) {
+  int64_t total = (int64_t)batch * channels * hw;
+  if (total == 0) return 0;
+  int grid = (int)ceil_div64(total, 256);
+  if (dtype == LDM_DT_BF16) nchw_to_nhwc_kernel<bf16><<<grid, 256, 0, st>>>(x, (bf16*)y, channels, hw, total);
+  else nchw_to_nhwc_kernel<float><<<grid, 256, 0, st>>>(x, (float*)y, channels, hw, total);
+  LDM_LAUNCHED("nchw_to_nhwc");
+  return 0;
+}
+int k_nhwc_to_nchw(const void* x, int ldx, float* y, int batch, int channels, int hw, int dtype,
+                   cudaStream_t st) {
+  int64_t total = (int64_t)batch * channels * hw;
+  if (total == 0) return 0;
+  int grid = (int)ceil_div64(total, 256);
+  if (dtype == LDM_DT_BF16) nhwc_to_nchw_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, ldx, y, channels, hw, total);
+  else nhwc_to_nchw_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ldx, y, channels, hw, total);
+  LDM_LAUNCHED("nhwc_to_nchw");
+  return 0;
+}
+
+// ------------------------------------------------------------------ MaxPool2d(2,2)  src/UNet.py:183,207
+template <typename T>
+__global__ void maxpool2_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int H, int W,
+                                int C, int64_t total_chunks) {
+  constexpr int V = VecTraits<T>::N;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_chunks) return;
+  int cpp = C / V;
+  int ci = (int)(i % cpp);
+  int64_t r = i / cpp;
+  int Wo = W / 2, Ho = H / 2;
+  int wo = (int)(r % Wo); r /= Wo;
+  int ho = (int)(r % Ho);
+  int64_t b = r / Ho;
+  const T* p00 = x + ((b * H + 2 * ho) * W + 2 * wo) * (int64_t)ldx + ci * V;
+  float a[V], c[V], d[V], e[V], o[V];
+  load_chunk(p00, a);
+  load_chunk(p00 + ldx, c);
+  load_chunk(p00 + (int64_t)W * ldx, d);
+  load_chunk(p00 + (int64_t)W * ldx + ldx, e);
+#pragma unroll
+  for (int k = 0; k < V; ++k) o[k] = fmaxf(fmaxf(a[k], c[k]), fmaxf(d[k], e[k]));
+  store_chunk(y + ((b * Ho + ho) * Wo + wo) * (int64_t)ldy + ci * V, o);
+}
+int k_maxpool2(const void* x, int ldx, void* y, int ldy, int batch, int height, int width, int channels,
+               int dtype, cudaStream_t st) {
+  int V = dtype == LDM_DT_BF16 ? 8 : 4;
+  LDM_REQUIRE(channels % V == 0 && ldx % V == 0 && ldy % V == 0, "maxpool2: channels/ld must be a multiple of %d", V);
+  LDM_REQUIRE(height % 2 == 0 && width % 2 == 0, "maxpool2: odd spatial size %dx%d", height, width);
+  int64_t total = (int64_t)batch * (height / 2) * (width / 2) * (channels / V);
+  if (total == 0) return 0;
+  int grid = (int)ceil_div64(total, 256);
+  if (dtype == LDM_DT_BF16)
+    maxpool2_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, ldx, (bf16*)y, ldy, height, width, channels, total);
+  else
+    maxpool2_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ldx, (float*)y, ldy, height, width, channels, total);
+  LDM_LAUNCHED("maxpool2");
+  return 0;
+}
+
+// ------------------------------------------------------------------ schedule coefficient table
+// coef[t] = {alpha^-1/2, (1-alpha)/sqrt(1-abar), sqrt(beta), 0}: the per-step scalars of src/DDPM.py:74-96
+__global__ void build_coef_kernel(const float* beta, const float* alpha, const float* abar, int T, float* coef) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  float a = alpha[t], ab = abar[t], b = beta[t];
+  float4 c;
+  c.x = 1.0f / sqrtf(a);
+  c.y = (1.0f - a) / sqrtf(1.0f - ab);
+  c.z = sqrtf(b);
+  c.w = 0.0f;
+  reinterpret_cast<float4*>(coef)[t] = c;
+}
+int k_build_coef(const float* beta, const float* alpha, const float* alpha_bar, int n_steps, float* coef,
+                 cudaStream_t st) {
+  LDM_REQUIRE(n_steps > 0, "build_coef: n_steps must be positive");
+  build_coef_kernel<<<(n_steps + 127) / 128, 128, 0, st>>>(beta, alpha, alpha_bar, n_steps, coef);
+  LDM_LAUNCHED("build_coef");
+  return 0;
+}
+
+// ------------------------------------------------------------------ randn (x_T ~ N(0,I), src/DDPM.py:108)
+__global__ void randn_kernel(float* __restrict__ out, int64_t n4, int64_t total4, uint64_t seed,
+                             uint64_t sample_offset, uint32_t stream_id, uint32_t step) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  int64_t b = i / n4, e4 = i % n4;
+  uint64_t s = sample_offset + (uint64_t)b;
+  float z[4];
+  philox_normal4(seed, (uint32_t)e4, (uint32_t)s, step, stream_id ^ ((uint32_t)(s >> 32) << 8), z);
+  reinterpret_cast<float4*>(out)[i] = make_float4(z[0], z[1], z[2], z[3]);
+}
+int k_randn(float* out, int batch, int64_t n_per_sample, uint64_t seed, uint64_t sample_offset,
+            uint64_t stream_id, cudaStream_t st) {
+  LDM_REQUIRE(n_per_sample % 4 == 0, "randn: n_per_sample must be a multiple of 4");
+  int64_t n4 = n_per_sample / 4, total4 = n4 * batch;
+  if (total4 == 0) return 0;
+  randn_kernel<<<(int)ceil_div64(total4, 256), 256, 0, st>>>(out, n4, total4, seed, sample_offset,
+                                                            (uint32_t)stream_id, 0xFFFFFFFFu);
+  LDM_LAUNCHED("randn");
+  return 0;
+}
+
+// ------------------------------------------------------------------ q_sample  src/DDPM.py:46-68,133-149
+__global__ void q_sample_kernel(const float4* __restrict__ x0, const int64_t* __restrict__ t,
+                                const float* __restrict__ abar, int T, const float4* __restrict__ eps,
+                                float4* __restrict__ eps_out, float4* __restrict__ xt, int64_t n4,
+                                int64_t total4, uint64_t seed, uint64_t sample_offset) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  int64_t b = i / n4, e4 = i % n4;
+  int64_t tb = t[b];
+  tb = tb < 0 ? 0 : (tb >= T ? T - 1 : tb);
+  float ab = abar[tb];
+  float sa = sqrtf(ab), sb = sqrtf(1.0f - ab);
+  float4 x = x0[i], e;
+  if (eps) {
+    e = eps[i];
+  } else {
+    float z[4];
+    uint64_t s = sample_offset + (uint64_t)b;
+    philox_normal4(seed, (uint32_t)e4, (uint32_t)s, (uint32_t)tb, 0x71u ^ ((uint32_t)(s >> 32) << 8), z);
+    e = make_float4(z[0], z[1], z[2], z[3]);
+  }
+  if (eps_out) eps_out[i] = e;
+  xt[i] = make_float4(sa * x.x + sb * e.x, sa * x.y + sb * e.y, sa * x.z + sb * e.z, sa * x.w + sb * e.w);
+}
+int k_q_sample(const float* x0, const int64_t* t, const float* alpha_bar, int n_steps, const float* eps,
+               float* eps_out, float* xt, int batch, int64_t n_per_sample, uint64_t seed,
+               uint64_t sample_offset, cudaStream_t st) {
+  LDM_REQUIRE(n_per_sample % 4 == 0, "q_sample: n_per_sample must be a multiple of 4");
+  LDM_REQUIRE(eps != nullptr || eps_out != nullptr, "q_sample: eps_out is required when eps is drawn in-kernel");
+  int64_t n4 = n_per_sample / 4, total4 = n4 * batch;
+  if (total4 == 0) return 0;
+  q_sample_kernel<<<(int)ceil_div64(total4, 256), 256, 0, st>>>(
+      (const float4*)x0, t, alpha_bar, n_steps, (const float4*)eps, (float4*)eps_out, (float4*)xt, n4, total4,
+      seed, sample_offset);
+  LDM_LAUNCHED("q_sample");
+  return 0;
+}
+
+// ------------------------------------------------------------------ p_sample + CFG  src/DDPM.py:71-96,120-124
+__device__ __forceinline__ float lerp_torch(float start, float end, float w) {
+  // at::lerp: w < 0.5 ? start + w (end-start) : end - (end-start)(1-w)
+  float d = end - start;
+  return w < 0.5f ? start + w * d : end - d * (1.0f - w);
+}
+__global__ void p_sample_kernel(const float4* __restrict__ xt, const float4* __restrict__ ec,
+                                const float4* __restrict__ eu, float cfg, const int64_t* __restrict__ t_dev,
+                                int t_stride, const float4* __restrict__ coef, int T, const float* __restrict__ noise,
+                                int64_t noise_t_stride, uint64_t seed, uint64_t sample_offset,
+                                float4* __restrict__ out, int64_t n4, int64_t total4) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  // the reference gathers alpha/alpha_bar per sample but takes the noise branch on t[0] (src/DDPM.py:74-85)
+  int64_t t = t_dev[0];
+  t = t < 0 ? 0 : (t >= T ? T - 1 : t);
+  int64_t tb = t_stride ? t_dev[(i / n4) * t_stride] : t;
+  tb = tb < 0 ? 0 : (tb >= T ? T - 1 : tb);
+  float4 c = coef[tb];
+  float4 x = xt[i], e = ec[i];
+  if (eu) {
+    float4 u = eu[i];
+    e.x = lerp_torch(u.x, e.x, cfg); e.y = lerp_torch(u.y, e.y, cfg);
+    e.z = lerp_torch(u.z, e.z, cfg); e.w = lerp_torch(u.w, e.w, cfg);
+  }
+  float4 m;
+  m.x = c.x * (x.x - c.y * e.x); m.y = c.x * (x.y - c.y * e.y);
+  m.z = c.x * (x.z - c.y * e.z); m.w = c.x * (x.w - c.y * e.w);
+  if (t > 0) {
+    float z[4];
+    if (noise) {
+      float4 zz = reinterpret_cast<const float4*>(noise + t * noise_t_stride)[i];
+      z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
+    } else {
+      int64_t b = i / n4, e4 = i % n4;
+      uint64_t s = sample_offset + (uint64_t)b;
+      philox_normal4(seed, (uint32_t)e4, (uint32_t)s, (uint32_t)t, 0x9Eu ^ ((uint32_t)(s >> 32) << 8), z);
+    }
+    m.x += c.z * z[0]; m.y += c.z * z[1]; m.z += c.z * z[2]; m.w += c.z * z[3];
+  }
+  out[i] = m;
+}
+int k_p_sample(const float* xt, const float* eps_c, const float* eps_u, float cfg_scale, const int64_t* t_dev,
+               int t_stride, const float* coef, int n_steps, const float* noise, int64_t noise_t_stride, uint64_t seed,
+               uint64_t sample_offset, float* out, int batch, int64_t n_per_sample, cudaStream_t st) {
+  LDM_REQUIRE(n_per_sample % 4 == 0, "p_sample: n_per_sample must be a multiple of 4");
+  int64_t n4 = n_per_sample / 4, total4 = n4 * batch;
+  if (total4 == 0) return 0;
+  p_sample_kernel<<<(int)ceil_div64(total4, 256), 256, 0, st>>>(
+      (const float4*)xt, (const float4*)eps_c, (const float4*)eps_u, cfg_scale, t_dev, t_stride, (const float4*)coef,
+      n_steps, noise, noise_t_stride, seed, sample_offset, (float4*)out, n4, total4);
+  LDM_LAUNCHED("p_sample");
+  return 0;
+}
+
+__global__ void set_i64_kernel(int64_t* p, int64_t v) { *p = v; }
+__global__ void add_i64_kernel(int64_t* p, int64_t v) { *p += v; }
+int k_set_i64(int64_t* p, int64_t v, cudaStream_t st) {
+  set_i64_kernel<<<1, 1, 0, st>>>(p, v);
+  LDM_LAUNCHED("set_i64");
+  return 0;
+}
+int k_add_i64(int64_t* p, int64_t v, cudaStream_t st) {
+  add_i64_kernel<<<1, 1, 0, st>>>(p, v);
+  LDM_LAUNCHED("add_i64");
+  return 0;
+}
+
+// ------------------------------------------------------------------ time embedding  src/UNet.py:23-44,263-268,373-376
+// One CTA handles TE_ROWS batch rows so each weight is read once per TE_ROWS rows. blockDim = D.
+#define TE_ROWS 8
+__global__ void time_embed_kernel(const int64_t* __restrict__ t, const int64_t* __restrict__ t_scalar,
+                                  const int64_t* __restrict__ y, int y_len, int y_rows,
+                                  const float* __restrict__ w1t, const float* __restrict__ b1,
+                                  const float* __restrict__ w3t, const float* __restrict__ b3,
+                                  const float* __restrict__ label_emb, float* __restrict__ temb, int batch,
+                                  int D) {
+  extern __shared__ float sm[];
+  const int Din = D / 4, half = D / 8;
+  float* emb = sm;                 // [TE_ROWS][Din]
+  float* h1 = sm + TE_ROWS * Din;  // [TE_ROWS][D]
+  const int j = threadIdx.x;
+  const int b0 = blockIdx.x * TE_ROWS;
+  // sinusoid: f_i = exp(i * -(ln 1e4 / (half-1))) in fp32, arg = float(t) * f_i
+  const float neg = -(float)(9.210340371976184 / (double)(half - 1));
+  for (int idx = j; idx < TE_ROWS * Din; idx += blockDim.x) {
+    int r = idx / Din, i = idx % Din;
+    int b = b0 + r;
+    float v = 0.f;
+    if (b < batch) {
+      float tv = (float)(t ? t[b] : *t_scalar);
+      int fi = i < half ? i : i - half;
+      float arg = tv * expf((float)fi * neg);
+      v = i < half ? sinf(arg) : cosf(arg);
+    }
+    emb[idx] = v;
+  }
+  __syncthreads();
+  float acc[TE_ROWS];
+#pragma unroll
+  for (int r = 0; r < TE_ROWS; ++r) acc[r] = 0.f;
+  for (int i = 0; i < Din; ++i) {
+    float w = w1t[i * D + j];
+#pragma unroll
+    for (int r = 0; r < TE_ROWS; ++r) acc[r] = fmaf(emb[r * Din + i], w, acc[r]);
+  }
+  float bb = b1[j];
+#pragma unroll
+  for (int r = 0; r < TE_ROWS; ++r) {
+    float v = acc[r] + bb;
+    h1[r * D + j] = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));  // exact-erf GELU
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < TE_ROWS; ++r) acc[r] = 0.f;
+  for (int k = 0; k < D; ++k) {
+    float w = w3t[k * D + j];
+#pragma unroll
+    for (int r = 0; r < TE_ROWS; ++r) acc[r] = fmaf(h1[r * D + k], w, acc[r]);
+  }
+  bb = b3[j];
+#pragma unroll
+  for (int r = 0; r < TE_ROWS; ++r) {
+    int b = b0 + r;
+    if (b >= batch) break;
+    float v = acc[r] + bb;
+    if (y && y_len > 0 && b < y_rows) {
+      int64_t cls = y_len == 1 ? y[0] : y[b];
+      v += label_emb[cls * D + j];
+    }
+    temb[(int64_t)b * D + j] = v;
+  }
+}
+int k_time_embed(const int64_t* t, const int64_t* t_scalar, const int64_t* y, int y_len, int y_rows,
+                 const float* w1t, const float* b1, const float* w3t, const float* b3, const float* label_emb,
+                 float* temb, int batch, int D, cudaStream_t st) {
+  LDM_REQUIRE(D % 32 == 0 && D <= 1024 && D >= 32, "time_embed: unsupported embedding width %d", D);
+  LDM_REQUIRE(t != nullptr || t_scalar != nullptr, "time_embed: need t or t_dev_scalar");
+  if (batch == 0) return 0;
+  size_t smem = (size_t)TE_ROWS * (D / 4 + D) * sizeof(float);
+  time_embed_kernel<<<(batch + TE_ROWS - 1) / TE_ROWS, D, smem, st>>>(t, t_scalar, y, y_len, y_rows, w1t, b1,
+                                                                      w3t, b3, label_emb, temb, batch, D);
+  LDM_LAUNCHED("time_embed");
+  return 0;
+}
+
+// tproj = Linear(SiLU(temb)) for all ResNetBlocks at once  src/UNet.py:70-73,90-93
+#define TP_ROWS 16
+__global__ void time_proj_kernel(const float* __restrict__ temb, const float* __restrict__ wt,
+                                 const float* __restrict__ bias, float* __restrict__ tproj, int batch, int D,
+                                 int total) {
+  extern __shared__ float s[];  // [TP_ROWS][D] silu(temb)
+  const int b0 = blockIdx.y * TP_ROWS;
+  for (int idx = threadIdx.x; idx < TP_ROWS * D; idx += blockDim.x) {
+    int r = idx / D, k = idx % D;
+    float v = 0.f;
+    if (b0 + r < batch) v = silu_acc(temb[(int64_t)(b0 + r) * D + k]);
+    s[idx] = v;
+  }
+  __syncthreads();
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= total) return;
+  float acc[TP_ROWS];
+#pragma unroll
+  for (int r = 0; r < TP_ROWS; ++r) acc[r] = 0.f;
+  for (int k = 0; k < D; ++k) {
+    float w = wt[(int64_t)k * total + o];
+#pragma unroll
+    for (int r = 0; r < TP_ROWS; ++r) acc[r] = fmaf(s[r * D + k], w, acc[r]);
+  }
+  float bb = bias[o];
+#pragma unroll
+  for (int r = 0; r < TP_ROWS; ++r)
+    if (b0 + r < batch) tproj[(int64_t)(b0 + r) * total + o] = acc[r] + bb;
+}
+int k_time_proj(const float* temb, const float* wt, const float* bias, float* tproj, int batch, int D,
+                int total, cudaStream_t st) {
+  if (batch == 0 || total == 0) return 0;
+  dim3 grid((total + 127) / 128, (batch + TP_ROWS - 1) / TP_ROWS);
+  size_t smem = (size_t)TP_ROWS * D * sizeof(float);
+  LDM_REQUIRE(smem <= 48 * 1024, "time_proj: embedding width %d too large", D);
+  time_proj_kernel<<<grid, 128, smem, st>>>(temb, wt, bias, tproj, batch, D, total);
+  LDM_LAUNCHED("time_proj");
+  return 0;
+}
+
+// ------------------------------------------------------------------ initial 3x3 conv (Cin <= 8)  src/UNet.py:331,378
+// fp32 NCHW in -> NHWC out.  One thread: one pixel x 8 output channels.  w smem [9][Cin][Cout].
+template <typename T>
+__global__ void initial_conv_kernel(const float* __restrict__ x, int x_batch, const float* __restrict__ w,
+                                    const float* __restrict__ bias, T* __restrict__ y, int Cin, int Cout, int H,
+                                    int W, int64_t total) {
+  extern __shared__ float sw[];  // 9*Cin*Cout weights, then Cout bias
+  for (int i = threadIdx.x; i < 9 * Cin * Cout; i += blockDim.x) sw[i] = w[i];
+  float* sb = sw + 9 * Cin * Cout;
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias[i];
+  __syncthreads();
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int cg = Cout / 8;
+  int g = (int)(i % cg);
+  int64_t r = i / cg;
+  int wq = (int)(r % W); r /= W;
+  int hq = (int)(r % H);
+  int64_t b = r / H;
+  int64_t bs = b % x_batch;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = sb[g * 8 + k];
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float* xp = x + (bs * Cin + ci) * (int64_t)H * W;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      int hh = hq + dy - 1;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        int ww = wq + dx - 1;
+        if (ww < 0 || ww >= W) continue;
+        float xv = xp[hh * W + ww];
+        const float* wp = sw + ((dy * 3 + dx) * Cin + ci) * Cout + g * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv, wp[k], acc[k]);
+      }
+    }
+  }
+  T* yp = y + ((b * H + hq) * W + wq) * (int64_t)Cout + g * 8;
+  if constexpr (sizeof(T) == 2) {
+    store_chunk(yp, acc);
+  } else {
+    float lo[4] = {acc[0], acc[1], acc[2], acc[3]}, hi[4] = {acc[4], acc[5], acc[6], acc[7]};
+    store_chunk(yp, lo);
+    store_chunk(yp + 4, hi);
+  }
+}
+int k_initial_conv(const float* x, int x_batch, const float* w, const float* bias, void* y, int batch, int cin,
+                   int cout, int height, int width, int dtype, cudaStream_t st) {
+  LDM_REQUIRE(cin >= 1 && cin <= 8, "initial_conv: in_channels %d not in [1,8]", cin);
+  LDM_REQUIRE(cout % 8 == 0, "initial_conv: channels must be a multiple of 8");
+  int64_t total = (int64_t)batch * height * width * (cout / 8);
+  if (total == 0) return 0;
+  size_t smem = (size_t)(9 * cin * cout + cout) * sizeof(float);
+  LDM_REQUIRE(smem <= 48 * 1024, "initial_conv: weights do not fit shared memory");
+  int grid = (int)ceil_div64(total, 256);
+  if (dtype == LDM_DT_BF16)
+    initial_conv_kernel<bf16><<<grid, 256, smem, st>>>(x, x_batch, w, bias, (bf16*)y, cin, cout, height, width, total);
+  else
+    initial_conv_kernel<float><<<grid, 256, smem, st>>>(x, x_batch, w, bias, (float*)y, cin, cout, height, width, total);
+  LDM_LAUNCHED("initial_conv");
+  return 0;
+}
+
+// ------------------------------------------------------------------ final 1x1 conv (Cout <= 8)  src/UNet.py:347
+template <typename T>
+__global__ void final_conv_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ w,
+                                  const float* __restrict__ bias, float* __restrict__ y, int Cin, int Cout,
+                                  int HW, int64_t total) {
+  constexpr int V = VecTraits<T>::N;
+  extern __shared__ float sw[];  // [Cout][Cin] then bias
+  for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[Cout * Cin + i] = bias[i];
+  __syncthreads();
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int64_t b = i / HW;
+  int p = (int)(i % HW);
+  const T* xp = x + i * (int64_t)ldx;
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = o < Cout ? sw[Cout * Cin + o] : 0.f;
+  for (int c0 = 0; c0 < Cin; c0 += V) {
+    float v[V];
+    load_chunk(xp + c0, v);
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      if (o < Cout) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[o] = fmaf(v[k], sw[o * Cin + c0 + k], acc[o]);
+      }
+    }
+  }
+  for (int o = 0; o < Cout; ++o) y[(b * Cout + o) * (int64_t)HW + p] = acc[o];
+}
+int k_final_conv(const void* x, int ldx, const float* w, const float* bias, float* y, int batch, int cin,
+                 int cout, int hw, int dtype, cudaStream_t st) {
+  LDM_REQUIRE(cout >= 1 && cout <= 8, "final_conv: out_channels %d not in [1,8]", cout);
+  int V = dtype == LDM_DT_BF16 ? 8 : 4;
+  LDM_REQUIRE(cin % V == 0 && ldx % V == 0, "final_conv: channels must be a multiple of %d", V);
+  int64_t total = (int64_t)batch * hw;
+  if (total == 0) return 0;
+  size_t smem = (size_t)(cout * cin + cout) * sizeof(float);
+  int grid = (int)ceil_div64(total, 128);
+  if (dtype == LDM_DT_BF16)
+    final_conv_kernel<bf16><<<grid, 128, smem, st>>>((const bf16*)x, ldx, w, bias, y, cin, cout, hw, total);
+  else
+    final_conv_kernel<float><<<grid, 128, smem, st>>>((const float*)x, ldx, w, bias, y, cin, cout, hw, total);
+  LDM_LAUNCHED("final_conv");
+  return 0;
+}

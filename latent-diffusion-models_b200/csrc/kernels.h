@@ -1,0 +1,82 @@
+// Internal host-side launchers shared between translation units (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+// ---- elementwise.cu
+int k_nchw_to_nhwc(const float* x, void* y, int batch, int channels, int hw, int dtype, cudaStream_t st);
+int k_nhwc_to_nchw(const void* x, int ldx, float* y, int batch, int channels, int hw, int dtype, cudaStream_t st);
+int k_maxpool2(const void* x, int ldx, void* y, int ldy, int batch, int height, int width, int channels,
+               int dtype, cudaStream_t st);
+int k_build_coef(const float* beta, const float* alpha, const float* alpha_bar, int n_steps, float* coef,
+                 cudaStream_t st);
+int k_randn(float* out, int batch, int64_t n_per_sample, uint64_t seed, uint64_t sample_offset,
+            uint64_t stream_id, cudaStream_t st);
+int k_q_sample(const float* x0, const int64_t* t, const float* alpha_bar, int n_steps, const float* eps,
+               float* eps_out, float* xt, int batch, int64_t n_per_sample, uint64_t seed,
+               uint64_t sample_offset, cudaStream_t st);
+// noise_t_stride: elements between consecutive timesteps in `noise` (0: `noise` is this step's tensor)
+// t_stride: 0 = one batch-constant timestep at t_dev[0]; 1 = per-sample t_dev[b] (noise branch still on t_dev[0])
+int k_p_sample(const float* xt, const float* eps_c, const float* eps_u, float cfg_scale, const int64_t* t_dev,
+               int t_stride, const float* coef, int n_steps, const float* noise, int64_t noise_t_stride, uint64_t seed,
+               uint64_t sample_offset, float* out, int batch, int64_t n_per_sample, cudaStream_t st);
+int k_set_i64(int64_t* p, int64_t v, cudaStream_t st);
+int k_add_i64(int64_t* p, int64_t v, cudaStream_t st);
+
+// time embedding (src/UNet.py:23-44,263-268,373-376): temb [batch,D] fp32
+//   w1t [D/4][D], w3t [D][D] are the transposed Linear weights; label_emb [num_classes][D]
+int k_time_embed(const int64_t* t, const int64_t* t_scalar, const int64_t* y, int y_len, int y_rows,
+                 const float* w1t, const float* b1, const float* w3t, const float* b3, const float* label_emb,
+                 float* temb, int batch, int D, cudaStream_t st);
+// tproj[b][o] = sum_k silu(temb[b][k]) wt[k][o] + bias[o]   (src/UNet.py:70-73,90-93), o < total
+int k_time_proj(const float* temb, const float* wt, const float* bias, float* tproj, int batch, int D,
+                int total, cudaStream_t st);
+
+// initial 3x3 conv, tiny Cin: fp32 NCHW in (row b reads image b % x_batch) -> NHWC out (src/UNet.py:331,378)
+//   w [3][3][Cin][Cout] fp32
+int k_initial_conv(const float* x, int x_batch, const float* w, const float* bias, void* y, int batch, int cin,
+                   int cout, int height, int width, int dtype, cudaStream_t st);
+// final 1x1 conv, tiny Cout: NHWC in -> fp32 NCHW out (src/UNet.py:347); w [Cout][Cin] fp32
+int k_final_conv(const void* x, int ldx, const float* w, const float* bias, float* y, int batch, int cin,
+                 int cout, int hw, int dtype, cudaStream_t st);
+
+// ---- groupnorm.cu
+int64_t k_group_norm_ws_bytes(int batch, int groups);
+int k_group_norm(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
+                 const float* beta, int batch, int hw, int channels, int groups, float eps, int silu, int dtype,
+                 void* workspace, cudaStream_t st);
+
+// ---- attention.cu
+int k_linear_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, cudaStream_t st);
+int k_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, cudaStream_t st);
+
+// ---- conv (conv_simt.cu / conv_tc.cu)
+struct ConvArgs {
+  const void* x; int ldx; int cin;        // main source, NHWC [batch,H,W,*]
+  const void* x2; int ldx2; int cin2;     // optional K-concatenated 1x1 source (same spatial size)
+  const void* w;                          // packed [Cout_total][taps*cin + cin2], element type = dtype
+  const float* bias;                      // [cout_total] or null (indexed by output channel, see `up2`)
+  const float* rowvec; int ld_rowvec;     // optional [batch][ld_rowvec] per-sample, per-channel add
+  const void* res; int ldres;             // optional residual NHWC (same spatial size, cout channels)
+  void* y; int ldy;                       // output NHWC
+  int cout;                               // GEMM N (for up2: 4 * output channels)
+  int batch, height, width;
+  int ksize;                              // 1 or 3 (pad = ksize/2)
+  int up2;                                // 1: ConvTranspose2d k2 s2 scatter epilogue (GEMM N = 4*Cout, quadrant-major)
+  int dtype;
+};
+int k_conv_simt(const ConvArgs& a, cudaStream_t st);
+int k_conv_tc(const ConvArgs& a, cudaStream_t st);   // bf16 only, tcgen05/TMEM/TMA
+int k_conv_tc_prepare();  // resolve the driver entry point + opt in to large dynamic smem (call outside graph capture)
+int k_conv(const ConvArgs& a, int impl, cudaStream_t st);
+
+// weight packing (pack.cu)
+int k_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, const float* w2_oi11, int cin2,
+                       void* w_packed, int dtype, cudaStream_t st);
+// ConvTranspose2d IOHW [Cin][Cout][2][2] -> [(dy,dx,co)][ci]
+int k_pack_convT_weight(const float* w_iohw, int cin, int cout, void* w_packed, int dtype, cudaStream_t st);
+int k_transpose_f32(const float* w, int rows, int cols, float* wt, int ld_out, int col_off, cudaStream_t st);
+int k_copy_f32(const float* src, float* dst, int64_t n, cudaStream_t st);
+// initial conv weight OIHW -> [3][3][Cin][Cout]
+int k_pack_initial_weight(const float* w_oihw, int cout, int cin, float* out, cudaStream_t st);
+// dst = a + b (b may be null): fused conv2 + shortcut bias
+int k_add2_f32(const float* a, const float* b, float* dst, int n, cudaStream_t st);

@@ -1,0 +1,539 @@
+// UNet eps-model handle: parameter inventory, weight packing and the forward pass as a fixed sequence of
+// kernel launches on the caller's stream (graph-capturable: no allocation, no host sync).
+// Mirrors src/UNet.py:293-389 of the reference; activations are NHWC in the handle's compute dtype.
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/ldm_b200.h"
+#include "kernels.h"
+#include "unet_internal.h"
+
+namespace {
+
+constexpr int HIDDEN = 128;  // heads(4) * dim_head(32), src/UNet.py:114,140
+constexpr float GN_EPS = 1e-5f;
+
+struct ParamInfo {
+  std::string name;
+  int64_t numel;
+};
+
+struct ResW {
+  int cin = 0, cout = 0;
+  bool has_t = false, has_sc = false;
+  int p_mlp_w = -1, p_mlp_b = -1, p_n1w = -1, p_n1b = -1, p_c1w = -1, p_c1b = -1, p_n2w = -1, p_n2b = -1,
+      p_c2w = -1, p_c2b = -1, p_scw = -1, p_scb = -1;
+  void* w1 = nullptr; float* b1 = nullptr;
+  void* w2 = nullptr; float* b2 = nullptr;  // conv2 (+K-concatenated shortcut), bias = conv2.bias (+ shortcut.bias)
+  float *g1 = nullptr, *be1 = nullptr, *g2 = nullptr, *be2 = nullptr;
+  int tproj_off = -1;  // column offset into the concatenated time projection (-1: no live time embedding)
+};
+struct AttnW {
+  int dim = 0;
+  bool linear = true;
+  int p_qkv = -1, p_ow = -1, p_ob = -1, p_ogw = -1, p_ogb = -1, p_nw = -1, p_nb = -1;
+  void* wqkv = nullptr; void* wout = nullptr; float* bout = nullptr;
+  float *og = nullptr, *ob = nullptr, *ng = nullptr, *nb = nullptr;
+};
+struct UpW {
+  int cin = 0, cout = 0;
+  int p_w = -1, p_b = -1;
+  void* w = nullptr; float* b = nullptr;
+};
+
+struct Tap {
+  std::string name;
+  float* out = nullptr;
+  int64_t numel = 0;
+};
+
+}  // namespace
+
+struct ldm_unet {
+  ldm_unet_desc d;
+  int L = 0;                 // levels
+  int D = 0;                 // time embedding width (channels*4)
+  std::vector<int> dims;     // [channels, channels*m0, ...]
+  std::vector<ParamInfo> params;
+  // parameter indices of the non-block tensors
+  int p_t1w = -1, p_t1b = -1, p_t3w = -1, p_t3b = -1, p_label = -1, p_iw = -1, p_ib = -1, p_fw = -1, p_fb = -1;
+  std::vector<ResW> enc_res, dec_res;
+  std::vector<AttnW> enc_attn, dec_attn;
+  std::vector<UpW> ups;
+  ResW bott1, bott2, final_res;
+  AttnW bott_attn;
+  // packed time path
+  float *w1t = nullptr, *b1 = nullptr, *w3t = nullptr, *b3 = nullptr, *label = nullptr;
+  float *tproj_wt = nullptr, *tproj_b = nullptr;
+  int tproj_total = 0;
+  float *init_w = nullptr, *init_b = nullptr, *fin_w = nullptr, *fin_b = nullptr;
+  // arena
+  uint8_t* arena = nullptr;
+  int64_t arena_bytes = 0;
+  bool loaded = false;
+  Tap tap;
+  int es() const { return dtype_size(d.dtype); }
+};
+
+namespace {
+
+int add_param(ldm_unet* h, const std::string& name, int64_t numel) {
+  h->params.push_back({name, numel});
+  return (int)h->params.size() - 1;
+}
+
+void add_res(ldm_unet* h, ResW& r, const std::string& p, int cin, int cout, bool temb) {
+  r.cin = cin; r.cout = cout; r.has_t = temb; r.has_sc = cin != cout;
+  if (temb) {
+    r.p_mlp_w = add_param(h, p + ".mlp_t.1.weight", (int64_t)cout * h->D);
+    r.p_mlp_b = add_param(h, p + ".mlp_t.1.bias", cout);
+  }
+  r.p_n1w = add_param(h, p + ".block1.norm.weight", cin);
+  r.p_n1b = add_param(h, p + ".block1.norm.bias", cin);
+  r.p_c1w = add_param(h, p + ".block1.conv2d.weight", (int64_t)cout * cin * 9);
+  r.p_c1b = add_param(h, p + ".block1.conv2d.bias", cout);
+  r.p_n2w = add_param(h, p + ".block2.norm.weight", cout);
+  r.p_n2b = add_param(h, p + ".block2.norm.bias", cout);
+  r.p_c2w = add_param(h, p + ".block2.conv2d.weight", (int64_t)cout * cout * 9);
+  r.p_c2b = add_param(h, p + ".block2.conv2d.bias", cout);
+  if (r.has_sc) {
+    r.p_scw = add_param(h, p + ".shortcut.weight", (int64_t)cout * cin);
+    r.p_scb = add_param(h, p + ".shortcut.bias", cout);
+  }
+}
+void add_attn(ldm_unet* h, AttnW& a, const std::string& p, int dim, bool linear) {
+  a.dim = dim; a.linear = linear;
+  a.p_qkv = add_param(h, p + ".fn.fn.to_qkv.weight", (int64_t)3 * HIDDEN * dim);
+  if (linear) {
+    a.p_ow = add_param(h, p + ".fn.fn.to_out.0.weight", (int64_t)dim * HIDDEN);
+    a.p_ob = add_param(h, p + ".fn.fn.to_out.0.bias", dim);
+    a.p_ogw = add_param(h, p + ".fn.fn.to_out.1.weight", dim);
+    a.p_ogb = add_param(h, p + ".fn.fn.to_out.1.bias", dim);
+  } else {
+    a.p_ow = add_param(h, p + ".fn.fn.to_out.weight", (int64_t)dim * HIDDEN);
+    a.p_ob = add_param(h, p + ".fn.fn.to_out.bias", dim);
+  }
+  a.p_nw = add_param(h, p + ".fn.norm.weight", dim);
+  a.p_nb = add_param(h, p + ".fn.norm.bias", dim);
+}
+
+// bump allocator over the arena (two passes: size, then assign)
+struct Bump {
+  uint8_t* base;
+  int64_t off = 0;
+  template <typename T>
+  void take(T*& p, int64_t bytes) {
+    off = align_up64(off, 256);
+    p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += bytes;
+  }
+};
+
+void layout_res(Bump& b, ResW& r, int es) {
+  b.take(r.w1, (int64_t)r.cout * 9 * r.cin * es);
+  b.take(r.b1, r.cout * 4);
+  b.take(r.w2, (int64_t)r.cout * (9 * r.cout + (r.has_sc ? r.cin : 0)) * es);
+  b.take(r.b2, r.cout * 4);
+  b.take(r.g1, r.cin * 4); b.take(r.be1, r.cin * 4);
+  b.take(r.g2, r.cout * 4); b.take(r.be2, r.cout * 4);
+}
+void layout_attn(Bump& b, AttnW& a, int es) {
+  b.take(a.wqkv, (int64_t)3 * HIDDEN * a.dim * es);
+  b.take(a.wout, (int64_t)a.dim * HIDDEN * es);
+  b.take(a.bout, a.dim * 4);
+  if (a.linear) { b.take(a.og, a.dim * 4); b.take(a.ob, a.dim * 4); }
+  b.take(a.ng, a.dim * 4); b.take(a.nb, a.dim * 4);
+}
+int64_t layout_all(ldm_unet* h, uint8_t* base) {
+  Bump b{base};
+  const int es = h->es(), D = h->D, C0 = h->dims[0];
+  if (h->d.with_time_emb) {
+    b.take(h->w1t, (int64_t)(D / 4) * D * 4); b.take(h->b1, D * 4);
+    b.take(h->w3t, (int64_t)D * D * 4); b.take(h->b3, D * 4);
+    if (h->d.num_classes > 0) b.take(h->label, (int64_t)h->d.num_classes * D * 4);
+    b.take(h->tproj_wt, (int64_t)D * (h->tproj_total > 0 ? h->tproj_total : 1) * 4);
+    b.take(h->tproj_b, (int64_t)(h->tproj_total > 0 ? h->tproj_total : 1) * 4);
+  }
+  b.take(h->init_w, (int64_t)9 * h->d.in_channels * C0 * 4); b.take(h->init_b, C0 * 4);
+  b.take(h->fin_w, (int64_t)h->d.out_channels * C0 * 4); b.take(h->fin_b, h->d.out_channels * 4);
+  for (auto& r : h->enc_res) layout_res(b, r, es);
+  for (auto& a : h->enc_attn) layout_attn(b, a, es);
+  layout_res(b, h->bott1, es); layout_attn(b, h->bott_attn, es); layout_res(b, h->bott2, es);
+  for (auto& r : h->dec_res) layout_res(b, r, es);
+  for (auto& a : h->dec_attn) layout_attn(b, a, es);
+  for (auto& u : h->ups) { b.take(u.w, (int64_t)4 * u.cout * u.cin * es); b.take(u.b, u.cout * 4); }
+  layout_res(b, h->final_res, es);
+  return align_up64(b.off, 256);
+}
+
+// workspace plan for one forward of `batch` rows
+struct Plan {
+  int64_t temb, tproj, gnws, qkv, s[4], total;
+  std::vector<int64_t> hin;  // [L+1]
+  std::vector<int64_t> cat;  // [L]
+};
+Plan make_plan(const ldm_unet* h, int batch) {
+  Plan p;
+  const int es = h->es(), L = h->L, S = h->d.image_size;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { off = align_up64(off, 1024); int64_t o = off; off += bytes; return o; };
+  p.temb = take((int64_t)batch * (h->D > 0 ? h->D : 1) * 4);
+  p.tproj = take((int64_t)batch * (h->tproj_total > 0 ? h->tproj_total : 1) * 4);
+  p.gnws = take(k_group_norm_ws_bytes(batch, 8));
+  int64_t max_elems = 0;
+  for (int i = 0; i < L; ++i) {
+    int64_t R = S >> i;
+    int64_t catc = h->dims[i + 1] + h->dims[i];  // decoder level L-1-i concat: up(dims[i]) + skip(dims[i+1])
+    // (decoder j = L-1-i: rd[j+1] = dims[i], rd[j] = dims[i+1])
+    int64_t c = std::max<int64_t>(std::max<int64_t>(catc, h->dims[i + 1]), HIDDEN);
+    max_elems = std::max(max_elems, R * R * c);
+  }
+  {
+    int64_t R = S >> L;
+    max_elems = std::max(max_elems, R * R * std::max<int64_t>(h->dims[L], HIDDEN));
+  }
+  for (int i = 0; i < 4; ++i) p.s[i] = take(batch * max_elems * es);
+  p.qkv = take((int64_t)batch * S * S * 3 * HIDDEN * es);
+  p.hin.resize(L + 1);
+  for (int i = 0; i <= L; ++i) {
+    int64_t R = S >> i;
+    p.hin[i] = take(batch * R * R * h->dims[i] * es);
+  }
+  p.cat.resize(L);
+  for (int j = 0; j < L; ++j) {
+    int i = L - 1 - j;  // encoder level whose skip feeds decoder level j
+    int64_t R = S >> i;
+    p.cat[j] = take(batch * R * R * (h->dims[i] + h->dims[i + 1]) * es);
+  }
+  p.total = align_up64(off, 1024);
+  return p;
+}
+
+}  // namespace
+
+// ================================================================== C ABI
+extern "C" int ldm_unet_create(const ldm_unet_desc* desc, ldm_unet** out) {
+  LDM_REQUIRE(desc && out, "ldm_unet_create: null argument");
+  LDM_REQUIRE(desc->n_levels >= 1 && desc->n_levels <= 8, "channel_multipliers: need 1..8 levels");
+  LDM_REQUIRE(desc->dtype == LDM_F32 || desc->dtype == LDM_BF16, "unknown dtype %d", desc->dtype);
+  LDM_REQUIRE(desc->channels > 0 && desc->channels % 64 == 0,
+              "channels=%d: the implicit-GEMM kernels need a multiple of 64", desc->channels);
+  LDM_REQUIRE(desc->in_channels >= 1 && desc->in_channels <= 8 && desc->out_channels >= 1 && desc->out_channels <= 8,
+              "in/out_channels must be in [1,8]");
+  LDM_REQUIRE(desc->image_size > 0 && desc->image_size % (1 << desc->n_levels) == 0,
+              "image_size %d is not divisible by 2^%d (the reference decoder would fail at torch.cat, src/UNet.py:245)",
+              desc->image_size, desc->n_levels);
+  LDM_REQUIRE(desc->num_classes == 0 || desc->with_time_emb, "num_classes without time embedding is unsupported (src/UNet.py:375)");
+  ldm_unet* h = new ldm_unet();
+  h->d = *desc;
+  h->L = desc->n_levels;
+  h->D = desc->with_time_emb ? desc->channels * 4 : 0;
+  h->dims.push_back(desc->channels);
+  for (int i = 0; i < h->L; ++i) {
+    if (desc->channel_multipliers[i] < 1) { delete h; return ldm_set_error("channel multiplier must be >= 1"); }
+    h->dims.push_back(desc->channels * desc->channel_multipliers[i]);
+  }
+  const bool te = desc->with_time_emb != 0;
+  // ---- parameter inventory in reference state_dict order
+  if (te) {
+    h->p_t1w = add_param(h, "time_emb.time_mlp.1.weight", (int64_t)h->D * (h->D / 4));
+    h->p_t1b = add_param(h, "time_emb.time_mlp.1.bias", h->D);
+    h->p_t3w = add_param(h, "time_emb.time_mlp.3.weight", (int64_t)h->D * h->D);
+    h->p_t3b = add_param(h, "time_emb.time_mlp.3.bias", h->D);
+  }
+  if (desc->num_classes > 0) h->p_label = add_param(h, "label_emb.weight", (int64_t)desc->num_classes * h->D);
+  h->p_iw = add_param(h, "initial_conv.weight", (int64_t)desc->channels * desc->in_channels * 9);
+  h->p_ib = add_param(h, "initial_conv.bias", desc->channels);
+  h->enc_res.resize(h->L); h->enc_attn.resize(h->L);
+  for (int i = 0; i < h->L; ++i) {
+    std::string p = "encoder.downs." + std::to_string(i);
+    add_res(h, h->enc_res[i], p + ".0", h->dims[i], h->dims[i + 1], te);
+    add_attn(h, h->enc_attn[i], p + ".1", h->dims[i + 1], true);
+  }
+  const int CB = h->dims[h->L];
+  add_res(h, h->bott1, "bottleneck.res1", CB, CB, te);
+  add_attn(h, h->bott_attn, "bottleneck.attn", CB, false);
+  add_res(h, h->bott2, "bottleneck.res2", CB, CB, te);
+  h->dec_res.resize(h->L); h->dec_attn.resize(h->L); h->ups.resize(h->L);
+  for (int j = 0; j < h->L; ++j) {
+    const int cin = h->dims[h->L - j], cout = h->dims[h->L - j - 1];  // rd[j], rd[j+1]
+    std::string p = "decoder.ups." + std::to_string(j);
+    add_res(h, h->dec_res[j], p + ".0", cin + cout, cout, te);
+    add_attn(h, h->dec_attn[j], p + ".1", cout, true);
+    h->ups[j].cin = cin; h->ups[j].cout = cout;
+    h->ups[j].p_w = add_param(h, p + ".2.weight", (int64_t)cin * cout * 4);
+    h->ups[j].p_b = add_param(h, p + ".2.bias", cout);
+  }
+  add_res(h, h->final_res, "final_conv.0", desc->channels, desc->channels, false);
+  h->p_fw = add_param(h, "final_conv.1.weight", (int64_t)desc->out_channels * desc->channels);
+  h->p_fb = add_param(h, "final_conv.1.bias", desc->out_channels);
+  // live time projections: encoder + decoder ResNetBlocks (BottleNeck never passes t: src/UNet.py:287-288)
+  int off = 0;
+  if (te) {
+    for (auto& r : h->enc_res) { r.tproj_off = off; off += r.cout; }
+    for (auto& r : h->dec_res) { r.tproj_off = off; off += r.cout; }
+  }
+  h->tproj_total = off;
+  if (desc->dtype == LDM_BF16 && desc->conv_impl == 0) {
+    if (int rc = k_conv_tc_prepare()) { delete h; return rc; }
+  }
+  h->arena_bytes = layout_all(h, nullptr);
+  cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
+  if (e != cudaSuccess) {
+    delete h;
+    return ldm_set_error("cudaMalloc(%lld bytes of packed weights) failed: %s", (long long)h->arena_bytes, cudaGetErrorString(e));
+  }
+  layout_all(h, h->arena);
+  *out = h;
+  return 0;
+}
+
+extern "C" void ldm_unet_destroy(ldm_unet* h) {
+  if (!h) return;
+  if (h->arena) cudaFree(h->arena);
+  delete h;
+}
+extern "C" int ldm_unet_num_params(const ldm_unet* h) { return h ? (int)h->params.size() : 0; }
+extern "C" const char* ldm_unet_param_name(const ldm_unet* h, int i) {
+  return (h && i >= 0 && i < (int)h->params.size()) ? h->params[i].name.c_str() : nullptr;
+}
+extern "C" int64_t ldm_unet_param_numel(const ldm_unet* h, int i) {
+  return (h && i >= 0 && i < (int)h->params.size()) ? h->params[i].numel : -1;
+}
+
+namespace {
+#define RC(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+
+int pack_res(ldm_unet* h, ResW& r, const float* const* P, cudaStream_t st) {
+  const int dt = h->d.dtype;
+  RC(k_pack_conv_weight(P[r.p_c1w], r.cout, r.cin, 3, nullptr, 0, r.w1, dt, st));
+  RC(k_copy_f32(P[r.p_c1b], r.b1, r.cout, st));
+  RC(k_pack_conv_weight(P[r.p_c2w], r.cout, r.cout, 3, r.has_sc ? P[r.p_scw] : nullptr, r.has_sc ? r.cin : 0, r.w2, dt, st));
+  RC(k_add2_f32(P[r.p_c2b], r.has_sc ? P[r.p_scb] : nullptr, r.b2, r.cout, st));
+  RC(k_copy_f32(P[r.p_n1w], r.g1, r.cin, st)); RC(k_copy_f32(P[r.p_n1b], r.be1, r.cin, st));
+  RC(k_copy_f32(P[r.p_n2w], r.g2, r.cout, st)); RC(k_copy_f32(P[r.p_n2b], r.be2, r.cout, st));
+  if (r.tproj_off >= 0) {
+    RC(k_transpose_f32(P[r.p_mlp_w], r.cout, h->D, h->tproj_wt, h->tproj_total, r.tproj_off, st));
+    RC(k_copy_f32(P[r.p_mlp_b], h->tproj_b + r.tproj_off, r.cout, st));
+  }
+  return 0;
+}
+int pack_attn(ldm_unet* h, AttnW& a, const float* const* P, cudaStream_t st) {
+  const int dt = h->d.dtype;
+  RC(k_pack_conv_weight(P[a.p_qkv], 3 * HIDDEN, a.dim, 1, nullptr, 0, a.wqkv, dt, st));
+  RC(k_pack_conv_weight(P[a.p_ow], a.dim, HIDDEN, 1, nullptr, 0, a.wout, dt, st));
+  RC(k_copy_f32(P[a.p_ob], a.bout, a.dim, st));
+  if (a.linear) { RC(k_copy_f32(P[a.p_ogw], a.og, a.dim, st)); RC(k_copy_f32(P[a.p_ogb], a.ob, a.dim, st)); }
+  RC(k_copy_f32(P[a.p_nw], a.ng, a.dim, st)); RC(k_copy_f32(P[a.p_nb], a.nb, a.dim, st));
+  return 0;
+}
+}  // namespace
+
+extern "C" int ldm_unet_load_params(ldm_unet* h, const float* const* P, int n_params, void* stream) {
+  LDM_REQUIRE(h && P, "ldm_unet_load_params: null argument");
+  LDM_REQUIRE(n_params == (int)h->params.size(), "state_dict has %d tensors, this UNet needs %d", n_params, (int)h->params.size());
+  for (int i = 0; i < n_params; ++i) LDM_REQUIRE(P[i] != nullptr, "parameter %s is null", h->params[i].name.c_str());
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = h->D;
+  if (h->d.with_time_emb) {
+    RC(k_transpose_f32(P[h->p_t1w], D, D / 4, h->w1t, D, 0, st));
+    RC(k_copy_f32(P[h->p_t1b], h->b1, D, st));
+    RC(k_transpose_f32(P[h->p_t3w], D, D, h->w3t, D, 0, st));
+    RC(k_copy_f32(P[h->p_t3b], h->b3, D, st));
+    if (h->p_label >= 0) RC(k_copy_f32(P[h->p_label], h->label, (int64_t)h->d.num_classes * D, st));
+  }
+  RC(k_pack_initial_weight(P[h->p_iw], h->d.channels, h->d.in_channels, h->init_w, st));
+  RC(k_copy_f32(P[h->p_ib], h->init_b, h->d.channels, st));
+  RC(k_copy_f32(P[h->p_fw], h->fin_w, (int64_t)h->d.out_channels * h->d.channels, st));
+  RC(k_copy_f32(P[h->p_fb], h->fin_b, h->d.out_channels, st));
+  for (auto& r : h->enc_res) RC(pack_res(h, r, P, st));
+  for (auto& a : h->enc_attn) RC(pack_attn(h, a, P, st));
+  RC(pack_res(h, h->bott1, P, st)); RC(pack_attn(h, h->bott_attn, P, st)); RC(pack_res(h, h->bott2, P, st));
+  for (auto& r : h->dec_res) RC(pack_res(h, r, P, st));
+  for (auto& a : h->dec_attn) RC(pack_attn(h, a, P, st));
+  for (auto& u : h->ups) {
+    RC(k_pack_convT_weight(P[u.p_w], u.cin, u.cout, u.w, h->d.dtype, st));
+    RC(k_copy_f32(P[u.p_b], u.b, u.cout, st));
+  }
+  RC(pack_res(h, h->final_res, P, st));
+  h->loaded = true;
+  return 0;
+}
+
+extern "C" int64_t ldm_unet_workspace_bytes(const ldm_unet* h, int batch) {
+  if (!h || batch < 0) return -1;
+  return make_plan(h, batch > 0 ? batch : 1).total;
+}
+
+extern "C" int ldm_unet_set_tap(ldm_unet* h, const char* name, float* out_nchw, int64_t out_numel) {
+  LDM_REQUIRE(h, "ldm_unet_set_tap: null handle");
+  h->tap.name = name ? name : "";
+  h->tap.out = out_nchw;
+  h->tap.numel = out_numel;
+  return 0;
+}
+
+namespace {
+
+struct Fwd {
+  ldm_unet* h;
+  cudaStream_t st;
+  int B, dt, es, impl;
+  uint8_t* ws;
+  Plan plan;
+  const float* tproj;
+  void* s(int i) { return ws + plan.s[i]; }
+  void* gnws() { return ws + plan.gnws; }
+
+  int tap(const char* name, const void* x, int ld, int C, int R) {
+    if (h->tap.out && h->tap.name == name) {
+      LDM_REQUIRE(h->tap.numel == (int64_t)B * C * R * R, "tap %s holds %lld elements, buffer has %lld", name,
+                  (long long)B * C * R * R, (long long)h->tap.numel);
+      return k_nhwc_to_nchw(x, ld, h->tap.out, B, C, R * R, dt, st);
+    }
+    return 0;
+  }
+  int gn(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* g, const float* b, int R,
+         int C, int groups, int silu) {
+    return k_group_norm(x, ldx, y, ldy, res, ldres, g, b, B, R * R, C, groups, GN_EPS, silu, dt, gnws(), st);
+  }
+  int conv(const void* x, int ldx, int cin, const void* x2, int ldx2, int cin2, const void* w, const float* bias,
+           const float* rowvec, int ldrv, const void* res, int ldres, void* y, int ldy, int cout, int R, int ksize,
+           int up2 = 0) {
+    ConvArgs a;
+    a.x = x; a.ldx = ldx; a.cin = cin; a.x2 = x2; a.ldx2 = ldx2; a.cin2 = cin2; a.w = w; a.bias = bias;
+    a.rowvec = rowvec; a.ld_rowvec = ldrv; a.res = res; a.ldres = ldres; a.y = y; a.ldy = ldy; a.cout = cout;
+    a.batch = B; a.height = R; a.width = R; a.ksize = ksize; a.up2 = up2; a.dtype = dt;
+    return k_conv(a, impl, st);
+  }
+  // ResNetBlock  src/UNet.py:85-99.  x must not alias s0/s1/out.
+  int resblock(const ResW& r, const void* x, int ldx, void* out, int ldo, int R, bool use_t) {
+    RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
+    const float* rv = (use_t && r.tproj_off >= 0) ? tproj + r.tproj_off : nullptr;
+    RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, rv, h->tproj_total, nullptr, 0, s(1), r.cout, r.cout, R, 3));
+    RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1));
+    if (r.has_sc)  // 1x1 shortcut conv K-concatenated into the second 3x3 GEMM
+      RC(conv(s(0), r.cout, r.cout, x, ldx, r.cin, r.w2, r.b2, nullptr, 0, nullptr, 0, out, ldo, r.cout, R, 3));
+    else           // identity shortcut added in the epilogue
+      RC(conv(s(0), r.cout, r.cout, nullptr, 0, 0, r.w2, r.b2, nullptr, 0, x, ldx, out, ldo, r.cout, R, 3));
+    return 0;
+  }
+  // Residual(PreNorm(dim, LinearAttention | Attention))  src/UNet.py:14-20,102-164.  d must not alias s0/s1/out.
+  int attn_block(const AttnW& a, const void* d, int ldd, void* out, int ldo, int R) {
+    void* qkv = ws + plan.qkv;
+    RC(gn(d, ldd, s(0), a.dim, nullptr, 0, a.ng, a.nb, R, a.dim, 1, 0));
+    RC(conv(s(0), a.dim, a.dim, nullptr, 0, 0, a.wqkv, nullptr, nullptr, 0, nullptr, 0, qkv, 3 * HIDDEN, 3 * HIDDEN, R, 1));
+    if (a.linear) {
+      RC(k_linear_attention(qkv, s(0), B, R * R, dt, st));
+      RC(conv(s(0), HIDDEN, HIDDEN, nullptr, 0, 0, a.wout, a.bout, nullptr, 0, nullptr, 0, s(1), a.dim, a.dim, R, 1));
+      RC(gn(s(1), a.dim, out, ldo, d, ldd, a.og, a.ob, R, a.dim, 1, 0));  // x + GroupNorm(1,C)(to_out(...))
+    } else {
+      RC(k_attention(qkv, s(0), B, R * R, dt, st));
+      RC(conv(s(0), HIDDEN, HIDDEN, nullptr, 0, 0, a.wout, a.bout, nullptr, 0, d, ldd, out, ldo, a.dim, R, 1));
+    }
+    return 0;
+  }
+};
+
+}  // namespace
+
+extern "C" int ldm_unet_forward(ldm_unet* h, const float* x, const int64_t* t, const int64_t* t_dev_scalar,
+                                const int64_t* y, int y_len, int y_rows, int batch, float* out, void* workspace,
+                                int64_t workspace_bytes, void* stream) {
+  return ldm_unet_forward_ex(h, x, batch, t, t_dev_scalar, y, y_len, y_rows, batch, out, workspace, workspace_bytes,
+                             stream);
+}
+
+int ldm_unet_forward_ex(ldm_unet* h, const float* x, int x_batch, const int64_t* t, const int64_t* t_dev_scalar,
+                        const int64_t* y, int y_len, int y_rows, int batch, float* out, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
+  LDM_REQUIRE(h && x && out, "ldm_unet_forward: null argument");
+  LDM_REQUIRE(x_batch > 0 && batch % x_batch == 0, "x_batch %d must divide batch %d", x_batch, batch);
+  LDM_REQUIRE(h->loaded, "ldm_unet_forward: parameters were never loaded (ldm_unet_load_params)");
+  LDM_REQUIRE(batch >= 0, "negative batch");
+  if (batch == 0) return 0;
+  LDM_REQUIRE(y_len == 0 || y_len == 1 || y_len == batch || (y_rows > 0 && y_len == y_rows),
+              "labels: y has %d entries for a batch of %d (the reference broadcasts only length 1, src/UNet.py:375-376)",
+              y_len, batch);
+  LDM_REQUIRE(!(y && y_len > 0) || h->p_label >= 0, "labels given but the UNet has num_classes=None");
+  LDM_REQUIRE(!h->d.with_time_emb || t || t_dev_scalar, "t is required");
+  Fwd f;
+  f.h = h; f.st = (cudaStream_t)stream; f.B = batch; f.dt = h->d.dtype; f.es = h->es(); f.impl = h->d.conv_impl;
+  f.plan = make_plan(h, batch);
+  LDM_REQUIRE(workspace && workspace_bytes >= f.plan.total, "workspace too small: %lld < %lld bytes",
+              (long long)workspace_bytes, (long long)f.plan.total);
+  LDM_REQUIRE(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
+  f.ws = (uint8_t*)workspace;
+  const int L = h->L, S = h->d.image_size;
+  float* temb = (float*)(f.ws + f.plan.temb);
+  float* tproj = (float*)(f.ws + f.plan.tproj);
+  f.tproj = tproj;
+  if (h->d.with_time_emb) {
+    RC(k_time_embed(t, t_dev_scalar, (y && y_len > 0) ? y : nullptr, y_len, y_rows > 0 ? y_rows : batch, h->w1t, h->b1,
+                    h->w3t, h->b3, h->label, temb, batch, h->D, f.st));
+    if (h->tap.out && h->tap.name == "temb") {
+      LDM_REQUIRE(h->tap.numel == (int64_t)batch * h->D, "tap temb size mismatch");
+      RC(k_copy_f32(temb, h->tap.out, (int64_t)batch * h->D, f.st));
+    }
+    if (h->tproj_total > 0) RC(k_time_proj(temb, h->tproj_wt, h->tproj_b, tproj, batch, h->D, h->tproj_total, f.st));
+  }
+  // initial conv: fp32 NCHW -> NHWC
+  void* hin0 = f.ws + f.plan.hin[0];
+  RC(k_initial_conv(x, x_batch, h->init_w, h->init_b, hin0, batch, h->d.in_channels, h->dims[0], S, S, f.dt, f.st));
+  RC(f.tap("initial", hin0, h->dims[0], h->dims[0], S));
+  // ---- encoder  src/UNet.py:200-209
+  for (int i = 0; i < L; ++i) {
+    const int R = S >> i, cout = h->dims[i + 1];
+    const int j = L - 1 - i;                          // decoder level consuming this skip
+    const int catc = h->dims[i] + h->dims[i + 1];     // = up channels (dims[i]) + skip channels (dims[i+1])
+    uint8_t* cat = f.ws + f.plan.cat[j];
+    void* skip = cat + (int64_t)h->dims[i] * f.es;    // skip occupies channels [dims[i], catc)
+    void* hin = f.ws + f.plan.hin[i];
+    RC(f.resblock(h->enc_res[i], hin, h->dims[i], f.s(2), cout, R, true));
+    RC(f.tap(("enc" + std::to_string(i) + ".res").c_str(), f.s(2), cout, cout, R));
+    RC(f.attn_block(h->enc_attn[i], f.s(2), cout, skip, catc, R));
+    RC(f.tap(("enc" + std::to_string(i) + ".attn").c_str(), skip, catc, cout, R));
+    RC(k_maxpool2(skip, catc, f.ws + f.plan.hin[i + 1], cout, batch, R, R, cout, f.dt, f.st));
+  }
+  // ---- bottleneck (no time embedding)  src/UNet.py:287-290
+  {
+    const int R = S >> L, C = h->dims[L];
+    RC(f.resblock(h->bott1, f.ws + f.plan.hin[L], C, f.s(2), C, R, false));
+    RC(f.attn_block(h->bott_attn, f.s(2), C, f.s(3), C, R));
+    RC(f.resblock(h->bott2, f.s(3), C, f.s(2), C, R, false));
+    RC(f.tap("bottleneck", f.s(2), C, C, R));
+  }
+  // ---- decoder  src/UNet.py:240-248
+  const void* z = f.s(2);
+  for (int j = 0; j < L; ++j) {
+    const int i = L - 1 - j;
+    const int Rin = S >> (i + 1), R = S >> i;
+    const UpW& u = h->ups[j];
+    const int catc = u.cout + u.cin;  // up(rd[j+1]) + skip(rd[j])
+    uint8_t* cat = f.ws + f.plan.cat[j];
+    // ConvTranspose2d(k2,s2) as a [M, 4*Cout] GEMM scattered into channels [0, Cout) of the concat buffer
+    {
+      ConvArgs a;
+      a.x = z; a.ldx = u.cin; a.cin = u.cin; a.x2 = nullptr; a.ldx2 = 0; a.cin2 = 0; a.w = u.w; a.bias = u.b;
+      a.rowvec = nullptr; a.ld_rowvec = 0; a.res = nullptr; a.ldres = 0; a.y = cat; a.ldy = catc; a.cout = 4 * u.cout;
+      a.batch = batch; a.height = Rin; a.width = Rin; a.ksize = 1; a.up2 = 1; a.dtype = f.dt;
+      RC(k_conv(a, f.impl, f.st));
+    }
+    RC(f.resblock(h->dec_res[j], cat, catc, f.s(2), u.cout, R, true));
+    RC(f.attn_block(h->dec_attn[j], f.s(2), u.cout, f.s(3), u.cout, R));
+    RC(f.tap(("dec" + std::to_string(j)).c_str(), f.s(3), u.cout, u.cout, R));
+    z = f.s(3);
+  }
+  // ---- final  src/UNet.py:345-348,387
+  RC(f.resblock(h->final_res, z, h->dims[0], f.s(2), h->dims[0], S, false));
+  RC(f.tap("final.res", f.s(2), h->dims[0], h->dims[0], S));
+  RC(k_final_conv(f.s(2), h->dims[0], h->fin_w, h->fin_b, out, batch, h->dims[0], h->d.out_channels, S * S, f.dt, f.st));
+  return 0;
+}
+
+int ldm_unet_in_channels(const ldm_unet* h) { return h->d.in_channels; }
+int ldm_unet_out_channels(const ldm_unet* h) { return h->d.out_channels; }
+int ldm_unet_image_size(const ldm_unet* h) { return h->d.image_size; }
