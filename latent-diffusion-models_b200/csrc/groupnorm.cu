@@ -155,12 +155,13 @@ static int gn_launch(const void* x, int ldx, void* y, int ldy, const void* res, 
   if (k < 1) k = 1;
   if (k > hw) k = hw;
   const int threads = (cpp * k + 31) / 32 * 32;
-  // enough slabs to fill 148 SMs a few times over, at least 16 pixels per thread-lane slab
-  int splits = (int)ceil_div64(148 * 4, batch);
-  int max_splits = hw / (k * 4) > 0 ? hw / (k * 4) : 1;
-  if (splits > max_splits) splits = max_splits;
+  // Slab count depends only on the per-sample geometry (never on the batch), so a sample's reduction
+  // order -- and therefore its bits -- is the same however the batch is sharded across GPUs.
+  int splits = hw / (k * 4);
+  if (splits > 8) splits = 8;
   if (splits > GN_MAX_SPLITS) splits = GN_MAX_SPLITS;
   if (splits < 1) splits = 1;
+  (void)batch;
   float* part = (float*)workspace;
   gn_stats_kernel<T><<<dim3(splits, batch), threads, threads * 3 * sizeof(float), st>>>(
       (const T*)x, ldx, part, hw, channels, groups, splits, k);

@@ -132,10 +132,12 @@ class Diffusion(nn.Module):
     @torch.no_grad()
     def sample(self, eps_model, classes, shape, device, cfg_scale=3, *, x_T: Optional[torch.Tensor] = None,
                noise: Optional[torch.Tensor] = None, seed: Optional[int] = None, sample_offset: int = 0,
-               use_graph: bool = True, return_device: bool = False):
+               use_graph: bool = True, return_device: bool = False, first_step: Optional[int] = None,
+               num_steps: Optional[int] = None):
         """Same call as the reference; the extra keyword-only arguments are for parity and sharding:
         ``x_T`` fixes the initial noise, ``noise`` ([T,B,C,S,S], indexed by t) fixes every step's z,
-        ``seed``/``sample_offset`` key the in-kernel Philox streams by global sample index."""
+        ``seed``/``sample_offset`` key the in-kernel Philox streams by global sample index;
+        ``first_step``/``num_steps`` run only timesteps first_step, first_step-1, ... (chunked trajectories)."""
         dev = torch.device(device)
         if dev.type != "cuda":
             raise _lib.LdmError("ldm_b200.Diffusion.sample needs a CUDA device (no CPU fallback)")
@@ -184,8 +186,11 @@ class Diffusion(nn.Module):
             coef = self._coef_table(dev)
             before = _lib.launch_count()
             _lib.check(lib.ldm_sampler_run(ent["s"], xbuf.data_ptr(), x_init, ybuf.data_ptr() if y is not None else None,
-                                           coef.data_ptr(), _lib.ptr(z), seed, sample_offset, self.n_steps - 1,
-                                           self.n_steps, ws.data_ptr() + off, ent["nbytes"], _lib.stream_ptr()))
+                                           coef.data_ptr(), _lib.ptr(z), seed, sample_offset,
+                                           self.n_steps - 1 if first_step is None else int(first_step),
+                                           (self.n_steps if first_step is None else int(first_step) + 1)
+                                           if num_steps is None else int(num_steps),
+                                           ws.data_ptr() + off, ent["nbytes"], _lib.stream_ptr()))
             self.last_launches = _lib.launch_count() - before
             if return_device:
                 return xbuf.clone()

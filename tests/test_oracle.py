@@ -1,0 +1,147 @@
+"""CPU: the oracle restatement against the golden vectors produced by the unmodified reference
+(oracle/make_golden.py), and against the live reference when /root/reference is mounted."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REFERENCE, golden, rel_l2
+import oracle
+from oracle import unet_oracle as U
+from oracle import ddpm_oracle as D
+
+T = torch.from_numpy
+
+
+def _sha(sd):
+    h = hashlib.sha256()
+    for k in sd:
+        h.update(k.encode())
+        h.update(sd[k].contiguous().numpy().tobytes())
+    return h.digest()
+
+
+@pytest.mark.parametrize("tag,cin", [("cifar", 3), ("mnist", 1)])
+def test_unet_matches_reference_golden(tag, cin):
+    g = golden(f"g1_unet_{tag}.npz")
+    sd = oracle.init_state_dict(int(g["weight_seed"]), cin, cin, 64, (1, 2, 4, 8), True, 10)
+    assert len(sd) == 200
+    assert _sha(sd) == bytes(g["weight_sha256"]), "default init no longer reproduces the reference's weights"
+    x, t, y = T(g["x"]), T(g["t"]), T(g["y"])
+    with torch.no_grad():
+        assert rel_l2(U.unet_forward(sd, x, t, y), T(g["eps_cond"])) < 2e-6
+        assert rel_l2(U.unet_forward(sd, x, t, None), T(g["eps_uncond"])) < 2e-6
+        assert rel_l2(U.unet_forward(sd, x, t, torch.tensor([3])), T(g["eps_bcast3"])) < 2e-6
+
+
+def test_unet_fp64_vs_fp32_floor():
+    g = golden("g1_unet_cifar.npz")
+    sd = oracle.init_state_dict(0, 3, 3, 64, (1, 2, 4, 8), True, 10)
+    sd64 = U.cast_state_dict(sd, torch.float64)
+    with torch.no_grad():
+        out = U.unet_forward(sd64, T(g["x"]).double(), T(g["t"]), T(g["y"]))
+    assert rel_l2(out, T(g["eps_cond"])) < 5e-6  # fp32 vs fp64 floor 2.4e-7
+
+
+@pytest.mark.parametrize("name,fn,prefix", [
+    ("linattn_64_n1024", U.linear_attention, ""),
+    ("linattn_128_n16", U.linear_attention, ""),
+    ("attn_512_n4", U.attention, ""),
+    ("attn_64_n64", U.attention, ""),
+])
+def test_attention_submodules(name, fn, prefix):
+    g = golden(f"g4_{name}.npz")
+    sd = {"p." + k[3:]: T(g[k]) for k in g.files if k.startswith("w::")}
+    with torch.no_grad():
+        out = fn(sd, "p", T(g["in0"]))
+    assert rel_l2(out, T(g["out"])) < 2e-6
+
+
+def test_block_and_resblocks():
+    g = golden("g4_block_64_64_r8.npz")
+    sd = {"p." + k[3:]: T(g[k]) for k in g.files if k.startswith("w::")}
+    with torch.no_grad():
+        assert rel_l2(U.block(sd, "p", T(g["in0"])), T(g["out"])) < 2e-6
+    g = golden("g4_resblock_64_128_t_r8.npz")
+    sd = {"p." + k[3:]: T(g[k]) for k in g.files if k.startswith("w::")}
+    with torch.no_grad():
+        assert rel_l2(U.resnet_block(sd, "p", T(g["in0"]), T(g["in1"])), T(g["out"])) < 2e-6
+    g = golden("g4_resblock_64_64_not_r16.npz")
+    sd = {"p." + k[3:]: T(g[k]) for k in g.files if k.startswith("w::")}
+    with torch.no_grad():
+        assert rel_l2(U.resnet_block(sd, "p", T(g["in0"]), None), T(g["out"])) < 2e-6
+
+
+def test_time_embedding():
+    g = golden("g4_time_embedding_256.npz")
+    sd = {"time_emb." + k[3:]: T(g[k]) for k in g.files if k.startswith("w::")}
+    with torch.no_grad():
+        out = U.time_embedding(sd, T(g["in0"]), torch.float32)
+    assert rel_l2(out, T(g["out"])) < 2e-6
+
+
+@pytest.mark.parametrize("n_steps", [1000, 400])
+def test_schedule_and_p_sample(n_steps):
+    g = golden(f"g2_p_sample_T{n_steps}.npz")
+    s = D.make_schedule(n_steps)
+    assert torch.equal(s["beta"], T(g["beta"])) and torch.equal(s["alpha_bar"], T(g["alpha_bar"]))
+    xt, eps = T(g["xt"]), T(g["eps"])
+    for i, step in enumerate(g["steps"]):
+        t = torch.full((4,), int(step), dtype=torch.long)
+        out = D.p_sample(s, xt, t, eps, T(g["noise"][i]))
+        assert torch.allclose(out, T(g["out"][i]), rtol=1e-6, atol=1e-6), f"t={step}"
+    if n_steps == 1000:
+        assert abs(float(s["alpha_bar"][-1]) - 4.036e-5) < 1e-7
+
+
+def test_q_sample_and_forward():
+    g = golden("g3_q_sample.npz")
+    s = D.make_schedule(1000)
+    xt = D.q_sample(s, T(g["x0"]), T(g["t"]), T(g["noise"]))
+    assert torch.allclose(xt, T(g["xt"]), rtol=1e-6, atol=1e-6)
+
+
+def test_trajectory_statistics_short():
+    """Teacher-forced check of the oracle loop on the reference's trajectory checkpoints (3 steps only:
+    a full 1000-step CPU trajectory is minutes; the GPU test runs all of it)."""
+    g = golden("g6_trajectory_T1000.npz")
+    sd = oracle.init_state_dict(int(g["weight_seed"]), 3, 3, 64, (1, 2, 4, 8), True, 10)
+    s = D.make_schedule(1000)
+    torch.manual_seed(int(g["noise_seed"]))
+    x_T = torch.randn(2, 3, 32, 32)
+    assert torch.equal(x_T, T(g["x_at_999"])), "x_T draw no longer matches the reference's RNG order"
+    model = lambda x, t, y: U.unet_forward(sd, x, t, y)
+    x = x_T
+    with torch.no_grad():
+        for step in (999, 998):
+            t = torch.full((2,), step, dtype=torch.long)
+            eps = D.cfg_combine(model(x, t, torch.tensor([3])), model(x, t, None), 3.0)
+            z = torch.randn(2, 3, 32, 32)
+            x = D.p_sample(s, x, t, eps, z)
+            st = g["stats"][step - 1]
+            assert abs(float(x.mean()) - st[0]) < 1e-4 * max(1.0, abs(st[1]))
+            assert abs(float(x.std()) - st[1]) < 1e-4 * st[1]
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not mounted")
+def test_against_live_reference():
+    sys.path.insert(0, REFERENCE)
+    try:
+        from src.UNet import UNet as RefUNet
+    finally:
+        sys.path.remove(REFERENCE)
+    torch.manual_seed(11)
+    ref = RefUNet(3, 3, 64, [1, 2], True, 10).eval()   # 2-level variant, cheap
+    sd = {k: v.detach() for k, v in ref.state_dict().items()}
+    mine = oracle.init_state_dict(11, 3, 3, 64, (1, 2), True, 10)
+    assert all(torch.equal(mine[k], sd[k]) for k in sd)
+    x = torch.randn(2, 3, 16, 16)
+    t = torch.tensor([5, 700])
+    y = torch.tensor([1, 9])
+    with torch.no_grad():
+        assert rel_l2(U.unet_forward(sd, x, t, y), ref(x, t, y)) < 2e-6
+    for m in [k for k in list(sys.modules) if k == "src" or k.startswith("src.")]:
+        del sys.modules[m]
