@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Headline benchmark: CIFAR-10-shaped DDPM sampling throughput (images/sec), 1000-step reverse process with
+classifier-free guidance, batch 256 per GPU (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one full pass of the hot path over one batch: ``Diffusion.sample(model, classes, (B,3,32,32), device,
+cfg_scale=3)`` = T x {one 2B-row UNet eps-prediction (cond + uncond), fused CFG + p_sample update}.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  value        images/sec, inputs resident in HBM (x_T drawn on the device, result left on the device)
+  e2e          the same call through the public API with HOST inputs: x_T from pinned host memory, host labels,
+               result copied back to the host (the reference's ``xt.detach().cpu()``), inside the timed region
+  roofline     dominant kernel family (tcgen05 implicit-GEMM convolutions): algorithmic FLOPs / CUDA-event time of
+               every conv launch of one 2B-row UNet pass, against MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle (a restatement of the reference's PyTorch code, oracle/) on the host cores, bounded sample
+  clocks       nvidia-smi samples taken during the timed region
+
+``--impl reference`` times the reference algorithm on the host CPU (the oracle port; the reference itself is a
+Python checkout that does not exist on the GPU box) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+UNET_GFLOP_PER_IMAGE = 1.5132  # one UNet forward, CIFAR config (2xMAC, FlopCounterMode on the reference)
+METRIC = "cifar10_ddpm_sampling_images_per_sec"
+UNIT = "images/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sampling_rate(batch: int, timesteps: int, n_steps: int, cfg_scale: float, warmup: int = 1):
+    """images/sec of the CPU oracle: `timesteps` reverse steps at `batch` images are timed and extrapolated to the
+    full n_steps-step trajectory (every step costs the same: 2 UNet passes + the p_sample update)."""
+    import torch
+    import oracle
+    from oracle import unet_oracle as U, ddpm_oracle as D
+    torch.manual_seed(42)
+    sd = oracle.init_state_dict(42, 3, 3, 64, (1, 2, 4, 8), True, 10)
+    sched = D.make_schedule(n_steps)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(batch, 3, 32, 32, generator=g)
+    cls = torch.tensor([3])
+
+    def one_step(x, step):
+        t = torch.full((batch,), step, dtype=torch.long)
+        eps = U.unet_forward(sd, x, t, cls)
+        if cfg_scale > 0:
+            eps = D.cfg_combine(eps, U.unet_forward(sd, x, t, None), cfg_scale)
+        return D.p_sample(sched, x, t, eps, torch.randn(x.shape, generator=g))
+
+    with torch.no_grad():
+        for i in range(warmup):
+            x = one_step(x, n_steps - 1 - i)
+        t0 = time.perf_counter()
+        for i in range(timesteps):
+            x = one_step(x, n_steps - 1 - warmup - i)
+        dt = time.perf_counter() - t0
+    per_step = dt / timesteps
+    return batch / (per_step * n_steps), per_step, torch.get_num_threads()
+
+
+def run_reference(args):
+    """The reference algorithm on the host CPU (oracle port), bounded sample; rank 0 only."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    b, ts = args.cpu_batch, args.cpu_timesteps
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, per_step, cores = cpu_sampling_rate(b, ts, args.n_steps, args.cfg_scale, warmup=1 if i == 0 else 0)
+        if i >= args.warmup:
+            vals.append((v, per_step))
+    v = statistics.mean(x[0] for x in vals)
+    per_step = statistics.mean(x[1] for x in vals)
+    sample = (f"{ts} of {args.n_steps} reverse timesteps at batch {b} (cfg_scale {args.cfg_scale}: 2 UNet passes + p_sample "
+              f"per timestep), extrapolated x{args.n_steps}/{ts}; fp32, torch CPU kernels, {cores} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * b / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(args, args.batch, 1), bounded_sample=sample),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch, world):
+    return {"workload": f"pixel_diffusion_model_cifar10: Diffusion.sample, 3x32x32, T={args.n_steps}, cfg_scale={args.cfg_scale}, "
+                        f"UNet(64,[1,2,4,8],num_classes=10), batch {batch} per GPU",
+            "batch_per_gpu": batch, "global_batch": batch * world, "n_steps": args.n_steps, "cfg_scale": args.cfg_scale,
+            "image": [3, 32, 32], "parallelism": f"batch-sharded x{world}, no collectives",
+            "weights": "random init, torch.manual_seed(42)"}
+
+
+def run_ours(args):
+    import torch
+    import ldm_b200
+    from ldm_b200 import _lib, dist as ldist
+    import torch.distributed as tdist
+
+    rank, local_rank, world = ldist.init_from_env("nccl")
+    if world != args.gpus and rank == 0:
+        sys.stderr.write(f"bench: WORLD_SIZE={world} but --gpus {args.gpus}; using WORLD_SIZE\n")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    B, T, cfg = args.batch, args.n_steps, args.cfg_scale
+    shape = (B, 3, 32, 32)
+    torch.manual_seed(42)
+    model = ldm_b200.UNet(3, 3, 64, (1, 2, 4, 8), True, 10, dtype=args.dtype).to(dev)
+    model.requires_grad_(False)
+    diffusion = ldm_b200.Diffusion(T, dev)
+    classes_host = torch.tensor([3])                       # length-1 label, broadcast (main.py:318)
+    classes_dev = classes_host.to(dev)
+    g = torch.Generator().manual_seed(7 + rank)
+    x_T_host = torch.randn(shape, generator=g).pin_memory()
+    offset = ldist.shard_offset(B, rank)
+    stream = torch.cuda.Stream(dev)
+
+    def device_step(i):
+        return diffusion.sample(model, classes_dev, shape, dev, cfg_scale=cfg, seed=1234 + i, sample_offset=offset,
+                                return_device=True)
+
+    def e2e_step():
+        return diffusion.sample(model, classes_host, shape, dev, cfg_scale=cfg, x_T=x_T_host, seed=99,
+                                sample_offset=offset)
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            device_step(-1 - i)
+        torch.cuda.synchronize(dev)
+        clocks = ClockSampler(local_rank).start() if rank == 0 else None
+        barrier()
+        torch.cuda.synchronize(dev)
+        launches0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            out = device_step(i)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        barrier()
+        launches = _lib.launch_count() - launches0
+        ms_total = ldist.max_over_ranks(e0.elapsed_time(e1), dev)
+        clock_rec = clocks.stop() if clocks else None
+        assert bool(torch.isfinite(out).all()), "sampler produced non-finite images"
+
+        # ---- end to end through the public API with host buffers
+        e2e_steps = max(1, args.e2e_steps)
+        e2e_step()
+        torch.cuda.synchronize(dev)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        s0.record(stream)
+        for _ in range(e2e_steps):
+            res = e2e_step()
+        s1.record(stream)
+        torch.cuda.synchronize(dev)
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        assert res.device.type == "cpu" and tuple(res.shape) == shape
+        e2e_ms = ldist.max_over_ranks(max(s0.elapsed_time(s1), wall_ms), dev)
+
+        # ---- roofline leg: every launch of one 2B-row UNet pass timed with CUDA events on this stream
+        prof = None
+        if rank == 0:
+            rows = 2 * B if cfg > 0 else B
+            xx = torch.randn(rows, 3, 32, 32, device=dev)
+            tt = torch.full((rows,), T // 2, dtype=torch.long, device=dev)
+            model.profile(xx, tt, classes_dev, y_rows=B)
+            acc = {}
+            reps = 3
+            for _ in range(reps):
+                for k, v in model.profile(xx, tt, classes_dev, y_rows=B).items():
+                    a = acc.setdefault(k, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+                    for kk in a:
+                        a[kk] += v[kk]
+            prof = {k: {kk: vv / reps for kk, vv in v.items()} for k, v in acc.items()}
+
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    images = B * world * args.steps
+    value = images / (ms_total / 1e3)
+    e2e_value = B * world * e2e_steps / (e2e_ms / 1e3)
+    passes = 2 if cfg > 0 else 1
+    unet_tflops = images * T * passes * UNET_GFLOP_PER_IMAGE / 1e3 / (ms_total / 1e3)
+    conv_name = "conv_tc" if "conv_tc" in prof else "conv_ffma"
+    conv = prof[conv_name]
+    total_ms = sum(v["ms"] for v in prof.values())
+    achieved = conv["flops"] / (conv["ms"] / 1e3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")   # written from the committed `ncu --set full` capture
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv: 3x3, 1x1, conv-transpose)" if conv_name == "conv_tc" else "conv_simt",
+        "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["bf16_tflops_sustained"], "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
+        "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
+        "traffic": traffic,
+        "launches_per_unet_pass": conv["launches"], "flops_per_launch_avg": conv["flops"] / conv["launches"],
+        "avg_launch_ms": conv["ms"] / conv["launches"], "share_of_unet_pass": conv["ms"] / total_ms,
+        "families": {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
+                         "tflops": v["flops"] / (v["ms"] / 1e3) / 1e12 if v["ms"] > 0 else 0.0,
+                         "gbs": v["bytes"] / (v["ms"] / 1e3) / 1e9 if v["ms"] > 0 else 0.0,
+                         "share": v["ms"] / total_ms} for k, v in prof.items()},
+        "whole_step": {"unet_tflops": unet_tflops, "frac_of_sustained_peak": unet_tflops / peaks["bf16_tflops_sustained"],
+                       "gflop_per_image_per_unet_pass": UNET_GFLOP_PER_IMAGE},
+    }
+    cpu = None
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        v, per_step, cores = cpu_sampling_rate(args.cpu_batch, args.cpu_timesteps, T, cfg)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_timesteps} of {T} reverse timesteps at batch {args.cpu_batch} after 1 warm-up timestep "
+                         f"({per_step:.2f} s per timestep), extrapolated to the full trajectory; oracle/ (torch CPU fp32)"}
+    act_mb = (2 * B if cfg > 0 else B) * 64 * 32 * 32 * 2 / 1e6
+    config = workload_config(args, B, world)
+    config["l2"] = (f"no flush needed: every timestep streams ~40.7 MB of bf16 weights plus {act_mb:.0f} MB per full-resolution "
+                    f"activation tensor (working set >> 126 MB L2)")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic", "config": config,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_T_host.numel() * 4 + classes_host.numel() * 8,
+                "d2h_bytes_per_step": x_T_host.numel() * 4, "steps": e2e_steps},
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_rec,
+        "unet_tflops": unet_tflops,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per sampling call")
+    ap.add_argument("--n-steps", type=int, default=1000, help="diffusion timesteps T")
+    ap.add_argument("--cfg-scale", type=float, default=3.0)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--cpu-timesteps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

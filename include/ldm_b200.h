@@ -93,6 +93,32 @@ int ldm_unet_forward(ldm_unet* h, const float* x, const int64_t* t, const int64_
  * names: "initial", "enc{i}.res", "enc{i}.attn", "bottleneck", "dec{i}", "final.res", "temb". */
 int ldm_unet_set_tap(ldm_unet* h, const char* name, float* out_nchw, int64_t out_numel);
 
+/* Measurement aid (bench.py's roofline leg; no reference counterpart): one forward with a CUDA-event pair
+ * around every kernel launch on `stream`, summed per kernel family.  flops / bytes are the ALGORITHMIC work of
+ * the launches (conv: 2*M*N*K; memory-bound kernels: one read + one write of each live tensor).
+ * Synchronises `stream` before returning; not capturable. */
+enum ldm_kernel_family {
+  LDM_FAM_CONV_TC = 0,          /* tcgen05 implicit-GEMM convolutions (3x3, 1x1, conv-transpose)  */
+  LDM_FAM_CONV_FFMA = 1,        /* fp32 / forced-FFMA implicit-GEMM convolutions                  */
+  LDM_FAM_GROUP_NORM = 2,       /* GroupNorm (+SiLU) (+residual)                                  */
+  LDM_FAM_LINEAR_ATTENTION = 3,
+  LDM_FAM_ATTENTION = 4,
+  LDM_FAM_OTHER = 5,            /* time-embedding MLPs, initial/final conv, max-pool              */
+  LDM_FAM_COUNT = 8
+};
+typedef struct ldm_profile_family {
+  double ms;        /* sum of launch durations (CUDA events) */
+  double flops;     /* algorithmic FLOPs of those launches   */
+  double bytes;     /* algorithmic bytes of those launches   */
+  int64_t launches;
+} ldm_profile_family;
+typedef struct ldm_profile {
+  ldm_profile_family family[LDM_FAM_COUNT];
+} ldm_profile;
+int ldm_unet_profile(ldm_unet* h, const float* x, const int64_t* t, const int64_t* y, int y_len, int y_rows,
+                     int batch, float* out, void* workspace, int64_t workspace_bytes, void* stream,
+                     ldm_profile* result);
+
 /* ---- diffusion process: replaces src/DDPM.py --------------------------------------- */
 
 /* q_sample: x_t = sqrt(abar[t_b]) x0 + sqrt(1-abar[t_b]) eps      (src/DDPM.py:46-68)

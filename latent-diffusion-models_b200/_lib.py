@@ -31,6 +31,16 @@ class SamplerDesc(C.Structure):
                 ("y_len", C.c_int32), ("use_graph", C.c_int32)]
 
 
+class ProfileFamily(C.Structure):
+    _fields_ = [("ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double), ("launches", C.c_int64)]
+
+
+class Profile(C.Structure):
+    _fields_ = [("family", ProfileFamily * 8)]
+
+
+FAMILIES = ["conv_tc", "conv_ffma", "group_norm", "linear_attention", "attention", "other"]
+
 # name -> (restype, argtypes); mirrors include/ldm_b200.h one to one
 SIGNATURES = {
     "ldm_abi_version": (C.c_int, []),
@@ -45,6 +55,7 @@ SIGNATURES = {
     "ldm_unet_load_params": (C.c_int, [vp, C.POINTER(vp), C.c_int, vp]),
     "ldm_unet_workspace_bytes": (C.c_int64, [vp, C.c_int]),
     "ldm_unet_forward": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int64, vp]),
+    "ldm_unet_profile": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int64, vp, C.POINTER(Profile)]),
     "ldm_unet_set_tap": (C.c_int, [vp, C.c_char_p, vp, C.c_int64]),
     "ldm_q_sample": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int64, C.c_uint64, C.c_uint64, vp]),
     "ldm_p_sample": (C.c_int, [vp, vp, vp, C.c_float, vp, C.c_int, vp, C.c_int, vp, C.c_uint64, C.c_uint64, vp,

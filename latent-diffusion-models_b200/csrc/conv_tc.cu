@@ -47,7 +47,10 @@ struct TcParams {
   const float* bias;
   const float* rowvec; int ld_rowvec;
   const bf16* res; int ldres;
-  bf16* y; int ldy;
+  bf16* y; int ldy;   // may be null when only the fused projection output is wanted
+  // fused trailing 1x1 projection (the UNet's final_conv.1, src/UNet.py:347): out[b][o][pix] = fin_b[o] +
+  // sum_c fin_w[o][c] * row[c], computed from the fp32 accumulators; requires one N-tile (BLOCK_N == cout)
+  const float* fin_w; const float* fin_b; float* fin_out; int fin_cout;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -288,6 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bf16* rrow = p.res ? p.res + (int64_t)m * p.ldres + cc0 : nullptr;
       const float* rvrow = p.rowvec ? p.rowvec + (int64_t)img * p.ld_rowvec + cc0 : nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+      float fo[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t r[32];
@@ -320,14 +324,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int u = 0; u < 8; ++u) v[j + u] += t8[u];
             }
           }
+          if (p.y) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float t8[8];
+            for (int j = 0; j < 32; j += 8) {
+              float t8[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) t8[u] = v[j + u];
-            store_chunk(yrow + c0 + j, t8);
+              for (int u = 0; u < 8; ++u) t8[u] = v[j + u];
+              store_chunk(yrow + c0 + j, t8);
+            }
+          }
+          if (p.fin_out) {
+            for (int o = 0; o < p.fin_cout; ++o) {
+              const float* wrow = p.fin_w + o * p.cout + c0;
+              float s = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + j));
+                s = fmaf(v[j], w4.x, s); s = fmaf(v[j + 1], w4.y, s);
+                s = fmaf(v[j + 2], w4.z, s); s = fmaf(v[j + 3], w4.w, s);
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (u == o) fo[u] += s;
+            }
           }
         }
+      }
+      if (p.fin_out && valid) {
+        const int pix = m - img * hw;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (u < p.fin_cout) p.fin_out[((int64_t)img * p.fin_cout + u) * hw + pix] = fo[u] + __ldg(p.fin_b + u);
       }
       tc_fence_before();
       __syncwarp();
@@ -410,7 +437,8 @@ int k_conv_tc(const ConvArgs& a, cudaStream_t st) {
   LDM_REQUIRE(a.cout % 64 == 0, "conv_tc: Cout (%d) must be a multiple of 64", a.cout);
   LDM_REQUIRE(a.ldx % 8 == 0 && a.ldy % 8 == 0 && (!a.x2 || a.ldx2 % 8 == 0) && (!a.res || a.ldres % 8 == 0),
               "conv_tc: pixel strides must be multiples of 8 elements");
-  LDM_REQUIRE(((uintptr_t)a.x & 15) == 0 && ((uintptr_t)a.w & 15) == 0 && ((uintptr_t)a.y & 15) == 0,
+  LDM_REQUIRE(((uintptr_t)a.x & 15) == 0 && ((uintptr_t)a.w & 15) == 0 && ((uintptr_t)a.y & 15) == 0 &&
+                  ((uintptr_t)a.fin_w & 15) == 0,
               "conv_tc: pointers must be 16-byte aligned");
   LDM_REQUIRE(!a.up2 || (a.ksize == 1 && !a.x2 && !a.res && !a.rowvec), "conv_tc: up2 epilogue only for plain 1x1 GEMMs");
   const int H = a.height, W = a.width;
@@ -436,11 +464,17 @@ int k_conv_tc(const ConvArgs& a, cudaStream_t st) {
   p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec;
   p.res = (const bf16*)a.res; p.ldres = a.ldres;
   p.y = (bf16*)a.y; p.ldy = a.ldy;
+  p.fin_w = a.fin_w; p.fin_b = a.fin_b; p.fin_out = a.fin_out; p.fin_cout = a.fin_cout;
+  LDM_REQUIRE(!a.fin_out || (a.fin_cout >= 1 && a.fin_cout <= 8 && !a.up2 && (a.cout == 64 || a.cout == 128 || a.cout == 256)),
+              "conv_tc: fused projection needs Cout in {64,128,256} and <= 8 outputs");
+  LDM_REQUIRE(a.y || a.fin_out, "conv_tc: no output requested");
   const int ktot = p.kb_total * BLOCK_K;
 
   // tile-N: the widest of 256/128/64 that divides Cout (and the up2 quadrant) and still yields >= 1 wave
   int block_n = 64;
   const int nlimit = p.cout_real;
+  if (a.fin_out) block_n = a.cout;  // the whole channel row must sit in one accumulator tile
+  else
   for (int bn : {256, 128}) {
     if (a.cout % bn == 0 && nlimit % bn == 0 && (int64_t)p.num_m_tiles * (a.cout / bn) >= g_num_sms) { block_n = bn; break; }
   }

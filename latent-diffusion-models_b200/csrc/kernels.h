@@ -57,7 +57,11 @@ struct ConvArgs {
   const float* bias;                      // [cout_total] or null (indexed by output channel, see `up2`)
   const float* rowvec; int ld_rowvec;     // optional [batch][ld_rowvec] per-sample, per-channel add
   const void* res; int ldres;             // optional residual NHWC (same spatial size, cout channels)
-  void* y; int ldy;                       // output NHWC
+  void* y; int ldy;                       // output NHWC (may be null with fin_out)
+  const float* fin_w = nullptr;           // optional fused trailing 1x1 projection [fin_cout][cout] fp32 ...
+  const float* fin_b = nullptr;           // ... + bias, written as fp32 NCHW [batch][fin_cout][H*W] (tcgen05 path only)
+  float* fin_out = nullptr;
+  int fin_cout = 0;
   int cout;                               // GEMM N (for up2: 4 * output channels)
   int batch, height, width;
   int ksize;                              // 1 or 3 (pad = ksize/2)

@@ -21,6 +21,10 @@ struct ldm_sampler {
   int64_t n;          // elements per sample
   int64_t off_eps, off_t, off_unet, total;
   cudaGraphExec_t exec = nullptr;
+  // The legacy default stream cannot be captured: when the caller hands us stream 0 the work is forked onto
+  // this private stream (event-ordered after the caller's stream, and joined back before returning).
+  cudaStream_t own = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   long long step_kernels = 0;  // kernels inside one captured step (for ldm_launch_count under graph replay)
   // capture key: everything baked into the graph's kernel arguments
   struct Key {
@@ -51,12 +55,21 @@ extern "C" int ldm_sampler_create(ldm_unet* unet, const ldm_sampler_desc* desc, 
   s->off_t = off; off += 1024;
   s->off_unet = off; off += ldm_unet_workspace_bytes(unet, s->ub);
   s->total = off;
+  if (cudaStreamCreateWithFlags(&s->own, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+    ldm_sampler_destroy(s);
+    return ldm_set_error("sampler: could not create its stream/events: %s", cudaGetErrorString(cudaGetLastError()));
+  }
   *out = s;
   return 0;
 }
 extern "C" void ldm_sampler_destroy(ldm_sampler* s) {
   if (!s) return;
   if (s->exec) cudaGraphExecDestroy(s->exec);
+  if (s->ev_in) cudaEventDestroy(s->ev_in);
+  if (s->ev_out) cudaEventDestroy(s->ev_out);
+  if (s->own) cudaStreamDestroy(s->own);
   delete s;
 }
 extern "C" int64_t ldm_sampler_workspace_bytes(const ldm_sampler* s) { return s ? s->total : -1; }
@@ -76,9 +89,31 @@ static int sampler_step(ldm_sampler* s, float* x, const int64_t* y, const float*
   return k_add_i64(tdev, -1, st);
 }
 
+static int sampler_run_on(ldm_sampler* s, float* x, int x_is_init, const int64_t* y, const float* coef,
+                          const float* noise, uint64_t seed, uint64_t sample_offset, int first_step, int num_steps,
+                          void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+
 extern "C" int ldm_sampler_run(ldm_sampler* s, float* x, int x_is_init, const int64_t* y, const float* coef,
                                const float* noise, uint64_t seed, uint64_t sample_offset, int first_step,
                                int num_steps, void* workspace, int64_t workspace_bytes, void* stream) {
+  LDM_REQUIRE(s, "ldm_sampler_run: null sampler");
+  cudaStream_t user = (cudaStream_t)stream;
+  const bool fork = s->d.use_graph && (user == nullptr || user == cudaStreamLegacy || user == cudaStreamPerThread);
+  if (!fork)
+    return sampler_run_on(s, x, x_is_init, y, coef, noise, seed, sample_offset, first_step, num_steps, workspace,
+                          workspace_bytes, user);
+  LDM_CUDA(cudaEventRecord(s->ev_in, user));
+  LDM_CUDA(cudaStreamWaitEvent(s->own, s->ev_in, 0));
+  int rc = sampler_run_on(s, x, x_is_init, y, coef, noise, seed, sample_offset, first_step, num_steps, workspace,
+                          workspace_bytes, s->own);
+  LDM_CUDA(cudaEventRecord(s->ev_out, s->own));
+  LDM_CUDA(cudaStreamWaitEvent(user, s->ev_out, 0));
+  return rc;
+}
+
+static int sampler_run_on(ldm_sampler* s, float* x, int x_is_init, const int64_t* y, const float* coef,
+                          const float* noise, uint64_t seed, uint64_t sample_offset, int first_step, int num_steps,
+                          void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
   LDM_REQUIRE(s && x && coef, "ldm_sampler_run: null argument");
   LDM_REQUIRE(workspace && workspace_bytes >= s->total, "sampler workspace too small: %lld < %lld bytes",
               (long long)workspace_bytes, (long long)s->total);
@@ -86,7 +121,7 @@ extern "C" int ldm_sampler_run(ldm_sampler* s, float* x, int x_is_init, const in
   LDM_REQUIRE(first_step >= 0 && first_step < s->d.n_steps && num_steps >= 0 && num_steps <= first_step + 1,
               "sampler: steps [%d down %d) outside the schedule of %d", first_step, num_steps, s->d.n_steps);
   LDM_REQUIRE(s->d.y_len == 0 || y != nullptr, "sampler: classes pointer required");
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t st = stream;
   uint8_t* ws = (uint8_t*)workspace;
   if (!x_is_init) {
     int rc = k_randn(x, s->d.batch, s->n, seed, sample_offset, 0x17u, st);

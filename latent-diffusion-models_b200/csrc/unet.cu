@@ -378,6 +378,35 @@ extern "C" int ldm_unet_set_tap(ldm_unet* h, const char* name, float* out_nchw, 
 
 namespace {
 
+// Optional per-launch timing (ldm_unet_profile): one CUDA-event pair around every launch on the forward's own
+// stream, aggregated per kernel family after a stream sync.  Never active inside the sampler / graph capture.
+struct Prof {
+  struct Rec { int fam; double flops, bytes; cudaEvent_t e0, e1; };
+  std::vector<Rec> recs;
+  cudaStream_t st;
+  int begin(int fam, double flops, double bytes) {
+    Rec r{fam, flops, bytes, nullptr, nullptr};
+    LDM_CUDA(cudaEventCreate(&r.e0));
+    LDM_CUDA(cudaEventCreate(&r.e1));
+    LDM_CUDA(cudaEventRecord(r.e0, st));
+    recs.push_back(r);
+    return 0;
+  }
+  int end() {
+    LDM_CUDA(cudaEventRecord(recs.back().e1, st));
+    return 0;
+  }
+  ~Prof() {
+    for (auto& r : recs) { if (r.e0) cudaEventDestroy(r.e0); if (r.e1) cudaEventDestroy(r.e1); }
+  }
+};
+#define PROF(fam, flops, bytes, call)                                   \
+  do {                                                                  \
+    if (prof) RC(prof->begin((fam), (double)(flops), (double)(bytes))); \
+    RC(call);                                                           \
+    if (prof) RC(prof->end());                                          \
+  } while (0)
+
 struct Fwd {
   ldm_unet* h;
   cudaStream_t st;
@@ -385,6 +414,8 @@ struct Fwd {
   uint8_t* ws;
   Plan plan;
   const float* tproj;
+  Prof* prof = nullptr;
+  const float* fin_w = nullptr; const float* fin_b = nullptr; float* fin_out = nullptr; int fin_cout = 0;
   void* s(int i) { return ws + plan.s[i]; }
   void* gnws() { return ws + plan.gnws; }
 
@@ -398,7 +429,10 @@ struct Fwd {
   }
   int gn(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* g, const float* b, int R,
          int C, int groups, int silu) {
-    return k_group_norm(x, ldx, y, ldy, res, ldres, g, b, B, R * R, C, groups, GN_EPS, silu, dt, gnws(), st);
+    const double elems = (double)B * R * R * C;
+    PROF(LDM_FAM_GROUP_NORM, 0, elems * es * (res ? 3 : 2),
+         k_group_norm(x, ldx, y, ldy, res, ldres, g, b, B, R * R, C, groups, GN_EPS, silu, dt, gnws(), st));
+    return 0;
   }
   int conv(const void* x, int ldx, int cin, const void* x2, int ldx2, int cin2, const void* w, const float* bias,
            const float* rowvec, int ldrv, const void* res, int ldres, void* y, int ldy, int cout, int R, int ksize,
@@ -407,7 +441,15 @@ struct Fwd {
     a.x = x; a.ldx = ldx; a.cin = cin; a.x2 = x2; a.ldx2 = ldx2; a.cin2 = cin2; a.w = w; a.bias = bias;
     a.rowvec = rowvec; a.ld_rowvec = ldrv; a.res = res; a.ldres = ldres; a.y = y; a.ldy = ldy; a.cout = cout;
     a.batch = B; a.height = R; a.width = R; a.ksize = ksize; a.up2 = up2; a.dtype = dt;
-    return k_conv(a, impl, st);
+    if (y == nullptr) { a.fin_w = fin_w; a.fin_b = fin_b; a.fin_out = fin_out; a.fin_cout = fin_cout; }
+    return conv_args(a);
+  }
+  int conv_args(const ConvArgs& a) {
+    const double M = (double)a.batch * a.height * a.width, K = (double)a.ksize * a.ksize * a.cin + a.cin2;
+    const double bytes = (M * (a.cin + a.cin2) + (double)a.cout * K + M * a.cout + (a.res ? M * a.cout : 0)) * es;
+    const bool tc = dt == LDM_DT_BF16 && impl == 0;
+    PROF(tc ? LDM_FAM_CONV_TC : LDM_FAM_CONV_FFMA, 2.0 * M * a.cout * K, bytes, k_conv(a, impl, st));
+    return 0;
   }
   // ResNetBlock  src/UNet.py:85-99.  x must not alias s0/s1/out.
   int resblock(const ResW& r, const void* x, int ldx, void* out, int ldo, int R, bool use_t) {
@@ -427,11 +469,14 @@ struct Fwd {
     RC(gn(d, ldd, s(0), a.dim, nullptr, 0, a.ng, a.nb, R, a.dim, 1, 0));
     RC(conv(s(0), a.dim, a.dim, nullptr, 0, 0, a.wqkv, nullptr, nullptr, 0, nullptr, 0, qkv, 3 * HIDDEN, 3 * HIDDEN, R, 1));
     if (a.linear) {
-      RC(k_linear_attention(qkv, s(0), B, R * R, dt, st));
+      // 2 GEMMs of 32x32xN per head (ctx = k v^T, out = ctx^T q): 2 * 2*N*32*32 * 4 heads
+      PROF(LDM_FAM_LINEAR_ATTENTION, (double)B * 4 * 2 * 2.0 * R * R * 32 * 32, (double)B * R * R * (3 + 1) * HIDDEN * es,
+           k_linear_attention(qkv, s(0), B, R * R, dt, st));
       RC(conv(s(0), HIDDEN, HIDDEN, nullptr, 0, 0, a.wout, a.bout, nullptr, 0, nullptr, 0, s(1), a.dim, a.dim, R, 1));
       RC(gn(s(1), a.dim, out, ldo, d, ldd, a.og, a.ob, R, a.dim, 1, 0));  // x + GroupNorm(1,C)(to_out(...))
     } else {
-      RC(k_attention(qkv, s(0), B, R * R, dt, st));
+      PROF(LDM_FAM_ATTENTION, (double)B * 4 * 2 * 2.0 * R * R * R * R * 32, (double)B * R * R * (3 + 1) * HIDDEN * es,
+           k_attention(qkv, s(0), B, R * R, dt, st));
       RC(conv(s(0), HIDDEN, HIDDEN, nullptr, 0, 0, a.wout, a.bout, nullptr, 0, d, ldd, out, ldo, a.dim, R, 1));
     }
     return 0;
@@ -447,9 +492,39 @@ extern "C" int ldm_unet_forward(ldm_unet* h, const float* x, const int64_t* t, c
                              stream);
 }
 
+static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t* t, const int64_t* t_dev_scalar,
+                        const int64_t* y, int y_len, int y_rows, int batch, float* out, void* workspace,
+                        int64_t workspace_bytes, void* stream, Prof* prof_sink);
+
 int ldm_unet_forward_ex(ldm_unet* h, const float* x, int x_batch, const int64_t* t, const int64_t* t_dev_scalar,
                         const int64_t* y, int y_len, int y_rows, int batch, float* out, void* workspace,
                         int64_t workspace_bytes, void* stream) {
+  return forward_impl(h, x, x_batch, t, t_dev_scalar, y, y_len, y_rows, batch, out, workspace, workspace_bytes, stream,
+                      nullptr);
+}
+
+// Forward with per-launch CUDA-event timing (bench.py's roofline leg): synchronises `stream` at the end.
+extern "C" int ldm_unet_profile(ldm_unet* h, const float* x, const int64_t* t, const int64_t* y, int y_len, int y_rows,
+                                int batch, float* out, void* workspace, int64_t workspace_bytes, void* stream,
+                                ldm_profile* result) {
+  LDM_REQUIRE(result, "ldm_unet_profile: null result");
+  memset(result, 0, sizeof(*result));
+  Prof prof;
+  prof.st = (cudaStream_t)stream;
+  RC(forward_impl(h, x, batch, t, nullptr, y, y_len, y_rows, batch, out, workspace, workspace_bytes, stream, &prof));
+  LDM_CUDA(cudaStreamSynchronize(prof.st));
+  for (auto& r : prof.recs) {
+    float ms = 0.f;
+    LDM_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    ldm_profile_family& f = result->family[r.fam];
+    f.ms += ms; f.flops += r.flops; f.bytes += r.bytes; f.launches += 1;
+  }
+  return 0;
+}
+
+static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t* t, const int64_t* t_dev_scalar,
+                        const int64_t* y, int y_len, int y_rows, int batch, float* out, void* workspace,
+                        int64_t workspace_bytes, void* stream, Prof* prof_sink) {
   LDM_REQUIRE(h && x && out, "ldm_unet_forward: null argument");
   LDM_REQUIRE(x_batch > 0 && batch % x_batch == 0, "x_batch %d must divide batch %d", x_batch, batch);
   LDM_REQUIRE(h->loaded, "ldm_unet_forward: parameters were never loaded (ldm_unet_load_params)");
@@ -462,6 +537,7 @@ int ldm_unet_forward_ex(ldm_unet* h, const float* x, int x_batch, const int64_t*
   LDM_REQUIRE(!h->d.with_time_emb || t || t_dev_scalar, "t is required");
   Fwd f;
   f.h = h; f.st = (cudaStream_t)stream; f.B = batch; f.dt = h->d.dtype; f.es = h->es(); f.impl = h->d.conv_impl;
+  f.prof = prof_sink;
   f.plan = make_plan(h, batch);
   LDM_REQUIRE(workspace && workspace_bytes >= f.plan.total, "workspace too small: %lld < %lld bytes",
               (long long)workspace_bytes, (long long)f.plan.total);
@@ -472,17 +548,24 @@ int ldm_unet_forward_ex(ldm_unet* h, const float* x, int x_batch, const int64_t*
   float* tproj = (float*)(f.ws + f.plan.tproj);
   f.tproj = tproj;
   if (h->d.with_time_emb) {
-    RC(k_time_embed(t, t_dev_scalar, (y && y_len > 0) ? y : nullptr, y_len, y_rows > 0 ? y_rows : batch, h->w1t, h->b1,
-                    h->w3t, h->b3, h->label, temb, batch, h->D, f.st));
+    Prof* prof = f.prof;
+    PROF(LDM_FAM_OTHER, 2.0 * batch * (h->D / 4 + h->D) * h->D, ((double)(h->D / 4 + h->D) * h->D + 2.0 * batch * h->D) * 4,
+         k_time_embed(t, t_dev_scalar, (y && y_len > 0) ? y : nullptr, y_len, y_rows > 0 ? y_rows : batch, h->w1t, h->b1,
+                      h->w3t, h->b3, h->label, temb, batch, h->D, f.st));
     if (h->tap.out && h->tap.name == "temb") {
       LDM_REQUIRE(h->tap.numel == (int64_t)batch * h->D, "tap temb size mismatch");
       RC(k_copy_f32(temb, h->tap.out, (int64_t)batch * h->D, f.st));
     }
-    if (h->tproj_total > 0) RC(k_time_proj(temb, h->tproj_wt, h->tproj_b, tproj, batch, h->D, h->tproj_total, f.st));
+    if (h->tproj_total > 0)
+      PROF(LDM_FAM_OTHER, 2.0 * batch * h->D * h->tproj_total, ((double)h->D * h->tproj_total + (double)batch * (h->D + h->tproj_total)) * 4,
+           k_time_proj(temb, h->tproj_wt, h->tproj_b, tproj, batch, h->D, h->tproj_total, f.st));
   }
+  Prof* prof = f.prof;
   // initial conv: fp32 NCHW -> NHWC
   void* hin0 = f.ws + f.plan.hin[0];
-  RC(k_initial_conv(x, x_batch, h->init_w, h->init_b, hin0, batch, h->d.in_channels, h->dims[0], S, S, f.dt, f.st));
+  PROF(LDM_FAM_OTHER, 2.0 * batch * S * S * 9 * h->d.in_channels * h->dims[0],
+       (double)batch * S * S * (h->d.in_channels * 4 + h->dims[0] * f.es),
+       k_initial_conv(x, x_batch, h->init_w, h->init_b, hin0, batch, h->d.in_channels, h->dims[0], S, S, f.dt, f.st));
   RC(f.tap("initial", hin0, h->dims[0], h->dims[0], S));
   // ---- encoder  src/UNet.py:200-209
   for (int i = 0; i < L; ++i) {
@@ -496,7 +579,8 @@ int ldm_unet_forward_ex(ldm_unet* h, const float* x, int x_batch, const int64_t*
     RC(f.tap(("enc" + std::to_string(i) + ".res").c_str(), f.s(2), cout, cout, R));
     RC(f.attn_block(h->enc_attn[i], f.s(2), cout, skip, catc, R));
     RC(f.tap(("enc" + std::to_string(i) + ".attn").c_str(), skip, catc, cout, R));
-    RC(k_maxpool2(skip, catc, f.ws + f.plan.hin[i + 1], cout, batch, R, R, cout, f.dt, f.st));
+    PROF(LDM_FAM_OTHER, 0, (double)batch * R * R * cout * f.es * 1.25,
+         k_maxpool2(skip, catc, f.ws + f.plan.hin[i + 1], cout, batch, R, R, cout, f.dt, f.st));
   }
   // ---- bottleneck (no time embedding)  src/UNet.py:287-290
   {
@@ -520,7 +604,7 @@ int ldm_unet_forward_ex(ldm_unet* h, const float* x, int x_batch, const int64_t*
       a.x = z; a.ldx = u.cin; a.cin = u.cin; a.x2 = nullptr; a.ldx2 = 0; a.cin2 = 0; a.w = u.w; a.bias = u.b;
       a.rowvec = nullptr; a.ld_rowvec = 0; a.res = nullptr; a.ldres = 0; a.y = cat; a.ldy = catc; a.cout = 4 * u.cout;
       a.batch = batch; a.height = Rin; a.width = Rin; a.ksize = 1; a.up2 = 1; a.dtype = f.dt;
-      RC(k_conv(a, f.impl, f.st));
+      RC(f.conv_args(a));
     }
     RC(f.resblock(h->dec_res[j], cat, catc, f.s(2), u.cout, R, true));
     RC(f.attn_block(h->dec_attn[j], f.s(2), u.cout, f.s(3), u.cout, R));
@@ -528,9 +612,19 @@ int ldm_unet_forward_ex(ldm_unet* h, const float* x, int x_batch, const int64_t*
     z = f.s(3);
   }
   // ---- final  src/UNet.py:345-348,387
+  const bool fuse_final = f.dt == LDM_DT_BF16 && f.impl == 0 && h->dims[0] <= 256 &&
+                          !(h->tap.out && h->tap.name == "final.res");
+  if (fuse_final) {
+    // the 1x1 output projection rides in the epilogue of the last 3x3 GEMM, on the fp32 accumulators
+    f.fin_w = h->fin_w; f.fin_b = h->fin_b; f.fin_out = out; f.fin_cout = h->d.out_channels;
+    RC(f.resblock(h->final_res, z, h->dims[0], nullptr, h->dims[0], S, false));
+    return 0;
+  }
   RC(f.resblock(h->final_res, z, h->dims[0], f.s(2), h->dims[0], S, false));
   RC(f.tap("final.res", f.s(2), h->dims[0], h->dims[0], S));
-  RC(k_final_conv(f.s(2), h->dims[0], h->fin_w, h->fin_b, out, batch, h->dims[0], h->d.out_channels, S * S, f.dt, f.st));
+  PROF(LDM_FAM_OTHER, 2.0 * batch * S * S * h->dims[0] * h->d.out_channels,
+       (double)batch * S * S * (h->dims[0] * f.es + h->d.out_channels * 4),
+       k_final_conv(f.s(2), h->dims[0], h->fin_w, h->fin_b, out, batch, h->dims[0], h->d.out_channels, S * S, f.dt, f.st));
   return 0;
 }
 

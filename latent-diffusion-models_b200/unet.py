@@ -225,6 +225,29 @@ class UNet(nn.Module):
             self.last_launches = _lib.launch_count() - before
         return out
 
+    @torch.no_grad()
+    def profile(self, x_noisy: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor] = None,
+                y_rows: Optional[int] = None) -> Dict[str, Dict[str, float]]:
+        """One forward with a CUDA-event pair around every launch; per-family {ms, flops, bytes, launches}."""
+        dev = x_noisy.device
+        B, _, H, _ = x_noisy.shape
+        x = x_noisy.detach().to(torch.float32).contiguous()
+        t = t.detach().to(device=dev, dtype=torch.int64).contiguous()
+        y = y.detach().to(device=dev, dtype=torch.int64).contiguous() if y is not None else None
+        with torch.cuda.device(dev):
+            lib = _lib.load()
+            h = self.native(H, dev)
+            nbytes = lib.ldm_unet_workspace_bytes(h, B)
+            ws = self._workspace(nbytes, dev)
+            out = torch.empty(B, self.out_channels, H, H, dtype=torch.float32, device=dev)
+            prof = _lib.Profile()
+            _lib.check(lib.ldm_unet_profile(h, x.data_ptr(), t.data_ptr(), _lib.ptr(y), y.numel() if y is not None else 0,
+                                            y_rows if y_rows is not None else B, B, out.data_ptr(), ws.data_ptr(), nbytes,
+                                            _lib.stream_ptr(), C.byref(prof)))
+        return {name: {"ms": prof.family[i].ms, "flops": prof.family[i].flops, "bytes": prof.family[i].bytes,
+                       "launches": int(prof.family[i].launches)}
+                for i, name in enumerate(_lib.FAMILIES) if prof.family[i].launches}
+
     def __del__(self):
         try:
             lib = _lib.load()

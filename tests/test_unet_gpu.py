@@ -110,6 +110,7 @@ def test_rejects_bad_shapes():
     import ldm_b200
     from ldm_b200 import _lib
     m, _ = make_model("fp32")
+    m.requires_grad_(False)
     with pytest.raises(_lib.LdmError):   # 28x28 is not divisible by 2^4: the reference crashes at torch.cat
         m(torch.zeros(1, 3, 28, 28, device=dev()), torch.zeros(1, dtype=torch.long, device=dev()))
     with pytest.raises(_lib.LdmError):
