@@ -96,6 +96,7 @@ int ldm_unet_set_tap(ldm_unet* h, const char* name, float* out_nchw, int64_t out
 /* Measurement aid (bench.py's roofline leg; no reference counterpart): one forward with a CUDA-event pair
  * around every kernel launch on `stream`, summed per kernel family.  flops / bytes are the ALGORITHMIC work of
  * the launches (conv: 2*M*N*K; memory-bound kernels: one read + one write of each live tensor).
+ * `t` is ONE device int64: the batch-constant timestep, used exactly as the sampler uses it.
  * Synchronises `stream` before returning; not capturable. */
 enum ldm_kernel_family {
   LDM_FAM_CONV_TC = 0,          /* tcgen05 implicit-GEMM convolutions (3x3, 1x1, conv-transpose)  */

@@ -5,6 +5,8 @@
 // qkv is [B, N, 384]: channel = part*128 + head*32 + c (part 0/1/2 = q/k/v; "b (h c) x y" split, :124-127);
 // out is [B, N, 128] with channel = head*32 + c.
 // One CTA per (sample, head).  fp32 math throughout; T only selects the storage type.
+#include <stdlib.h>
+
 #include "kernels.h"
 
 #define LA_HEADS 4
@@ -137,10 +139,310 @@ __global__ void __launch_bounds__(256) linattn_kernel(const T* __restrict__ qkv,
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// bf16 LinearAttention on the legacy tensor path (mma.sync m16n8k16, bf16 in / fp32 accumulate).
+// The two GEMMs of a head are 32x32xN (ctx = softmax_N(k) v^T) and Nx32x32 (out = softmax_d(q) ctx): far too small
+// for a tcgen05 tile (M >= 64 per CTA), and the kernel is HBM-bound by an order of magnitude (0.5 KB moved per
+// token for 8 kFLOP), so the point of the tensor pipe here is only to get the FFMA work out of the way.
+//   one CTA per sample, one warp per head; every warp runs its own cp.async double buffer (no __syncthreads)
+//   phase 1: stream k,v once, online softmax over the tokens (running per-channel max, accumulators rescaled in
+//            registers), ctx accumulated in the C fragments
+//   phase 2: stream q once, softmax over the 32 head channels inside a quad, out tile staged through shared memory
+//            so that global stores are 16-byte / full-sector
+// Every qkv element is read exactly once and every out element written once.
+namespace {
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void hmma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float2 unpack_bf2(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+constexpr int LM_TILE = 32;                 // tokens per pipeline stage
+constexpr int LM_ROW = 64;                  // bytes per token row of one head (32 bf16)
+constexpr int LM_BUF = LM_TILE * LM_ROW;    // 2 KB
+constexpr float LOG2E = 1.4426950408889634f;
+
+// byte offset of 16-byte chunk `c` (0..3) of row `r` inside a [rows][64 B] tile; the XOR keeps the 8 row addresses
+// of every ldmatrix 8x8 block (and the quad-strided fragment stores) on distinct bank groups
+__device__ __forceinline__ uint32_t lm_off(int r, int c) { return (uint32_t)(r * LM_ROW + ((c ^ ((r >> 1) & 3)) << 4)); }
+
+__global__ void __launch_bounds__(128) linattn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N) {
+  // per warp: [stage][k|v] tiles of 2 KB
+  __shared__ __align__(128) uint8_t smem[4][2][2][LM_BUF];
+  const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const bf16* base = qkv + (int64_t)b * N * 384 + h * LA_D;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&smem[h][0][0][0]);
+  auto buf = [&](int stage, int which) { return sbase + (uint32_t)((stage * 2 + which) * LM_BUF); };
+
+  const int steps = N >> 4;              // 16-token k-steps
+  const int tiles = (steps + 1) >> 1;    // 32-token pipeline tiles (the last one may hold a single step)
+
+  // ---------------- phase 1: ctx[d][e] = sum_n exp(k[n][d] - m[d]) v[n][e]
+  auto load_kv = [&](int tile, int stage) {
+    const int tok0 = tile * LM_TILE;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;              // 0..127: k chunks, 128..255: v chunks
+      const int which = c >> 7, r = (c & 127) >> 2, ch = c & 3;
+      if (tok0 + r < N)
+        cp_async16(buf(stage, which) + lm_off(r, ch), base + (int64_t)(tok0 + r) * 384 + 128 * (1 + which) + ch * 8);
+    }
+  };
+  float acc[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+  float m_run[2][2], z[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) { m_run[mt][hf] = -INFINITY; z[mt][hf] = 0.f; }
+
+  load_kv(0, 0);
+  cp_async_commit();
+  if (tiles > 1) load_kv(1, 1);
+  cp_async_commit();
+  for (int t = 0; t < tiles; ++t) {
+    cp_async_wait<1>();
+    __syncwarp();
+    const int stage = t & 1;
+    const int nst = min(2, steps - 2 * t);
+    uint32_t a[2][2][4];
+    // A fragments of P^T: rows = head channel d, cols = token.  Matrix i of the x4 load: a0 (tok 0-7, d 0-7),
+    // a1 (tok 0-7, d 8-15), a2 (tok 8-15, d 0-7), a3 (tok 8-15, d 8-15), transposed on the way in.
+#pragma unroll
+    for (int st = 0; st < 2; ++st)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        if (st < nst) {
+          const int r = st * 16 + ((lane >> 4) << 3) + (lane & 7);
+          const int ch = mt * 2 + ((lane >> 3) & 1);
+          ldsm_x4_t(a[st][mt], buf(stage, 0) + lm_off(r, ch));
+        } else {
+          a[st][mt][0] = a[st][mt][1] = a[st][mt][2] = a[st][mt][3] = 0u;
+        }
+      }
+    // running per-channel max over the tokens
+    float sc[2][2], ml2[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int st = 0; st < 2; ++st)
+          if (st < nst) {
+            float2 x0 = unpack_bf2(a[st][mt][hf]), x1 = unpack_bf2(a[st][mt][hf + 2]);
+            mx = fmaxf(mx, fmaxf(fmaxf(x0.x, x0.y), fmaxf(x1.x, x1.y)));
+          }
+        mx = quad_max(mx);
+        const float nm = fmaxf(m_run[mt][hf], mx);
+        sc[mt][hf] = ex2f((m_run[mt][hf] - nm) * LOG2E);
+        m_run[mt][hf] = nm;
+        ml2[mt][hf] = nm * LOG2E;
+        z[mt][hf] *= sc[mt][hf];
+      }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        acc[mt][nt][0] *= sc[mt][0]; acc[mt][nt][1] *= sc[mt][0];
+        acc[mt][nt][2] *= sc[mt][1]; acc[mt][nt][3] *= sc[mt][1];
+      }
+    // p = exp(k - m), in place in the A fragments
+#pragma unroll
+    for (int st = 0; st < 2; ++st)
+      if (st < nst) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int hf = i & 1;
+            float2 x = unpack_bf2(a[st][mt][i]);
+            const float p0 = ex2f(fmaf(x.x, LOG2E, -ml2[mt][hf])), p1 = ex2f(fmaf(x.y, LOG2E, -ml2[mt][hf]));
+            z[mt][hf] += p0 + p1;
+            a[st][mt][i] = pack_bf2(p0, p1);
+          }
+      }
+    // B fragments of V (rows = token, cols = e) and the MMAs
+#pragma unroll
+    for (int st = 0; st < 2; ++st)
+      if (st < nst) {
+        uint32_t bv[2][4];
+#pragma unroll
+        for (int jp = 0; jp < 2; ++jp) {
+          // matrices: (tok 0-7, chunk 2jp), (tok 8-15, chunk 2jp), (tok 0-7, chunk 2jp+1), (tok 8-15, chunk 2jp+1)
+          const int r = st * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+          const int ch = jp * 2 + (lane >> 4);
+          ldsm_x4_t(bv[jp], buf(stage, 1) + lm_off(r, ch));
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) hmma_bf16(acc[mt][nt], a[st][mt], bv[nt >> 1][(nt & 1) * 2], bv[nt >> 1][(nt & 1) * 2 + 1]);
+      }
+    __syncwarp();
+    if (t + 2 < tiles) load_kv(t + 2, stage);
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+
+  // ---------------- ctx -> bf16 in shared memory, rows scaled by 32^-1/2 / Z[d]  (src/UNet.py:156-161)
+  const uint32_t ctx_s = buf(0, 0);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const float f = 0.17677669529663687f / quad_sum(z[mt][hf]);
+      const int d = mt * 16 + hf * 8 + g;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const uint32_t v = pack_bf2(acc[mt][nt][hf * 2] * f, acc[mt][nt][hf * 2 + 1] * f);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(ctx_s + lm_off(d, nt) + tq * 4), "r"(v) : "memory");
+      }
+    }
+  __syncwarp();
+  uint32_t bc[2][2][4];  // [k-step over d][pair of n-tiles]
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int jp = 0; jp < 2; ++jp) {
+      const int r = ks * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+      const int ch = jp * 2 + (lane >> 4);
+      ldsm_x4_t(bc[ks][jp], ctx_s + lm_off(r, ch));
+    }
+  __syncwarp();
+
+  // ---------------- phase 2: out[n][e] = sum_d softmax_d(q[n][:])[d] * ctx[d][e]
+  auto load_q = [&](int tile, int stage) {
+    const int tok0 = tile * LM_TILE;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i, r = c >> 2, ch = c & 3;
+      if (tok0 + r < N) cp_async16(buf(stage, 1) + lm_off(r, ch), base + (int64_t)(tok0 + r) * 384 + ch * 8);
+    }
+  };
+  const uint32_t stg = buf(1, 0);  // 16-token output staging tile
+  bf16* obase = out + (int64_t)b * N * 128 + h * LA_D;
+  load_q(0, 0);
+  cp_async_commit();
+  if (tiles > 1) load_q(1, 1);
+  cp_async_commit();
+  for (int t = 0; t < tiles; ++t) {
+    cp_async_wait<1>();
+    __syncwarp();
+    const int stage = t & 1;
+    const int nst = min(2, steps - 2 * t);
+    for (int mi = 0; mi < nst; ++mi) {
+      uint32_t aq[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        // matrices: a0 (tok 0-7, d-chunk 2ks), a1 (tok 8-15, 2ks), a2 (tok 0-7, 2ks+1), a3 (tok 8-15, 2ks+1)
+        const int r = mi * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+        const int ch = ks * 2 + (lane >> 4);
+        ldsm_x4(aq[ks], buf(stage, 1) + lm_off(r, ch));
+      }
+      // softmax over the 32 channels of a token: rows g (regs 0,2) and g+8 (regs 1,3), spread over the quad
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float2 x[4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) { x[2 * ks] = unpack_bf2(aq[ks][hf]); x[2 * ks + 1] = unpack_bf2(aq[ks][hf + 2]); }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(x[i].x, x[i].y));
+        mx = quad_max(mx) * LOG2E;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          x[i].x = ex2f(fmaf(x[i].x, LOG2E, -mx)); x[i].y = ex2f(fmaf(x[i].y, LOG2E, -mx));
+          s += x[i].x + x[i].y;
+        }
+        const float inv = 1.0f / quad_sum(s);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          aq[ks][hf] = pack_bf2(x[2 * ks].x * inv, x[2 * ks].y * inv);
+          aq[ks][hf + 2] = pack_bf2(x[2 * ks + 1].x * inv, x[2 * ks + 1].y * inv);
+        }
+      }
+      float o[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) hmma_bf16(o[nt], aq[ks], bc[ks][nt >> 1][(nt & 1) * 2], bc[ks][nt >> 1][(nt & 1) * 2 + 1]);
+      }
+      // stage the 16x32 tile, then 16-byte coalesced stores
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + lm_off(g, nt) + tq * 4), "r"(pack_bf2(o[nt][0], o[nt][1])) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + lm_off(g + 8, nt) + tq * 4), "r"(pack_bf2(o[nt][2], o[nt][3])) : "memory");
+      }
+      __syncwarp();
+      const int tok0 = t * LM_TILE + mi * 16;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = lane + 32 * i, r = c >> 2, ch = c & 3;
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(stg + lm_off(r, ch)));
+        *reinterpret_cast<uint4*>(obase + (int64_t)(tok0 + r) * 128 + ch * 8) = v;
+      }
+      __syncwarp();
+    }
+    if (t + 2 < tiles) load_q(t + 2, stage);
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+}
+
+}  // namespace
+
 int k_linear_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, cudaStream_t st) {
   if (batch == 0 || n_tokens == 0) return 0;
   int grid = batch * LA_HEADS;
-  if (dtype == LDM_DT_BF16) linattn_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)qkv, (bf16*)out, n_tokens);
+  if (dtype == LDM_DT_BF16 && n_tokens % 16 == 0 && getenv("LDM_LINATTN_SIMT") == nullptr)
+    linattn_mma_kernel<<<batch, 128, 0, st>>>((const bf16*)qkv, (bf16*)out, n_tokens);
+  else if (dtype == LDM_DT_BF16) linattn_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)qkv, (bf16*)out, n_tokens);
   else linattn_kernel<float><<<grid, 256, 0, st>>>((const float*)qkv, (float*)out, n_tokens);
   LDM_LAUNCHED("linear_attention");
   return 0;

@@ -243,7 +243,7 @@ __global__ void time_embed_kernel(const int64_t* __restrict__ t, const int64_t* 
                                   const float* __restrict__ w1t, const float* __restrict__ b1,
                                   const float* __restrict__ w3t, const float* __restrict__ b3,
                                   const float* __restrict__ label_emb, float* __restrict__ temb, int batch,
-                                  int D) {
+                                  int D, int table_classes) {
   extern __shared__ float sm[];
   const int Din = D / 4, half = D / 8;
   float* emb = sm;                 // [TE_ROWS][Din]
@@ -268,6 +268,7 @@ __global__ void time_embed_kernel(const int64_t* __restrict__ t, const int64_t* 
   float acc[TE_ROWS];
 #pragma unroll
   for (int r = 0; r < TE_ROWS; ++r) acc[r] = 0.f;
+#pragma unroll 8
   for (int i = 0; i < Din; ++i) {
     float w = w1t[i * D + j];
 #pragma unroll
@@ -282,6 +283,7 @@ __global__ void time_embed_kernel(const int64_t* __restrict__ t, const int64_t* 
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < TE_ROWS; ++r) acc[r] = 0.f;
+#pragma unroll 8
   for (int k = 0; k < D; ++k) {
     float w = w3t[k * D + j];
 #pragma unroll
@@ -293,7 +295,9 @@ __global__ void time_embed_kernel(const int64_t* __restrict__ t, const int64_t* 
     int b = b0 + r;
     if (b >= batch) break;
     float v = acc[r] + bb;
-    if (y && y_len > 0 && b < y_rows) {
+    if (table_classes != 0) {  // table mode: row b = class b; rows >= table_classes (or all, if < 0) carry no label
+      if (b < table_classes) v += label_emb[(int64_t)b * D + j];
+    } else if (y && y_len > 0 && b < y_rows) {
       int64_t cls = y_len == 1 ? y[0] : y[b];
       v += label_emb[cls * D + j];
     }
@@ -302,13 +306,14 @@ __global__ void time_embed_kernel(const int64_t* __restrict__ t, const int64_t* 
 }
 int k_time_embed(const int64_t* t, const int64_t* t_scalar, const int64_t* y, int y_len, int y_rows,
                  const float* w1t, const float* b1, const float* w3t, const float* b3, const float* label_emb,
-                 float* temb, int batch, int D, cudaStream_t st) {
+                 float* temb, int batch, int D, int table_classes, cudaStream_t st) {
   LDM_REQUIRE(D % 32 == 0 && D <= 1024 && D >= 32, "time_embed: unsupported embedding width %d", D);
   LDM_REQUIRE(t != nullptr || t_scalar != nullptr, "time_embed: need t or t_dev_scalar");
   if (batch == 0) return 0;
   size_t smem = (size_t)TE_ROWS * (D / 4 + D) * sizeof(float);
   time_embed_kernel<<<(batch + TE_ROWS - 1) / TE_ROWS, D, smem, st>>>(t, t_scalar, y, y_len, y_rows, w1t, b1,
-                                                                      w3t, b3, label_emb, temb, batch, D);
+                                                                      w3t, b3, label_emb, temb, batch, D,
+                                                                      table_classes);
   LDM_LAUNCHED("time_embed");
   return 0;
 }
@@ -332,6 +337,7 @@ __global__ void time_proj_kernel(const float* __restrict__ temb, const float* __
   float acc[TP_ROWS];
 #pragma unroll
   for (int r = 0; r < TP_ROWS; ++r) acc[r] = 0.f;
+#pragma unroll 8
   for (int k = 0; k < D; ++k) {
     float w = wt[(int64_t)k * total + o];
 #pragma unroll
@@ -355,67 +361,114 @@ int k_time_proj(const float* temb, const float* wt, const float* bias, float* tp
 
 // ------------------------------------------------------------------ initial 3x3 conv (Cin <= 8)  src/UNet.py:331,378
 // fp32 NCHW in -> NHWC out.  One thread: one pixel x 8 output channels.  w smem [9][Cin][Cout].
-template <typename T>
-__global__ void initial_conv_kernel(const float* __restrict__ x, int x_batch, const float* __restrict__ w,
-                                    const float* __restrict__ bias, T* __restrict__ y, int Cin, int Cout, int H,
-                                    int W, int64_t total) {
-  extern __shared__ float sw[];  // 9*Cin*Cout weights, then Cout bias
-  for (int i = threadIdx.x; i < 9 * Cin * Cout; i += blockDim.x) sw[i] = w[i];
-  float* sb = sw + 9 * Cin * Cout;
+// One thread per output pixel: the 9*Cin inputs sit in registers, all Cout accumulators too (Cout == 64 chunks of 8
+// are looped), weights are warp-uniform shared-memory broadcasts.  Input reads are coalesced along W.
+template <typename T, int CIN>
+__global__ void __launch_bounds__(128)
+initial_conv_kernel(const float* __restrict__ x, int x_batch, const float* __restrict__ w,
+                    const float* __restrict__ bias, T* __restrict__ y, int Cout, int H, int W, int64_t total) {
+  extern __shared__ __align__(16) float sw[];  // [9*CIN][Cout] weights, then Cout bias
+  for (int i = threadIdx.x; i < 9 * CIN * Cout; i += blockDim.x) sw[i] = w[i];
+  float* sb = sw + 9 * CIN * Cout;
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int cg = Cout / 8;
-  int g = (int)(i % cg);
-  int64_t r = i / cg;
-  int wq = (int)(r % W); r /= W;
-  int hq = (int)(r % H);
-  int64_t b = r / H;
-  int64_t bs = b % x_batch;
-  float acc[8];
+  const int wq = (int)(i % W);
+  const int hq = (int)((i / W) % H);
+  const int64_t b = i / ((int64_t)W * H);
+  const int64_t bs = b % x_batch;
+  float xv[9 * CIN];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = sb[g * 8 + k];
-  for (int ci = 0; ci < Cin; ++ci) {
-    const float* xp = x + (bs * Cin + ci) * (int64_t)H * W;
+  for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      int hh = hq + dy - 1;
-      if (hh < 0 || hh >= H) continue;
+    for (int dx = 0; dx < 3; ++dx) {
+      const int hh = hq + dy - 1, ww = wq + dx - 1;
+      const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        int ww = wq + dx - 1;
-        if (ww < 0 || ww >= W) continue;
-        float xv = xp[hh * W + ww];
-        const float* wp = sw + ((dy * 3 + dx) * Cin + ci) * Cout + g * 8;
+      for (int ci = 0; ci < CIN; ++ci)
+        xv[(dy * 3 + dx) * CIN + ci] = ok ? __ldg(x + ((bs * CIN + ci) * H + hh) * (int64_t)W + ww) : 0.f;
+    }
+  T* yp = y + i * (int64_t)Cout;
+  for (int c0 = 0; c0 < Cout; c0 += 16) {
+    float acc[16];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv, wp[k], acc[k]);
+    for (int k = 0; k < 16; ++k) acc[k] = sb[c0 + k];
+#pragma unroll
+    for (int j = 0; j < 9 * CIN; ++j) {
+      const float4* wp = reinterpret_cast<const float4*>(sw + j * Cout + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w4 = wp[q];
+        acc[4 * q + 0] = fmaf(xv[j], w4.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(xv[j], w4.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(xv[j], w4.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(xv[j], w4.w, acc[4 * q + 3]);
+      }
+    }
+    if constexpr (sizeof(T) == 2) {
+      float lo[8], hi[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { lo[k] = acc[k]; hi[k] = acc[8 + k]; }
+      store_chunk(yp + c0, lo);
+      store_chunk(yp + c0 + 8, hi);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float t4[4] = {acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]};
+        store_chunk(yp + c0 + 4 * q, t4);
       }
     }
   }
-  T* yp = y + ((b * H + hq) * W + wq) * (int64_t)Cout + g * 8;
-  if constexpr (sizeof(T) == 2) {
-    store_chunk(yp, acc);
-  } else {
-    float lo[4] = {acc[0], acc[1], acc[2], acc[3]}, hi[4] = {acc[4], acc[5], acc[6], acc[7]};
-    store_chunk(yp, lo);
-    store_chunk(yp + 4, hi);
+}
+template <typename T>
+static int initial_conv_launch(const float* x, int x_batch, const float* w, const float* bias, T* y, int batch, int cin,
+                               int cout, int height, int width, size_t smem, cudaStream_t st) {
+  const int64_t total = (int64_t)batch * height * width;
+  const int grid = (int)ceil_div64(total, 128);
+#define IC_GO(C) initial_conv_kernel<T, C><<<grid, 128, smem, st>>>(x, x_batch, w, bias, y, cout, height, width, total)
+  switch (cin) {
+    case 1: IC_GO(1); break;
+    case 2: IC_GO(2); break;
+    case 3: IC_GO(3); break;
+    case 4: IC_GO(4); break;
+    case 5: IC_GO(5); break;
+    case 6: IC_GO(6); break;
+    case 7: IC_GO(7); break;
+    default: IC_GO(8); break;
   }
+#undef IC_GO
+  LDM_LAUNCHED("initial_conv");
+  return 0;
 }
 int k_initial_conv(const float* x, int x_batch, const float* w, const float* bias, void* y, int batch, int cin,
                    int cout, int height, int width, int dtype, cudaStream_t st) {
   LDM_REQUIRE(cin >= 1 && cin <= 8, "initial_conv: in_channels %d not in [1,8]", cin);
-  LDM_REQUIRE(cout % 8 == 0, "initial_conv: channels must be a multiple of 8");
-  int64_t total = (int64_t)batch * height * width * (cout / 8);
-  if (total == 0) return 0;
+  LDM_REQUIRE(cout % 16 == 0, "initial_conv: channels must be a multiple of 16");
+  if ((int64_t)batch * height * width == 0) return 0;
   size_t smem = (size_t)(9 * cin * cout + cout) * sizeof(float);
   LDM_REQUIRE(smem <= 48 * 1024, "initial_conv: weights do not fit shared memory");
-  int grid = (int)ceil_div64(total, 256);
   if (dtype == LDM_DT_BF16)
-    initial_conv_kernel<bf16><<<grid, 256, smem, st>>>(x, x_batch, w, bias, (bf16*)y, cin, cout, height, width, total);
-  else
-    initial_conv_kernel<float><<<grid, 256, smem, st>>>(x, x_batch, w, bias, (float*)y, cin, cout, height, width, total);
-  LDM_LAUNCHED("initial_conv");
+    return initial_conv_launch<bf16>(x, x_batch, w, bias, (bf16*)y, batch, cin, cout, height, width, smem, st);
+  return initial_conv_launch<float>(x, x_batch, w, bias, (float*)y, batch, cin, cout, height, width, smem, st);
+}
+
+// tproj[b][:] = tab[class(b)][:]: expands the per-class table of a batch-constant timestep (sampler) to batch rows.
+__global__ void tproj_gather_kernel(const float4* __restrict__ tab, const int64_t* __restrict__ y, int y_len,
+                                    int y_rows, int n_classes, float4* __restrict__ tproj, int batch, int total4) {
+  const int b = blockIdx.y;
+  int row = n_classes;  // unlabeled
+  if (y && y_len > 0 && b < y_rows) row = (int)(y_len == 1 ? y[0] : y[b]);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x)
+    tproj[(int64_t)b * total4 + i] = tab[(int64_t)row * total4 + i];
+}
+int k_tproj_gather(const float* tab, const int64_t* y, int y_len, int y_rows, int n_classes, float* tproj, int batch,
+                   int total, cudaStream_t st) {
+  LDM_REQUIRE(total % 4 == 0, "tproj_gather: width %d not a multiple of 4", total);
+  if (batch == 0 || total == 0) return 0;
+  tproj_gather_kernel<<<dim3((total / 4 + 127) / 128, batch), 128, 0, st>>>(
+      (const float4*)tab, y, y_len, y_rows, n_classes, (float4*)tproj, batch, total / 4);
+  LDM_LAUNCHED("tproj_gather");
   return 0;
 }
 

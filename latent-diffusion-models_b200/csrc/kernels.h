@@ -26,7 +26,10 @@ int k_add_i64(int64_t* p, int64_t v, cudaStream_t st);
 //   w1t [D/4][D], w3t [D][D] are the transposed Linear weights; label_emb [num_classes][D]
 int k_time_embed(const int64_t* t, const int64_t* t_scalar, const int64_t* y, int y_len, int y_rows,
                  const float* w1t, const float* b1, const float* w3t, const float* b3, const float* label_emb,
-                 float* temb, int batch, int D, cudaStream_t st);
+                 float* temb, int batch, int D, int table_classes, cudaStream_t st);
+// table_classes > 0: row b carries the label embedding of class b (rows >= table_classes none); y is ignored
+int k_tproj_gather(const float* tab, const int64_t* y, int y_len, int y_rows, int n_classes, float* tproj, int batch,
+                   int total, cudaStream_t st);
 // tproj[b][o] = sum_k silu(temb[b][k]) wt[k][o] + bias[o]   (src/UNet.py:70-73,90-93), o < total
 int k_time_proj(const float* temb, const float* wt, const float* bias, float* tproj, int batch, int D,
                 int total, cudaStream_t st);

@@ -1,6 +1,7 @@
 // UNet eps-model handle: parameter inventory, weight packing and the forward pass as a fixed sequence of
 // kernel launches on the caller's stream (graph-capturable: no allocation, no host sync).
 // Mirrors src/UNet.py:293-389 of the reference; activations are NHWC in the handle's compute dtype.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -171,7 +172,7 @@ int64_t layout_all(ldm_unet* h, uint8_t* base) {
 
 // workspace plan for one forward of `batch` rows
 struct Plan {
-  int64_t temb, tproj, gnws, qkv, s[4], total;
+  int64_t temb, tproj, temb_tab, tproj_tab, gnws, qkv, s[4], total;
   std::vector<int64_t> hin;  // [L+1]
   std::vector<int64_t> cat;  // [L]
 };
@@ -182,6 +183,9 @@ Plan make_plan(const ldm_unet* h, int batch) {
   auto take = [&](int64_t bytes) { off = align_up64(off, 1024); int64_t o = off; off += bytes; return o; };
   p.temb = take((int64_t)batch * (h->D > 0 ? h->D : 1) * 4);
   p.tproj = take((int64_t)batch * (h->tproj_total > 0 ? h->tproj_total : 1) * 4);
+  // per-class table used when the timestep is batch-constant (sampler): num_classes + 1 rows
+  p.temb_tab = take((int64_t)(h->d.num_classes + 1) * (h->D > 0 ? h->D : 1) * 4);
+  p.tproj_tab = take((int64_t)(h->d.num_classes + 1) * (h->tproj_total > 0 ? h->tproj_total : 1) * 4);
   p.gnws = take(k_group_norm_ws_bytes(batch, 8));
   int64_t max_elems = 0;
   for (int i = 0; i < L; ++i) {
@@ -511,11 +515,17 @@ extern "C" int ldm_unet_profile(ldm_unet* h, const float* x, const int64_t* t, c
   memset(result, 0, sizeof(*result));
   Prof prof;
   prof.st = (cudaStream_t)stream;
-  RC(forward_impl(h, x, batch, t, nullptr, y, y_len, y_rows, batch, out, workspace, workspace_bytes, stream, &prof));
+  // `t` is used as the sampler uses it: one device-resident, batch-constant timestep (t[0])
+  RC(forward_impl(h, x, batch, nullptr, t, y, y_len, y_rows, batch, out, workspace, workspace_bytes, stream, &prof));
   LDM_CUDA(cudaStreamSynchronize(prof.st));
+  const bool dump = getenv("LDM_PROFILE_DUMP") != nullptr;
+  int idx = 0;
   for (auto& r : prof.recs) {
     float ms = 0.f;
     LDM_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    if (dump)
+      fprintf(stderr, "ldm_profile %3d fam %d  %8.1f us  %8.2f GFLOP %7.1f TFLOP/s  %8.2f MB %7.1f GB/s\n", idx++, r.fam,
+              ms * 1e3, r.flops / 1e9, r.flops / (ms * 1e-3) / 1e12, r.bytes / 1e6, r.bytes / (ms * 1e-3) / 1e9);
     ldm_profile_family& f = result->family[r.fam];
     f.ms += ms; f.flops += r.flops; f.bytes += r.bytes; f.launches += 1;
   }
@@ -549,16 +559,33 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
   f.tproj = tproj;
   if (h->d.with_time_emb) {
     Prof* prof = f.prof;
-    PROF(LDM_FAM_OTHER, 2.0 * batch * (h->D / 4 + h->D) * h->D, ((double)(h->D / 4 + h->D) * h->D + 2.0 * batch * h->D) * 4,
-         k_time_embed(t, t_dev_scalar, (y && y_len > 0) ? y : nullptr, y_len, y_rows > 0 ? y_rows : batch, h->w1t, h->b1,
-                      h->w3t, h->b3, h->label, temb, batch, h->D, f.st));
-    if (h->tap.out && h->tap.name == "temb") {
-      LDM_REQUIRE(h->tap.numel == (int64_t)batch * h->D, "tap temb size mismatch");
-      RC(k_copy_f32(temb, h->tap.out, (int64_t)batch * h->D, f.st));
+    const int64_t* yy = (y && y_len > 0) ? y : nullptr;
+    const int yr = y_rows > 0 ? y_rows : batch;
+    const bool table = t == nullptr && h->tproj_total > 0 && !(h->tap.out && h->tap.name == "temb");
+    if (table) {
+      // Batch-constant timestep (the sampler): at most num_classes + 1 distinct embedding rows exist, so the two
+      // MLPs run on that table and a gather expands the projection to the batch (src/UNet.py:373-376,90-93).
+      const int ncls = yy ? h->d.num_classes : 0, R = ncls + 1;
+      float* temb_tab = (float*)(f.ws + f.plan.temb_tab);
+      float* tproj_tab = (float*)(f.ws + f.plan.tproj_tab);
+      PROF(LDM_FAM_OTHER, 2.0 * R * (h->D / 4 + h->D) * h->D, ((double)(h->D / 4 + h->D) * h->D + 2.0 * R * h->D) * 4,
+           k_time_embed(nullptr, t_dev_scalar, nullptr, 0, 0, h->w1t, h->b1, h->w3t, h->b3, h->label, temb_tab, R, h->D,
+                        ncls > 0 ? ncls : -1, f.st));
+      PROF(LDM_FAM_OTHER, 2.0 * R * h->D * h->tproj_total, ((double)h->D * h->tproj_total + (double)R * (h->D + h->tproj_total)) * 4,
+           k_time_proj(temb_tab, h->tproj_wt, h->tproj_b, tproj_tab, R, h->D, h->tproj_total, f.st));
+      PROF(LDM_FAM_OTHER, 0, (double)batch * h->tproj_total * 4,
+           k_tproj_gather(tproj_tab, yy, y_len, yr, ncls, tproj, batch, h->tproj_total, f.st));
+    } else {
+      PROF(LDM_FAM_OTHER, 2.0 * batch * (h->D / 4 + h->D) * h->D, ((double)(h->D / 4 + h->D) * h->D + 2.0 * batch * h->D) * 4,
+           k_time_embed(t, t_dev_scalar, yy, y_len, yr, h->w1t, h->b1, h->w3t, h->b3, h->label, temb, batch, h->D, 0, f.st));
+      if (h->tap.out && h->tap.name == "temb") {
+        LDM_REQUIRE(h->tap.numel == (int64_t)batch * h->D, "tap temb size mismatch");
+        RC(k_copy_f32(temb, h->tap.out, (int64_t)batch * h->D, f.st));
+      }
+      if (h->tproj_total > 0)
+        PROF(LDM_FAM_OTHER, 2.0 * batch * h->D * h->tproj_total, ((double)h->D * h->tproj_total + (double)batch * (h->D + h->tproj_total)) * 4,
+             k_time_proj(temb, h->tproj_wt, h->tproj_b, tproj, batch, h->D, h->tproj_total, f.st));
     }
-    if (h->tproj_total > 0)
-      PROF(LDM_FAM_OTHER, 2.0 * batch * h->D * h->tproj_total, ((double)h->D * h->tproj_total + (double)batch * (h->D + h->tproj_total)) * 4,
-           k_time_proj(temb, h->tproj_wt, h->tproj_b, tproj, batch, h->D, h->tproj_total, f.st));
   }
   Prof* prof = f.prof;
   // initial conv: fp32 NCHW -> NHWC
