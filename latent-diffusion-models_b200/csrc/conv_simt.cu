@@ -167,6 +167,9 @@ int k_conv_simt(const ConvArgs& a, cudaStream_t st) {
 }
 
 int k_conv(const ConvArgs& a, int impl, cudaStream_t st) {
-  if (a.dtype == LDM_DT_BF16 && impl == 0) return k_conv_tc(a, st);
+  if (a.dtype == LDM_DT_BF16 && impl == 0) {
+    if (k_conv_halo_applicable(a)) return k_conv_halo(a, st);
+    return k_conv_tc(a, st);
+  }
   return k_conv_simt(a, st);
 }

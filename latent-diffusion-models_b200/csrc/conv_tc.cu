@@ -24,12 +24,11 @@
 #include <initializer_list>
 
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace {
 
-constexpr int TILE_M = 128;
-constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
-constexpr int UMMA_K = 16;
+using namespace tc;
 constexpr int A_STAGE_BYTES = TILE_M * BLOCK_K * 2;
 
 struct TcParams {
@@ -53,112 +52,13 @@ struct TcParams {
   const float* fin_w; const float* fin_b; float* fin_out; int fin_cout;
 };
 
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded wait: a protocol bug must surface as a trapped kernel (launch error), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  const long long start = clock64();
-  while (true) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, P1;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (clock64() - start > 4000000000LL) __trap();  // ~2 s at 2 GHz
-  }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                            int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): rows are 128 B apart,
-// 8-row core-matrix groups are SBO = 1024 B apart; LBO is unused for a single swizzle atom along K.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
-  d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset, bits [32,46)
-  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
-  return d;
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BLOCK_N
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-}
-
 template <int BLOCK_N>
 struct TcCfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered accumulator (power of two >= 32)
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int BAR_BYTES = 1024 + 2 * BLOCK_N * 4;  // mbarriers + TMEM slot (1 KB), then 2 bias slices
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
@@ -176,6 +76,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
   const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 1024 - smem_u32(smem_raw)));  // [2][BLOCK_N]
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -205,30 +106,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // (all loop-carried parameters live in registers: the kernel-parameter constant bank is not touched per k-block)
     if (lane == 0) {
+      const int num_n_tiles = p.num_n_tiles, NB = p.NB, HB = p.HB, tpi = p.NB == 1 ? p.H / p.HB : 1;
+      const int kb_main = p.kb_main, kb_total = p.kb_total, cin_blocks = p.cin_blocks;
+      const bool three = p.taps == 9;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+        const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
         int n0, h0;
-        if (p.NB == 1) {
-          const int tpi = p.H / p.HB;
+        if (NB == 1) {
           n0 = mt / tpi;
-          h0 = (mt % tpi) * p.HB;
+          h0 = (mt - n0 * tpi) * HB;
         } else {
-          n0 = mt * p.NB;
+          n0 = mt * NB;
           h0 = 0;
         }
-        for (int kb = 0; kb < p.kb_total; ++kb) {
+        int tap = 0, cb = 0;  // (tap, channel block) of the main source, advanced incrementally
+        for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           mbar_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
-          if (kb < p.kb_main) {
-            const int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
+          if (kb < kb_main) {
             int dy = 0, dx = 0;
-            if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+            if (three) { dy = tap / 3 - 1; dx = tap - (dy + 1) * 3 - 1; }
             tma_load_4d(smem_a + stage * A_STAGE_BYTES, &tmap_a, full_bar + 8 * stage, cb * BLOCK_K, dx, h0 + dy, n0);
+            if (++cb == cin_blocks) { cb = 0; ++tap; }
           } else {
-            tma_load_4d(smem_a + stage * A_STAGE_BYTES, &tmap_a2, full_bar + 8 * stage, (kb - p.kb_main) * BLOCK_K,
+            tma_load_4d(smem_a + stage * A_STAGE_BYTES, &tmap_a2, full_bar + 8 * stage, (kb - kb_main) * BLOCK_K,
                         0, h0, n0);
           }
           tma_load_2d(smem_b + stage * Cfg::B_STAGE_BYTES, &tmap_b, full_bar + 8 * stage, kb * BLOCK_K, nt * BLOCK_N);
@@ -240,6 +145,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BLOCK_N);
+      const int kb_total = p.kb_total;
+      const uint64_t adesc0 = make_sw128_desc(smem_a), bdesc0 = make_sw128_desc(smem_b);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
@@ -248,16 +155,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(tempty_bar + 8 * acc, ((iter >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < p.kb_total; ++kb) {
+        uint32_t accum = 0u;
+        for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
-          const uint64_t adesc = make_sw128_desc(smem_a + stage * A_STAGE_BYTES);
-          const uint64_t bdesc = make_sw128_desc(smem_b + stage * Cfg::B_STAGE_BYTES);
+          const uint64_t adesc = adesc0 + (uint64_t)(stage * (A_STAGE_BYTES >> 4));
+          const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (Cfg::B_STAGE_BYTES >> 4));
+          // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (addr>>4) field
+          umma_bf16(tmem_d, adesc, bdesc, idesc, accum);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (addr>>4) field
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 1; k < BLOCK_K / UMMA_K; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+          accum = 1u;
           umma_commit(empty_bar + 8 * stage);  // frees the smem stage when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -268,45 +176,69 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
     const int row = quarter * 32 + lane;
+    const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+    // loop-invariant parameters in registers (no constant-bank traffic per tile)
+    const int num_n_tiles = p.num_n_tiles, M = p.M, H = p.H, W = p.W, hw = p.H * p.W, up2 = p.up2;
+    const int cout_real = p.cout_real, cout = p.cout, ldy = p.ldy, ldres = p.ldres, ld_rowvec = p.ld_rowvec;
+    const int fin_cout = p.fin_cout;
+    bf16* const y = p.y;
+    const bf16* const res = p.res;
+    const float* const bias = p.bias;
+    const float* const rowvec = p.rowvec;
+    const float* const fin_w = p.fin_w;
+    float* const fin_out = p.fin_out;
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
-      const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+      const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
       const int acc = iter & 1;
-      mbar_wait(tfull_bar + 8 * acc, (iter >> 1) & 1);
-      tc_fence_after();
       const int m = mt * TILE_M + row;
-      const bool valid = m < p.M;
-      const int hw = p.H * p.W;
+      const bool valid = m < M;
       const int img = valid ? m / hw : 0;
       // output placement
       const int ncol0 = nt * BLOCK_N;              // GEMM column of this tile
-      const int q = p.up2 ? ncol0 / p.cout_real : 0;
-      const int cc0 = p.up2 ? ncol0 % p.cout_real : ncol0;
+      const int q = up2 ? ncol0 / cout_real : 0;
+      const int cc0 = up2 ? ncol0 - q * cout_real : ncol0;
       int64_t orow = m;
-      if (p.up2) {
-        const int w_ = m % p.W, r_ = m / p.W, h_ = r_ % p.H;
-        orow = ((int64_t)img * 2 * p.H + 2 * h_ + (q >> 1)) * (2 * p.W) + 2 * w_ + (q & 1);
+      if (up2) {
+        const int r_ = m / W, w_ = m - r_ * W, h_ = r_ % H;
+        orow = ((int64_t)img * 2 * H + 2 * h_ + (q >> 1)) * (2 * W) + 2 * w_ + (q & 1);
       }
-      bf16* yrow = p.y + orow * p.ldy + cc0;
-      const bf16* rrow = p.res ? p.res + (int64_t)m * p.ldres + cc0 : nullptr;
-      const float* rvrow = p.rowvec ? p.rowvec + (int64_t)img * p.ld_rowvec + cc0 : nullptr;
+      bf16* yrow = y + orow * ldy + cc0;
+      const bf16* rrow = res ? res + (int64_t)m * ldres + cc0 : nullptr;
+      const float* rvrow = rowvec ? rowvec + (int64_t)img * ld_rowvec + cc0 : nullptr;
+      // Everything the accumulator will be combined with is requested BEFORE the wait for the MMAs: the tile's bias
+      // slice goes to shared memory (L1 is tiny under the maximum shared-memory carve-out, a __ldg would pay L2
+      // latency per chunk), the first residual chunk to registers.
+      float* sb = s_bias + acc * BLOCK_N;
+      for (int c = et; c < BLOCK_N; c += 128) sb[c] = bias ? __ldg(bias + cc0 + c) : 0.f;
+      uint4 rr[4];
+      if (rrow && valid) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rr[j] = __ldg(reinterpret_cast<const uint4*>(rrow) + j);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (lane == 0) mbar_wait(tfull_bar + 8 * acc, (iter >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
       float fo[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
+        uint4 rn[4];  // next chunk's residual, in flight while this chunk is processed
+        if (rrow && valid && c0 + 32 < BLOCK_N) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rn[j] = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + 32) + j);
+        }
         tmem_ld_wait();
         if (valid) {
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cc0 + c0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + j);
+            v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
           }
           if (rvrow) {
 #pragma unroll
@@ -317,14 +249,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           if (rrow) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float t8[8];
-              load_chunk(rrow + c0 + j, t8);
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
 #pragma unroll
-              for (int u = 0; u < 8; ++u) v[j + u] += t8[u];
+              for (int u = 0; u < 4; ++u) {
+                const float2 f = __bfloat1622float2(h2[u]);
+                v[8 * j + 2 * u] += f.x; v[8 * j + 2 * u + 1] += f.y;
+              }
             }
           }
-          if (p.y) {
+          if (y) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               float t8[8];
@@ -333,9 +267,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               store_chunk(yrow + c0 + j, t8);
             }
           }
-          if (p.fin_out) {
-            for (int o = 0; o < p.fin_cout; ++o) {
-              const float* wrow = p.fin_w + o * p.cout + c0;
+          if (fin_out) {
+            for (int o = 0; o < fin_cout; ++o) {
+              const float* wrow = fin_w + o * cout + c0;
               float s = 0.f;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -349,12 +283,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rr[j] = rn[j];
       }
-      if (p.fin_out && valid) {
+      if (fin_out && valid) {
         const int pix = m - img * hw;
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          if (u < p.fin_cout) p.fin_out[((int64_t)img * p.fin_cout + u) * hw + pix] = fo[u] + __ldg(p.fin_b + u);
+          if (u < fin_cout) fin_out[((int64_t)img * fin_cout + u) * hw + pix] = fo[u] + __ldg(p.fin_b + u);
       }
       tc_fence_before();
       __syncwarp();
@@ -426,7 +362,10 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& 
 
 }  // namespace
 
-int k_conv_tc_prepare() { return tc_init(); }
+int k_conv_tc_prepare() {
+  if (int rc = tc_init()) return rc;
+  return k_conv_halo_prepare();
+}
 
 int k_conv_tc(const ConvArgs& a, cudaStream_t st) {
   if (int rc = tc_init()) return rc;

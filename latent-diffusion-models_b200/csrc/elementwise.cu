@@ -361,11 +361,13 @@ int k_time_proj(const float* temb, const float* wt, const float* bias, float* tp
 
 // ------------------------------------------------------------------ initial 3x3 conv (Cin <= 8)  src/UNet.py:331,378
 // fp32 NCHW in -> NHWC out.  One thread: one pixel x 8 output channels.  w smem [9][Cin][Cout].
-// One thread per output pixel: the 9*Cin inputs sit in registers, all Cout accumulators too (Cout == 64 chunks of 8
-// are looped), weights are warp-uniform shared-memory broadcasts.  Input reads are coalesced along W.
+// One thread per vertical pixel PAIR of one distinct input image: the 4x3xCin input patch sits in registers, weights
+// are warp-uniform shared-memory broadcasts (each feeds two pixels), input reads are coalesced along W.  Rows
+// b, b + x_batch, ... of the output alias the same image (the sampler's cond/uncond halves): computed once, stored
+// `reps` times.
 template <typename T, int CIN>
 __global__ void __launch_bounds__(128)
-initial_conv_kernel(const float* __restrict__ x, int x_batch, const float* __restrict__ w,
+initial_conv_kernel(const float* __restrict__ x, int x_batch, int reps, const float* __restrict__ w,
                     const float* __restrict__ bias, T* __restrict__ y, int Cout, int H, int W, int64_t total) {
   extern __shared__ __align__(16) float sw[];  // [9*CIN][Cout] weights, then Cout bias
   for (int i = threadIdx.x; i < 9 * CIN * Cout; i += blockDim.x) sw[i] = w[i];
@@ -374,49 +376,47 @@ initial_conv_kernel(const float* __restrict__ x, int x_batch, const float* __res
   __syncthreads();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
+  const int H2 = H >> 1;
   const int wq = (int)(i % W);
-  const int hq = (int)((i / W) % H);
-  const int64_t b = i / ((int64_t)W * H);
-  const int64_t bs = b % x_batch;
-  float xv[9 * CIN];
+  const int h0 = (int)((i / W) % H2) * 2;
+  const int64_t bs = i / ((int64_t)W * H2);
+  float xv[12 * CIN];  // rows h0-1 .. h0+2
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy)
+  for (int dy = 0; dy < 4; ++dy)
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
-      const int hh = hq + dy - 1, ww = wq + dx - 1;
+      const int hh = h0 + dy - 1, ww = wq + dx - 1;
       const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci)
         xv[(dy * 3 + dx) * CIN + ci] = ok ? __ldg(x + ((bs * CIN + ci) * H + hh) * (int64_t)W + ww) : 0.f;
     }
-  T* yp = y + i * (int64_t)Cout;
-  for (int c0 = 0; c0 < Cout; c0 += 16) {
-    float acc[16];
+  for (int c0 = 0; c0 < Cout; c0 += 8) {
+    float acc[2][8];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] = sb[c0 + k];
+    for (int k = 0; k < 8; ++k) acc[0][k] = acc[1][k] = sb[c0 + k];
 #pragma unroll
     for (int j = 0; j < 9 * CIN; ++j) {
       const float4* wp = reinterpret_cast<const float4*>(sw + j * Cout + c0);
+      const float4 wa = wp[0], wb = wp[1];
+      const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 w4 = wp[q];
-        acc[4 * q + 0] = fmaf(xv[j], w4.x, acc[4 * q + 0]);
-        acc[4 * q + 1] = fmaf(xv[j], w4.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(xv[j], w4.z, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(xv[j], w4.w, acc[4 * q + 3]);
+      for (int k = 0; k < 8; ++k) {
+        acc[0][k] = fmaf(xv[j], wv[k], acc[0][k]);
+        acc[1][k] = fmaf(xv[j + 3 * CIN], wv[k], acc[1][k]);
       }
     }
-    if constexpr (sizeof(T) == 2) {
-      float lo[8], hi[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { lo[k] = acc[k]; hi[k] = acc[8 + k]; }
-      store_chunk(yp + c0, lo);
-      store_chunk(yp + c0 + 8, hi);
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float t4[4] = {acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]};
-        store_chunk(yp + c0 + 4 * q, t4);
+    for (int r = 0; r < 2; ++r) {
+      for (int rep = 0; rep < reps; ++rep) {
+        T* yp = y + ((((int64_t)rep * x_batch + bs) * H + h0 + r) * W + wq) * (int64_t)Cout + c0;
+        if constexpr (sizeof(T) == 2) {
+          store_chunk(yp, acc[r]);
+        } else {
+          float lo[4] = {acc[r][0], acc[r][1], acc[r][2], acc[r][3]}, hi[4] = {acc[r][4], acc[r][5], acc[r][6], acc[r][7]};
+          store_chunk(yp, lo);
+          store_chunk(yp + 4, hi);
+        }
       }
     }
   }
@@ -424,9 +424,10 @@ initial_conv_kernel(const float* __restrict__ x, int x_batch, const float* __res
 template <typename T>
 static int initial_conv_launch(const float* x, int x_batch, const float* w, const float* bias, T* y, int batch, int cin,
                                int cout, int height, int width, size_t smem, cudaStream_t st) {
-  const int64_t total = (int64_t)batch * height * width;
+  const int64_t total = (int64_t)x_batch * (height / 2) * width;
+  const int reps = batch / x_batch;
   const int grid = (int)ceil_div64(total, 128);
-#define IC_GO(C) initial_conv_kernel<T, C><<<grid, 128, smem, st>>>(x, x_batch, w, bias, y, cout, height, width, total)
+#define IC_GO(C) initial_conv_kernel<T, C><<<grid, 128, smem, st>>>(x, x_batch, reps, w, bias, y, cout, height, width, total)
   switch (cin) {
     case 1: IC_GO(1); break;
     case 2: IC_GO(2); break;
@@ -444,13 +445,97 @@ static int initial_conv_launch(const float* x, int x_batch, const float* w, cons
 int k_initial_conv(const float* x, int x_batch, const float* w, const float* bias, void* y, int batch, int cin,
                    int cout, int height, int width, int dtype, cudaStream_t st) {
   LDM_REQUIRE(cin >= 1 && cin <= 8, "initial_conv: in_channels %d not in [1,8]", cin);
-  LDM_REQUIRE(cout % 16 == 0, "initial_conv: channels must be a multiple of 16");
+  LDM_REQUIRE(cout % 8 == 0, "initial_conv: channels must be a multiple of 8");
+  LDM_REQUIRE(height % 2 == 0, "initial_conv: height must be even");
+  LDM_REQUIRE(x_batch > 0 && batch % x_batch == 0, "initial_conv: x_batch must divide batch");
   if ((int64_t)batch * height * width == 0) return 0;
   size_t smem = (size_t)(9 * cin * cout + cout) * sizeof(float);
   LDM_REQUIRE(smem <= 48 * 1024, "initial_conv: weights do not fit shared memory");
   if (dtype == LDM_DT_BF16)
     return initial_conv_launch<bf16>(x, x_batch, w, bias, (bf16*)y, batch, cin, cout, height, width, smem, st);
   return initial_conv_launch<float>(x, x_batch, w, bias, (float*)y, batch, cin, cout, height, width, smem, st);
+}
+
+// ---- batch-constant timestep (sampler): the time MLP runs once, the label rows and the 8 mlp_t projections on a
+// (num_classes + 1)-row table.  Warp-per-output dot products over the ORIGINAL [out][in] weight rows: every weight
+// is requested by exactly one coalesced load issued up front, so the kernels cost one memory latency, not D of them.
+__global__ void __launch_bounds__(1024)
+time_table_kernel(const int64_t* __restrict__ t_scalar, const float* __restrict__ w1, const float* __restrict__ b1,
+                  const float* __restrict__ w3, const float* __restrict__ b3, const float* __restrict__ label_emb,
+                  float* __restrict__ s_tab, int R, int n_classes, int D) {
+  extern __shared__ float sm[];
+  const int Din = D / 4, half = D / 8;
+  float* emb = sm;             // [Din]
+  float* h1 = sm + Din;        // [D]
+  float* tt = h1 + D;          // [D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const float neg = -(float)(9.210340371976184 / (double)(half - 1));
+  const float tv = (float)(*t_scalar);
+  for (int i = threadIdx.x; i < Din; i += blockDim.x) {
+    const int fi = i < half ? i : i - half;
+    const float arg = tv * expf((float)fi * neg);
+    emb[i] = i < half ? sinf(arg) : cosf(arg);
+  }
+  __syncthreads();
+  for (int j = warp; j < D; j += nwarps) {
+    float a = 0.f;
+    for (int i = lane; i < Din; i += 32) a = fmaf(emb[i], w1[(int64_t)j * Din + i], a);
+    a = warp_sum(a);
+    if (lane == 0) {
+      const float v = a + b1[j];
+      h1[j] = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    }
+  }
+  __syncthreads();
+  for (int j = warp; j < D; j += nwarps) {
+    float a = 0.f;
+    for (int k = lane * 4; k < D; k += 128) {
+      const float4 w4 = *reinterpret_cast<const float4*>(w3 + (int64_t)j * D + k);
+      a = fmaf(h1[k], w4.x, a); a = fmaf(h1[k + 1], w4.y, a); a = fmaf(h1[k + 2], w4.z, a); a = fmaf(h1[k + 3], w4.w, a);
+    }
+    a = warp_sum(a);
+    if (lane == 0) tt[j] = a + b3[j];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < R * D; idx += blockDim.x) {
+    const int r = idx / D, j = idx % D;
+    float v = tt[j];
+    if (r < n_classes) v += label_emb[(int64_t)r * D + j];
+    s_tab[idx] = silu_acc(v);   // SiLU of mlp_t (src/UNet.py:72) applied here, once per table entry
+  }
+}
+__global__ void __launch_bounds__(256)
+time_proj_table_kernel(const float* __restrict__ s_tab, const float* __restrict__ w, const float* __restrict__ bias,
+                       float* __restrict__ tproj_tab, int R, int D, int total) {
+  extern __shared__ float s[];  // [R][D]
+  for (int i = threadIdx.x; i < R * D; i += blockDim.x) s[i] = s_tab[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (o >= total) return;
+  for (int r = 0; r < R; ++r) {
+    float a = 0.f;
+    for (int k = lane * 4; k < D; k += 128) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + (int64_t)o * D + k));
+      const float4 s4 = *reinterpret_cast<const float4*>(s + r * D + k);
+      a = fmaf(s4.x, w4.x, a); a = fmaf(s4.y, w4.y, a); a = fmaf(s4.z, w4.z, a); a = fmaf(s4.w, w4.w, a);
+    }
+    a = warp_sum(a);
+    if (lane == 0) tproj_tab[(int64_t)r * total + o] = a + bias[o];
+  }
+}
+int k_time_table(const int64_t* t_scalar, const float* w1, const float* b1, const float* w3, const float* b3,
+                 const float* label_emb, const float* tproj_w, const float* tproj_b, float* s_tab, float* tproj_tab,
+                 int R, int n_classes, int D, int total, cudaStream_t st) {
+  LDM_REQUIRE(D % 128 == 0 && D <= 1024, "time_table: unsupported embedding width %d", D);
+  LDM_REQUIRE((size_t)R * D * 4 <= 48 * 1024, "time_table: %d table rows do not fit shared memory", R);
+  time_table_kernel<<<1, 1024, (size_t)(D / 4 + 2 * D) * sizeof(float), st>>>(t_scalar, w1, b1, w3, b3, label_emb, s_tab,
+                                                                           R, n_classes, D);
+  LDM_LAUNCHED("time_table");
+  time_proj_table_kernel<<<(total + 7) / 8, 256, (size_t)R * D * sizeof(float), st>>>(s_tab, tproj_w, tproj_b,
+                                                                                    tproj_tab, R, D, total);
+  LDM_LAUNCHED("time_proj_table");
+  return 0;
 }
 
 // tproj[b][:] = tab[class(b)][:]: expands the per-class table of a batch-constant timestep (sampler) to batch rows.

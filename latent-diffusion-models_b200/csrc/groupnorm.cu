@@ -69,11 +69,11 @@ __device__ __forceinline__ float group_reduce(float v, float* part, float* gsum,
   return gsum[my_group];
 }
 
-template <typename T, int NJ>  // NJ > 0: hold NJ chunks per thread in registers; NJ == 0: re-read mode
+template <typename T, int NJ, bool RV>  // NJ > 0: hold NJ chunks per thread in registers; NJ == 0: re-read mode
 __global__ void __launch_bounds__(GN_MAX_THREADS)
 gn_fused_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, const T* __restrict__ res, int ldres,
-                const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int G, float eps,
-                int silu) {
+                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rowvec,
+                int ld_rowvec, int HW, int C, int G, float eps, int silu) {
   constexpr int V = VecTraits<T>::N;
   constexpr int NH = NJ > 0 ? NJ : 1;
   __shared__ float part[GN_MAX_THREADS];
@@ -88,6 +88,11 @@ gn_fused_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, co
   const T* xb = x + (int64_t)n * HW * ldx + ci * V;
   uint4 raw[NH];
   float w[V];
+  // optional per-sample, per-channel vector added to x before the statistics (the ResNetBlock time embedding,
+  // src/UNet.py:88-93: h = h + mlp_t(t)[:, :, None, None], then block2's GroupNorm)
+  float rv[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) rv[i] = RV ? rowvec[(int64_t)n * ld_rowvec + ci * V + i] : 0.f;
   // ---- pass 1: load + sum
   float s = 0.f;
   if (NJ > 0) {
@@ -98,15 +103,17 @@ gn_fused_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, co
     }
 #pragma unroll
     for (int j = 0; j < NH; ++j) {
-      unpack(raw[j], w);
+      if (pl + j * ppi < HW) {
+        unpack(raw[j], w);
 #pragma unroll
-      for (int i = 0; i < V; ++i) s += w[i];
+        for (int i = 0; i < V; ++i) s += w[i] + rv[i];
+      }
     }
   } else {
     for (int p = pl; p < HW; p += ppi) {
       unpack(load_raw(xb + (int64_t)p * ldx), w);
 #pragma unroll
-      for (int i = 0; i < V; ++i) s += w[i];
+      for (int i = 0; i < V; ++i) s += w[i] + rv[i];
     }
   }
   const float inv_n = 1.0f / ((float)HW * (float)(cpg * V));
@@ -119,14 +126,14 @@ gn_fused_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, co
       if (pl + j * ppi < HW) {
         unpack(raw[j], w);
 #pragma unroll
-        for (int i = 0; i < V; ++i) { float d = w[i] - mean; q = fmaf(d, d, q); }
+        for (int i = 0; i < V; ++i) { float d = w[i] + rv[i] - mean; q = fmaf(d, d, q); }
       }
     }
   } else {
     for (int p = pl; p < HW; p += ppi) {
       unpack(load_raw(xb + (int64_t)p * ldx), w);
 #pragma unroll
-      for (int i = 0; i < V; ++i) { float d = w[i] - mean; q = fmaf(d, d, q); }
+      for (int i = 0; i < V; ++i) { float d = w[i] + rv[i] - mean; q = fmaf(d, d, q); }
     }
   }
   __syncthreads();  // part/gsum reuse
@@ -138,7 +145,7 @@ gn_fused_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, co
   for (int i = 0; i < V; ++i) {
     const float ga = gamma[ci * V + i], be = beta[ci * V + i];
     a[i] = ga * rstd;
-    b[i] = be - mean * a[i];
+    b[i] = be + (rv[i] - mean) * a[i];
   }
   T* yb = y + (int64_t)n * HW * ldy + ci * V;
   const T* rb = res ? res + (int64_t)n * HW * ldres + ci * V : nullptr;
@@ -173,7 +180,8 @@ int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
 template <typename T>
 int gn_launch(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
-              const float* beta, int batch, int hw, int channels, int groups, float eps, int silu, cudaStream_t st) {
+              const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
+              float eps, int silu, cudaStream_t st) {
   constexpr int V = VecTraits<T>::N;
   const int cpp = channels / V;
   const int unit = cpp / gcd_i(cpp, 32) * 32;  // lcm(cpp, 32): whole warps and whole pixels
@@ -185,7 +193,9 @@ int gn_launch(const void* x, int ldx, void* y, int ldy, const void* res, int ldr
   const int ppi = threads / cpp;
   const int nj = (hw + ppi - 1) / ppi;
   const T* xp = (const T*)x; T* yp = (T*)y; const T* rp = (const T*)res;
-#define GN_GO(NJV) gn_fused_kernel<T, NJV><<<batch, threads, 0, st>>>(xp, ldx, yp, ldy, rp, ldres, gamma, beta, hw, channels, groups, eps, silu)
+#define GN_GO(NJV)                                                                                                  \
+  if (rowvec) gn_fused_kernel<T, NJV, true><<<batch, threads, 0, st>>>(xp, ldx, yp, ldy, rp, ldres, gamma, beta, rowvec, ld_rowvec, hw, channels, groups, eps, silu); \
+  else gn_fused_kernel<T, NJV, false><<<batch, threads, 0, st>>>(xp, ldx, yp, ldy, rp, ldres, gamma, beta, rowvec, ld_rowvec, hw, channels, groups, eps, silu)
   if (nj <= 1) GN_GO(1);
   else if (nj <= 2) GN_GO(2);
   else if (nj <= 4) GN_GO(4);
@@ -206,6 +216,13 @@ int64_t k_group_norm_ws_bytes(int batch, int groups) {
 int k_group_norm(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
                  const float* beta, int batch, int hw, int channels, int groups, float eps, int silu, int dtype,
                  void* workspace, cudaStream_t st) {
+  return k_group_norm_rv(x, ldx, y, ldy, res, ldres, gamma, beta, nullptr, 0, batch, hw, channels, groups, eps, silu, dtype,
+                         workspace, st);
+}
+
+int k_group_norm_rv(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
+                    const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
+                    float eps, int silu, int dtype, void* workspace, cudaStream_t st) {
   (void)workspace;
   const int V = dtype == LDM_DT_BF16 ? 8 : 4;
   LDM_REQUIRE(groups >= 1 && groups <= GN_MAX_GROUPS, "group_norm: groups=%d unsupported", groups);
@@ -215,6 +232,6 @@ int k_group_norm(const void* x, int ldx, void* y, int ldy, const void* res, int 
   LDM_REQUIRE(channels / V <= 1024, "group_norm: too many channels (%d)", channels);
   if (batch == 0 || hw == 0) return 0;
   if (dtype == LDM_DT_BF16)
-    return gn_launch<bf16>(x, ldx, y, ldy, res, ldres, gamma, beta, batch, hw, channels, groups, eps, silu, st);
-  return gn_launch<float>(x, ldx, y, ldy, res, ldres, gamma, beta, batch, hw, channels, groups, eps, silu, st);
+    return gn_launch<bf16>(x, ldx, y, ldy, res, ldres, gamma, beta, rowvec, ld_rowvec, batch, hw, channels, groups, eps, silu, st);
+  return gn_launch<float>(x, ldx, y, ldy, res, ldres, gamma, beta, rowvec, ld_rowvec, batch, hw, channels, groups, eps, silu, st);
 }

@@ -28,6 +28,11 @@ int k_time_embed(const int64_t* t, const int64_t* t_scalar, const int64_t* y, in
                  const float* w1t, const float* b1, const float* w3t, const float* b3, const float* label_emb,
                  float* temb, int batch, int D, int table_classes, cudaStream_t st);
 // table_classes > 0: row b carries the label embedding of class b (rows >= table_classes none); y is ignored
+// batch-constant t: s_tab [R][D] = SiLU(time_mlp(t) + label row r), tproj_tab [R][total] = s_tab . tproj_w^T + b
+//   w1 [D][D/4], w3 [D][D], tproj_w [total][D] in the original PyTorch [out][in] layout
+int k_time_table(const int64_t* t_scalar, const float* w1, const float* b1, const float* w3, const float* b3,
+                 const float* label_emb, const float* tproj_w, const float* tproj_b, float* s_tab, float* tproj_tab,
+                 int R, int n_classes, int D, int total, cudaStream_t st);
 int k_tproj_gather(const float* tab, const int64_t* y, int y_len, int y_rows, int n_classes, float* tproj, int batch,
                    int total, cudaStream_t st);
 // tproj[b][o] = sum_k silu(temb[b][k]) wt[k][o] + bias[o]   (src/UNet.py:70-73,90-93), o < total
@@ -47,6 +52,11 @@ int64_t k_group_norm_ws_bytes(int batch, int groups);
 int k_group_norm(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
                  const float* beta, int batch, int hw, int channels, int groups, float eps, int silu, int dtype,
                  void* workspace, cudaStream_t st);
+
+// same, with x + rowvec[n][c] (fp32 [batch][ld_rowvec]) normalised instead of x
+int k_group_norm_rv(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
+                    const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
+                    float eps, int silu, int dtype, void* workspace, cudaStream_t st);
 
 // ---- attention.cu
 int k_linear_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, cudaStream_t st);
@@ -74,6 +84,10 @@ struct ConvArgs {
 int k_conv_simt(const ConvArgs& a, cudaStream_t st);
 int k_conv_tc(const ConvArgs& a, cudaStream_t st);   // bf16 only, tcgen05/TMEM/TMA
 int k_conv_tc_prepare();  // resolve the driver entry point + opt in to large dynamic smem (call outside graph capture)
+// 3x3 convolutions at full resolution: A slab + halo loaded once per tile, taps = descriptor shifts (conv_halo.cu)
+int k_conv_halo_prepare();
+bool k_conv_halo_applicable(const ConvArgs& a);
+int k_conv_halo(const ConvArgs& a, cudaStream_t st);
 int k_conv(const ConvArgs& a, int impl, cudaStream_t st);
 
 // weight packing (pack.cu)

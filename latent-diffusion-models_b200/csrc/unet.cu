@@ -69,6 +69,7 @@ struct ldm_unet {
   // packed time path
   float *w1t = nullptr, *b1 = nullptr, *w3t = nullptr, *b3 = nullptr, *label = nullptr;
   float *tproj_wt = nullptr, *tproj_b = nullptr;
+  float *w1 = nullptr, *w3 = nullptr, *tproj_w = nullptr;  // [out][in] copies for the warp-per-output table kernels
   int tproj_total = 0;
   float *init_w = nullptr, *init_b = nullptr, *fin_w = nullptr, *fin_b = nullptr;
   // arena
@@ -157,6 +158,9 @@ int64_t layout_all(ldm_unet* h, uint8_t* base) {
     if (h->d.num_classes > 0) b.take(h->label, (int64_t)h->d.num_classes * D * 4);
     b.take(h->tproj_wt, (int64_t)D * (h->tproj_total > 0 ? h->tproj_total : 1) * 4);
     b.take(h->tproj_b, (int64_t)(h->tproj_total > 0 ? h->tproj_total : 1) * 4);
+    b.take(h->w1, (int64_t)(D / 4) * D * 4);
+    b.take(h->w3, (int64_t)D * D * 4);
+    b.take(h->tproj_w, (int64_t)D * (h->tproj_total > 0 ? h->tproj_total : 1) * 4);
   }
   b.take(h->init_w, (int64_t)9 * h->d.in_channels * C0 * 4); b.take(h->init_b, C0 * 4);
   b.take(h->fin_w, (int64_t)h->d.out_channels * C0 * 4); b.take(h->fin_b, h->d.out_channels * 4);
@@ -321,6 +325,7 @@ int pack_res(ldm_unet* h, ResW& r, const float* const* P, cudaStream_t st) {
   RC(k_copy_f32(P[r.p_n2w], r.g2, r.cout, st)); RC(k_copy_f32(P[r.p_n2b], r.be2, r.cout, st));
   if (r.tproj_off >= 0) {
     RC(k_transpose_f32(P[r.p_mlp_w], r.cout, h->D, h->tproj_wt, h->tproj_total, r.tproj_off, st));
+    RC(k_copy_f32(P[r.p_mlp_w], h->tproj_w + (int64_t)r.tproj_off * h->D, (int64_t)r.cout * h->D, st));
     RC(k_copy_f32(P[r.p_mlp_b], h->tproj_b + r.tproj_off, r.cout, st));
   }
   return 0;
@@ -346,6 +351,8 @@ extern "C" int ldm_unet_load_params(ldm_unet* h, const float* const* P, int n_pa
     RC(k_transpose_f32(P[h->p_t1w], D, D / 4, h->w1t, D, 0, st));
     RC(k_copy_f32(P[h->p_t1b], h->b1, D, st));
     RC(k_transpose_f32(P[h->p_t3w], D, D, h->w3t, D, 0, st));
+    RC(k_copy_f32(P[h->p_t1w], h->w1, (int64_t)D * (D / 4), st));
+    RC(k_copy_f32(P[h->p_t3w], h->w3, (int64_t)D * D, st));
     RC(k_copy_f32(P[h->p_t3b], h->b3, D, st));
     if (h->p_label >= 0) RC(k_copy_f32(P[h->p_label], h->label, (int64_t)h->d.num_classes * D, st));
   }
@@ -432,10 +439,10 @@ struct Fwd {
     return 0;
   }
   int gn(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* g, const float* b, int R,
-         int C, int groups, int silu) {
+         int C, int groups, int silu, const float* rowvec = nullptr, int ld_rowvec = 0) {
     const double elems = (double)B * R * R * C;
     PROF(LDM_FAM_GROUP_NORM, 0, elems * es * (res ? 3 : 2),
-         k_group_norm(x, ldx, y, ldy, res, ldres, g, b, B, R * R, C, groups, GN_EPS, silu, dt, gnws(), st));
+         k_group_norm_rv(x, ldx, y, ldy, res, ldres, g, b, rowvec, ld_rowvec, B, R * R, C, groups, GN_EPS, silu, dt, gnws(), st));
     return 0;
   }
   int conv(const void* x, int ldx, int cin, const void* x2, int ldx2, int cin2, const void* w, const float* bias,
@@ -458,9 +465,11 @@ struct Fwd {
   // ResNetBlock  src/UNet.py:85-99.  x must not alias s0/s1/out.
   int resblock(const ResW& r, const void* x, int ldx, void* out, int ldo, int R, bool use_t) {
     RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
+    // the time-embedding projection (h = h + mlp_t(t), :88-93) is a per-sample channel vector: it is added where
+    // block2's GroupNorm loads h (one 8-float vector per thread), not in the conv epilogue
     const float* rv = (use_t && r.tproj_off >= 0) ? tproj + r.tproj_off : nullptr;
-    RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, rv, h->tproj_total, nullptr, 0, s(1), r.cout, r.cout, R, 3));
-    RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1));
+    RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3));
+    RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1, rv, h->tproj_total));
     if (r.has_sc)  // 1x1 shortcut conv K-concatenated into the second 3x3 GEMM
       RC(conv(s(0), r.cout, r.cout, x, ldx, r.cin, r.w2, r.b2, nullptr, 0, nullptr, 0, out, ldo, r.cout, R, 3));
     else           // identity shortcut added in the epilogue
@@ -561,18 +570,18 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
     Prof* prof = f.prof;
     const int64_t* yy = (y && y_len > 0) ? y : nullptr;
     const int yr = y_rows > 0 ? y_rows : batch;
-    const bool table = t == nullptr && h->tproj_total > 0 && !(h->tap.out && h->tap.name == "temb");
+    const bool table = t == nullptr && h->tproj_total > 0 && !(h->tap.out && h->tap.name == "temb") &&
+                       h->D % 128 == 0 && (int64_t)(h->d.num_classes + 1) * h->D * 4 <= 48 * 1024;
     if (table) {
       // Batch-constant timestep (the sampler): at most num_classes + 1 distinct embedding rows exist, so the two
       // MLPs run on that table and a gather expands the projection to the batch (src/UNet.py:373-376,90-93).
       const int ncls = yy ? h->d.num_classes : 0, R = ncls + 1;
       float* temb_tab = (float*)(f.ws + f.plan.temb_tab);
       float* tproj_tab = (float*)(f.ws + f.plan.tproj_tab);
-      PROF(LDM_FAM_OTHER, 2.0 * R * (h->D / 4 + h->D) * h->D, ((double)(h->D / 4 + h->D) * h->D + 2.0 * R * h->D) * 4,
-           k_time_embed(nullptr, t_dev_scalar, nullptr, 0, 0, h->w1t, h->b1, h->w3t, h->b3, h->label, temb_tab, R, h->D,
-                        ncls > 0 ? ncls : -1, f.st));
-      PROF(LDM_FAM_OTHER, 2.0 * R * h->D * h->tproj_total, ((double)h->D * h->tproj_total + (double)R * (h->D + h->tproj_total)) * 4,
-           k_time_proj(temb_tab, h->tproj_wt, h->tproj_b, tproj_tab, R, h->D, h->tproj_total, f.st));
+      PROF(LDM_FAM_OTHER, 2.0 * (h->D / 4 + h->D) * h->D + 2.0 * R * h->D * h->tproj_total,
+           ((double)(h->D / 4 + h->D) * h->D + (double)h->D * h->tproj_total + (double)R * (h->D + h->tproj_total)) * 4,
+           k_time_table(t_dev_scalar, h->w1, h->b1, h->w3, h->b3, h->label, h->tproj_w, h->tproj_b, temb_tab, tproj_tab, R,
+                        ncls, h->D, h->tproj_total, f.st));
       PROF(LDM_FAM_OTHER, 0, (double)batch * h->tproj_total * 4,
            k_tproj_gather(tproj_tab, yy, y_len, yr, ncls, tproj, batch, h->tproj_total, f.st));
     } else {
@@ -640,6 +649,7 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
   }
   // ---- final  src/UNet.py:345-348,387
   const bool fuse_final = f.dt == LDM_DT_BF16 && f.impl == 0 && h->dims[0] <= 256 &&
+                          (h->d.out_channels + 1) * h->dims[0] * 4 <= 3072 &&
                           !(h->tap.out && h->tap.name == "final.res");
   if (fuse_final) {
     // the 1x1 output projection rides in the epilogue of the last 3x3 GEMM, on the fp32 accumulators

@@ -153,6 +153,11 @@ CONV_CASES = [
     (3, 512, 384, 2, 1, 0, False, False),
     (1, 128, 512, 2, 1, 0, False, True),
     (1, 64, 64, 8, 3, 0, False, False),
+    # full-resolution layers of the decoder / final block (halo-slab kernel: resident filter, 2-source K concat)
+    (2, 128, 64, 32, 3, 0, True, False),
+    (3, 64, 64, 32, 3, 128, False, False),
+    (40, 64, 64, 32, 3, 0, True, False),     # 360 tiles: several tiles per persistent CTA, ring wrap-around
+    (37, 128, 64, 32, 3, 0, False, True),
 ]
 
 
