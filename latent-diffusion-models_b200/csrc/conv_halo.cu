@@ -17,7 +17,7 @@
 //   * weights: [Cout][K] K-major tiles, one per k-block; when the whole filter fits next to the A ring it is loaded
 //     once per CTA and stays resident (all 32x32 layers of the reference UNet), otherwise it streams through a ring.
 //   * an optional second source (the ResNetBlock 1x1 shortcut, K-concatenated) uses the same slab with the centre tap.
-// Roles (192 threads, persistent, 1 CTA/SM): warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue; TMEM holds
+// Roles (320 threads, persistent, 1 CTA/SM): warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue; TMEM holds
 // two accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -70,7 +70,7 @@ struct HaloParams {
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                  const __grid_constant__ CUtensorMap tmap_b, const HaloParams p) {
   constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
@@ -93,7 +93,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < 8; ++s) { mbar_init(afull + 8 * s, 1); mbar_init(aempty + 8 * s, 1); }
     for (int s = 0; s < 32; ++s) { mbar_init(bfull + 8 * s, 1); mbar_init(bempty + 8 * s, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull + 8 * i, 1); mbar_init(tempty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull + 8 * i, 1); mbar_init(tempty + 8 * i, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BLOCK_N);
@@ -252,25 +252,31 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // 8 epilogue warps: two per TMEM lane quarter, each taking half of the tile's columns (one warp per scheduler
+    // would leave every TMEM-load / convert / store chain exposed)
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int COLS = BLOCK_N / 2;
+    const int cw = half * COLS;
     const int row = quarter * 32 + lane;
     const int H = p.H, W = p.W, P = p.P, hw = p.H * p.W;
     const int tiles_per_image = p.tiles_per_image, num_tiles = p.num_tiles;
-    const int ldy = p.ldy, ldres = p.ldres, ld_rowvec = p.ld_rowvec, fin_cout = p.fin_cout, cout = p.cout;
+    const int ldy = p.ldy, ldres = p.ldres, ld_rowvec = p.ld_rowvec, fin_cout = p.fin_cout;
     bf16* const y = p.y;
     const bf16* const res = p.res;
     const float* const rowvec = p.rowvec;
     const float* const fin_w = p.fin_w;
     float* const fin_out = p.fin_out;
     const bool no_mem = p.debug & 1;
+    float* s_fin = s_bias + 768;  // [128][8] cross-warp sums of the fused projection (offset 3 KB in the 7 KB region)
     // the bias vector is read by every row of every tile: stage it in shared memory once (the CTA runs with the
     // maximum shared-memory carve-out, so L1 is tiny and a __ldg per tile would pay L2 latency each time)
     {
       const int et = threadIdx.x - 64;
-      for (int c = et; c < BLOCK_N; c += 128) s_bias[c] = p.bias ? p.bias[c] : 0.f;
+      for (int c = et; c < BLOCK_N; c += 256) s_bias[c] = p.bias ? p.bias[c] : 0.f;
       if (fin_out)  // fused output projection: [fin_cout][BLOCK_N] weights behind the bias vector
-        for (int c = et; c < fin_cout * BLOCK_N; c += 128) s_bias[BLOCK_N + c] = fin_w[c];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int c = et; c < fin_cout * BLOCK_N; c += 256) s_bias[BLOCK_N + c] = fin_w[c];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
@@ -282,24 +288,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const bool valid = r >= 1 && r <= H && c >= 1 && c <= W && !no_mem;  // a real pixel, not a halo column / tail row
       const int pix = (r - 1) * W + (c - 1);
       const int64_t m = (int64_t)n * hw + pix;
-      bf16* yrow = y ? y + m * ldy : nullptr;
-      const float* rvrow = rowvec ? rowvec + (int64_t)n * ld_rowvec : nullptr;
+      bf16* yrow = y ? y + m * ldy + cw : nullptr;
+      const float* rvrow = rowvec ? rowvec + (int64_t)n * ld_rowvec + cw : nullptr;
       // residual row: requested BEFORE waiting for the accumulator, so its latency hides behind the MMAs
-      uint4 rr[BLOCK_N / 8];
+      uint4 rr[COLS / 8];
       if (res && valid) {
-        const uint4* rp = reinterpret_cast<const uint4*>(res + m * ldres);
+        const uint4* rp = reinterpret_cast<const uint4*>(res + m * ldres + cw);
 #pragma unroll
-        for (int j = 0; j < BLOCK_N / 8; ++j) rr[j] = __ldg(rp + j);
+        for (int j = 0; j < COLS / 8; ++j) rr[j] = __ldg(rp + j);
       }
       if (warp == 2 && lane == 0) DBG_STAMP(4);
       if (lane == 0) mbar_wait(tfull + 8 * acc, (iter >> 1) & 1);
       __syncwarp();
       if (warp == 2 && lane == 0) DBG_STAMP(5);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + cw;
       float fo[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = 0; c0 < COLS; c0 += 32) {
         uint32_t rg[32];
         tmem_ld32(taddr + c0, rg);
         tmem_ld_wait();
@@ -307,7 +313,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cw + c0 + j);
             v[j] = __uint_as_float(rg[j]) + b4.x; v[j + 1] = __uint_as_float(rg[j + 1]) + b4.y;
             v[j + 2] = __uint_as_float(rg[j + 2]) + b4.z; v[j + 3] = __uint_as_float(rg[j + 3]) + b4.w;
           }
@@ -340,7 +346,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           if (fin_out) {
             for (int o = 0; o < fin_cout; ++o) {
-              const float* wrow = s_bias + BLOCK_N + o * BLOCK_N + c0;
+              const float* wrow = s_bias + BLOCK_N + o * BLOCK_N + cw + c0;
               float sacc = 0.f;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -355,14 +361,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
       }
-      if (fin_out && valid) {
+      if (fin_out) {
+        // the two column halves of a row live in two warps: combine through shared memory, half 0 writes
+        float* fx = s_fin + row * 8;
+        if (half == 1) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (u < fin_cout) fin_out[((int64_t)n * fin_cout + u) * hw + pix] = fo[u] + __ldg(p.fin_b + u);
+          for (int u = 0; u < 8; ++u) fx[u] = fo[u];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0 && valid) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (u < fin_cout) fin_out[((int64_t)n * fin_cout + u) * hw + pix] = fo[u] + fx[u] + __ldg(p.fin_b + u);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // fx is rewritten by the next tile
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty + 8 * acc);
+      if (lane == 0) mbar_arrive_relaxed(tempty + 8 * acc);
       if (warp == 2 && lane == 0) DBG_STAMP(6);
     }
   }
@@ -478,13 +494,14 @@ int k_conv_halo(const ConvArgs& a, cudaStream_t st) {
   p.fin_w = a.fin_w; p.fin_b = a.fin_b; p.fin_out = a.fin_out; p.fin_cout = a.fin_cout;
   // shared-memory plan: filter resident if it leaves room for >= 2 slabs, else a streaming ring of 8 tiles
   const int b_tile = a.cout * BLOCK_K * 2;
-  const int budget = 227 * 1024 - 5120;  // barriers (1 KB) + bias / projection vectors (3 KB) + alignment slack
+  // barriers (1 KB) + bias / projection vectors (3 KB) + projection cross-warp sums (4 KB) + alignment slack
+  const int budget = 227 * 1024 - 9216;
   if ((int64_t)p.n_kb * b_tile + 2 * p.a_stage_bytes <= budget && p.n_kb <= 32) p.b_stages = p.n_kb;
   else p.b_stages = 8;
   p.a_stages = (budget - p.b_stages * b_tile) / p.a_stage_bytes;
   if (p.a_stages > 8) p.a_stages = 8;
   LDM_REQUIRE(p.a_stages >= 2, "conv_halo: shared memory plan failed (cout %d, %d k-blocks)", a.cout, p.n_kb);
-  const int smem = p.b_stages * b_tile + p.a_stages * p.a_stage_bytes + 4096 + 1024;
+  const int smem = p.b_stages * b_tile + p.a_stages * p.a_stage_bytes + 8192 + 1024;
   CUtensorMap ma, ma2, mb;
   if (int rc = make_slab_map(&ma, a.x, a.ldx, a.cin, a.batch, a.height, a.width, p.P, p.RB)) return rc;
   if (a.x2) {
@@ -494,8 +511,8 @@ int k_conv_halo(const ConvArgs& a, cudaStream_t st) {
   }
   if (int rc = make_filter_map(&mb, a.w, a.cout, p.n_kb * BLOCK_K, a.cout)) return rc;
   const int grid = p.num_tiles < g_num_sms_h ? p.num_tiles : g_num_sms_h;
-  if (a.cout == 64) conv_halo_kernel<64><<<grid, 192, smem, st>>>(ma, ma2, mb, p);
-  else conv_halo_kernel<128><<<grid, 192, smem, st>>>(ma, ma2, mb, p);
+  if (a.cout == 64) conv_halo_kernel<64><<<grid, 320, smem, st>>>(ma, ma2, mb, p);
+  else conv_halo_kernel<128><<<grid, 320, smem, st>>>(ma, ma2, mb, p);
   LDM_LAUNCHED("conv_halo");
   return 0;
 }

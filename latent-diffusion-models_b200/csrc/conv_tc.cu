@@ -11,24 +11,41 @@
 //     no index arithmetic in the SM.  The box lands as 128 rows x 128 B with the 128-byte swizzle, which is
 //     exactly the canonical K-major SWIZZLE_128B UMMA operand layout.
 //   * the weight tile [BLOCK_N x 64] is a 2-D TMA load from the packed [Cout][K] matrix, same layout.
-// Execution (one persistent CTA per SM, 192 threads)
+// Execution (one persistent CTA per SM, 320 threads)
 //   warp 0      TMA producer (one lane): STAGES-deep mbarrier ring
 //   warp 1      TMEM allocator + tcgen05.mma issuer (one lane): 4 x (128 x BLOCK_N x 16) MMAs per k-block,
 //               tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> +bias +time-embedding row vector
+//   warps 2..9  epilogue (two per TMEM lane quarter, half the columns each): tcgen05.ld (32 lanes x 32 columns) -> +bias +time-embedding row vector
 //               +residual -> bf16 -> 16-byte global stores.  Two accumulator buffers in TMEM (2*BLOCK_N
 //               columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+
+#include <stdlib.h>
 
 #include <initializer_list>
 
 #include "kernels.h"
 #include "tc_common.cuh"
 
+// timeline probe (LDM_TC_DEBUG=1): CTA 0 records globaltimer stamps of its first tiles
+__device__ unsigned long long g_tc_dbg[1024];
+extern "C" int ldm_debug_read_tc(unsigned long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, g_tc_dbg, sizeof(unsigned long long) * (n < 1024 ? n : 1024)) == cudaSuccess ? 0 : -1;
+}
+
 namespace {
 
 using namespace tc;
+__device__ __forceinline__ unsigned long long gtime_tc() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(slot)                                                                     \
+  do {                                                                                     \
+    if (p.debug && blockIdx.x == 0 && iter < 60) g_tc_dbg[iter * 16 + (slot)] = gtime_tc(); \
+  } while (0)
 constexpr int A_STAGE_BYTES = TILE_M * BLOCK_K * 2;
 
 struct TcParams {
@@ -50,6 +67,7 @@ struct TcParams {
   // fused trailing 1x1 projection (the UNet's final_conv.1, src/UNet.py:347): out[b][o][pix] = fin_b[o] +
   // sum_c fin_w[o][c] * row[c], computed from the fp32 accumulators; requires one N-tile (BLOCK_N == cout)
   const float* fin_w; const float* fin_b; float* fin_out; int fin_cout;
+  int debug;
 };
 
 template <int BLOCK_N>
@@ -58,12 +76,13 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered accumulator (power of two >= 32)
-  static constexpr int BAR_BYTES = 1024 + 2 * BLOCK_N * 4;  // mbarriers + TMEM slot (1 KB), then 2 bias slices
+  // mbarriers + TMEM slot (1 KB), 2 bias slices, 128 x 8 floats for the fused projection's cross-warp sum
+  static constexpr int BAR_BYTES = 1024 + 2 * BLOCK_N * 4 + 4096;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
   using Cfg = TcCfg<BLOCK_N>;
@@ -77,6 +96,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 1024 - smem_u32(smem_raw)));  // [2][BLOCK_N]
+  float* s_fin = s_bias + 2 * BLOCK_N;                                                      // [128][8]
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -92,7 +112,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
-      mbar_init(tempty_bar + 8 * i, 4);  // one arrival per epilogue warp
+      mbar_init(tempty_bar + 8 * i, 8);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -152,12 +172,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int iter = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
         const int acc = iter & 1;
+        TC_STAMP(0);
         mbar_wait(tempty_bar + 8 * acc, ((iter >> 1) & 1) ^ 1);
+        TC_STAMP(1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         uint32_t accum = 0u;
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);
+          if (kb == 0) TC_STAMP(2);
           tc_fence_after();
           const uint64_t adesc = adesc0 + (uint64_t)(stage * (A_STAGE_BYTES >> 4));
           const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (Cfg::B_STAGE_BYTES >> 4));
@@ -170,13 +193,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull_bar + 8 * acc);  // accumulator complete
+        TC_STAMP(3);
       }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    // 8 epilogue warps: two per TMEM lane quarter, each taking half of the tile's columns.  One warp per scheduler
+    // is latency-bound (every TMEM load / convert / store chain is exposed); two overlap each other's stalls.
+    const int quarter = warp & 3;             // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    const int half = (warp - 2) >> 2;         // column half of the tile
+    constexpr int COLS = BLOCK_N / 2;         // columns per warp
     const int row = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 64;          // 0..255 among the epilogue threads
     // loop-invariant parameters in registers (no constant-bank traffic per tile)
     const int num_n_tiles = p.num_n_tiles, M = p.M, H = p.H, W = p.W, hw = p.H * p.W, up2 = p.up2;
     const int cout_real = p.cout_real, cout = p.cout, ldy = p.ldy, ldres = p.ldres, ld_rowvec = p.ld_rowvec;
@@ -192,7 +220,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
       const int acc = iter & 1;
       const int m = mt * TILE_M + row;
-      const bool valid = m < M;
+      const bool valid = m < M && !(p.debug & 2);
       const int img = valid ? m / hw : 0;
       // output placement
       const int ncol0 = nt * BLOCK_N;              // GEMM column of this tile
@@ -203,31 +231,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int r_ = m / W, w_ = m - r_ * W, h_ = r_ % H;
         orow = ((int64_t)img * 2 * H + 2 * h_ + (q >> 1)) * (2 * W) + 2 * w_ + (q & 1);
       }
-      bf16* yrow = y + orow * ldy + cc0;
-      const bf16* rrow = res ? res + (int64_t)m * ldres + cc0 : nullptr;
-      const float* rvrow = rowvec ? rowvec + (int64_t)img * ld_rowvec + cc0 : nullptr;
+      const int cw = half * COLS;                  // this warp's first column inside the tile
+      bf16* yrow = y + orow * ldy + cc0 + cw;
+      const bf16* rrow = res ? res + (int64_t)m * ldres + cc0 + cw : nullptr;
+      const float* rvrow = rowvec ? rowvec + (int64_t)img * ld_rowvec + cc0 + cw : nullptr;
       // Everything the accumulator will be combined with is requested BEFORE the wait for the MMAs: the tile's bias
       // slice goes to shared memory (L1 is tiny under the maximum shared-memory carve-out, a __ldg would pay L2
       // latency per chunk), the first residual chunk to registers.
       float* sb = s_bias + acc * BLOCK_N;
-      for (int c = et; c < BLOCK_N; c += 128) sb[c] = bias ? __ldg(bias + cc0 + c) : 0.f;
+      for (int c = et; c < BLOCK_N; c += 256) sb[c] = bias ? __ldg(bias + cc0 + c) : 0.f;
       uint4 rr[4];
       if (rrow && valid) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) rr[j] = __ldg(reinterpret_cast<const uint4*>(rrow) + j);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) TC_STAMP(4);
       if (lane == 0) mbar_wait(tfull_bar + 8 * acc, (iter >> 1) & 1);
       __syncwarp();
+      if (warp == 2 && lane == 0) TC_STAMP(5);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + cw;
       float fo[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = 0; c0 < COLS; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         uint4 rn[4];  // next chunk's residual, in flight while this chunk is processed
-        if (rrow && valid && c0 + 32 < BLOCK_N) {
+        if (rrow && valid && c0 + 32 < COLS) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) rn[j] = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + 32) + j);
         }
@@ -236,7 +267,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + j);
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + cw + c0 + j);
             v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
             v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
           }
@@ -269,7 +300,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           if (fin_out) {
             for (int o = 0; o < fin_cout; ++o) {
-              const float* wrow = fin_w + o * cout + c0;
+              const float* wrow = fin_w + o * cout + cw + c0;
               float s = 0.f;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -286,15 +317,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 4; ++j) rr[j] = rn[j];
       }
-      if (fin_out && valid) {
-        const int pix = m - img * hw;
+      if (fin_out) {
+        // the two column halves of a row live in two warps: combine through shared memory, half 0 writes
+        float* fx = s_fin + row * 8;
+        if (half == 1) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (u < fin_cout) fin_out[((int64_t)img * fin_cout + u) * hw + pix] = fo[u] + __ldg(p.fin_b + u);
+          for (int u = 0; u < 8; ++u) fx[u] = fo[u];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0 && valid) {
+          const int pix = m - img * hw;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (u < fin_cout) fin_out[((int64_t)img * fin_cout + u) * hw + pix] = fo[u] + fx[u] + __ldg(p.fin_b + u);
+        }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+      if (lane == 0) mbar_arrive_relaxed(tempty_bar + 8 * acc);
+      if (warp == 2 && lane == 0) TC_STAMP(6);
     }
   }
   tc_fence_before();
@@ -355,7 +396,7 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& 
   using Cfg = TcCfg<BLOCK_N>;
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  conv_tc_kernel<BLOCK_N><<<grid, 192, Cfg::SMEM_BYTES, st>>>(ma, ma2, mb, p);
+  conv_tc_kernel<BLOCK_N><<<grid, 320, Cfg::SMEM_BYTES, st>>>(ma, ma2, mb, p);
   LDM_LAUNCHED("conv_tc");
   return 0;
 }
@@ -404,6 +445,7 @@ int k_conv_tc(const ConvArgs& a, cudaStream_t st) {
   p.res = (const bf16*)a.res; p.ldres = a.ldres;
   p.y = (bf16*)a.y; p.ldy = a.ldy;
   p.fin_w = a.fin_w; p.fin_b = a.fin_b; p.fin_out = a.fin_out; p.fin_cout = a.fin_cout;
+  { const char* d = getenv("LDM_TC_DEBUG"); p.debug = d ? atoi(d) : 0; }
   LDM_REQUIRE(!a.fin_out || (a.fin_cout >= 1 && a.fin_cout <= 8 && !a.up2 && (a.cout == 64 || a.cout == 128 || a.cout == 256)),
               "conv_tc: fused projection needs Cout in {64,128,256} and <= 8 outputs");
   LDM_REQUIRE(a.y || a.fin_out, "conv_tc: no output requested");

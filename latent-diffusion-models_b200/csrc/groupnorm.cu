@@ -1,7 +1,15 @@
 // GroupNorm (+SiLU) (+residual) on NHWC tensors -- replaces F.group_norm / nn.SiLU / Residual add of
 // src/UNet.py:52-58 (Block: GN(8,C) -> SiLU), :106 (PreNorm GN(1,C)), :147 (to_out GN(1,C)), :20 (x + fn(x)).
 //
-// ONE kernel, one CTA per sample (HBM-bound: x is read once, y written once):
+// Two implementations:
+//  (A) bf16 product path: two streaming kernels with full occupancy.  gn_stats reads x once from HBM and leaves
+//      per-(sample, slab, group) shifted sums; gn_apply re-reads x -- an L2 hit for every tensor of the reference
+//      UNet but one, the producer->consumer distance being a single 10-20 us kernel -- and writes y.  HBM traffic is
+//      the ideal one read + one write, and unlike a one-CTA-per-sample kernel nothing ever waits on a reduction.
+//      Sums are taken about a per-group pivot K = x[n][first pixel][first channel of the group] so that
+//      var = E[(x-K)^2] - (E[x-K])^2 does not cancel; partials are combined in a fixed order (deterministic,
+//      independent of batch and GPU count).
+//  (B) fp32 parity path: ONE kernel, one CTA per sample, exact two-pass statistics:
 //   * every thread owns a fixed 16-byte channel chunk (so a fixed group and fixed affine coefficients) and walks
 //     the pixels with stride blockDim/chunks_per_pixel; all of a thread's loads are issued up front and the
 //     values stay in registers (NJ <= 8 chunks per thread) between the statistics and the apply step.
@@ -10,6 +18,8 @@
 //     shared memory in a fixed order: no atomics, so a sample's bits do not depend on the batch, the launch
 //     shape or the GPU count.
 //   * y = [silu](x * a + b) [+ res];  SiLU via one MUFU (tanh.approx) on the bf16 path.
+#include <stdlib.h>
+
 #include "kernels.h"
 
 #define GN_MAX_GROUPS 32
@@ -176,6 +186,180 @@ gn_fused_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, co
   }
 }
 
+// ------------------------------------------------------------------ (A) streaming stats + apply, bf16
+constexpr int GS_THREADS = 256;
+constexpr int GS_MAX_SPLITS = 16;
+
+// grid (splits, batch); thread -> fixed channel chunk; writes part[n][split][g] = {sum(x-K), sum((x-K)^2)}
+template <bool RV>
+__global__ void __launch_bounds__(GS_THREADS)
+gn_stats_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ rowvec, int ld_rowvec,
+                float2* __restrict__ part, int HW, int C, int G, int pix_per_split) {
+  constexpr int V = 8;
+  __shared__ float part_s[GS_THREADS], part_q[GS_THREADS];
+  const int n = blockIdx.y, split = blockIdx.x;
+  const int cpp = C / V, cpg = cpp / G;
+  const int ci = threadIdx.x % cpp, pl = threadIdx.x / cpp, ppi = blockDim.x / cpp;
+  const int g = ci / cpg;
+  const bf16* xs = x + (int64_t)n * HW * ldx;
+  float rv[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) rv[i] = RV ? rowvec[(int64_t)n * ld_rowvec + ci * V + i] : 0.f;
+  // pivot of this thread's group (same for every CTA of the sample)
+  const int c_first = g * cpg * V;
+  const float K = __bfloat162float(xs[c_first]) + (RV ? rowvec[(int64_t)n * ld_rowvec + c_first] : 0.f);
+  const int p0 = split * pix_per_split, p1 = min(p0 + pix_per_split, HW);
+  float s = 0.f, q = 0.f;
+  const bf16* xb = xs + ci * V;
+  int p = p0 + pl;
+  // 4 independent 16-byte loads in flight per thread
+  for (; p + 3 * ppi < p1; p += 4 * ppi) {
+    uint4 r0 = load_raw(xb + (int64_t)p * ldx), r1 = load_raw(xb + (int64_t)(p + ppi) * ldx);
+    uint4 r2 = load_raw(xb + (int64_t)(p + 2 * ppi) * ldx), r3 = load_raw(xb + (int64_t)(p + 3 * ppi) * ldx);
+    float w[V];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      unpack(u == 0 ? r0 : (u == 1 ? r1 : (u == 2 ? r2 : r3)), w);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { const float d = w[i] + rv[i] - K; s += d; q = fmaf(d, d, q); }
+    }
+  }
+  for (; p < p1; p += ppi) {
+    float w[V];
+    unpack(load_raw(xb + (int64_t)p * ldx), w);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { const float d = w[i] + rv[i] - K; s += d; q = fmaf(d, d, q); }
+  }
+  part_s[threadIdx.x] = s;
+  part_q[threadIdx.x] = q;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int members = (blockDim.x / cpp) * cpg;
+  for (int gg = warp; gg < G; gg += nwarps) {
+    float a = 0.f, b = 0.f;
+    for (int idx = lane; idx < members; idx += 32) {
+      const int t = (idx / cpg) * cpp + gg * cpg + idx % cpg;
+      a += part_s[t]; b += part_q[t];
+    }
+    a = warp_sum(a); b = warp_sum(b);
+    if (lane == 0) part[((int64_t)n * gridDim.x + split) * G + gg] = make_float2(a, b);
+  }
+}
+
+// grid (ceil(HW / pix_per_block), batch)
+template <bool RV>
+__global__ void __launch_bounds__(GS_THREADS)
+gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, const bf16* __restrict__ res,
+                int ldres, const float* __restrict__ gamma, const float* __restrict__ beta,
+                const float* __restrict__ rowvec, int ld_rowvec, const float2* __restrict__ part, int splits, int HW,
+                int C, int G, float eps, int silu, int pix_per_block) {
+  constexpr int V = 8;
+  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  const int n = blockIdx.y;
+  const int cpp = C / V, cpg = cpp / G;
+  const bf16* xs = x + (int64_t)n * HW * ldx;
+  if (threadIdx.x < G) {
+    const int gg = threadIdx.x;
+    float a = 0.f, b = 0.f;
+    for (int sp = 0; sp < splits; ++sp) {  // fixed order
+      const float2 v = part[((int64_t)n * splits + sp) * G + gg];
+      a += v.x; b += v.y;
+    }
+    const int c_first = gg * cpg * V;
+    const float K = __bfloat162float(xs[c_first]) + (RV ? rowvec[(int64_t)n * ld_rowvec + c_first] : 0.f);
+    const float inv_n = 1.0f / ((float)HW * (float)(cpg * V));
+    const float m1 = a * inv_n;                       // E[x - K]
+    const float var = fmaxf(b * inv_n - m1 * m1, 0.f);  // biased, as F.group_norm
+    s_mean[gg] = K + m1;
+    s_rstd[gg] = 1.0f / sqrtf(var + eps);
+  }
+  __syncthreads();
+  const int ci = threadIdx.x % cpp, pl = threadIdx.x / cpp, ppi = blockDim.x / cpp;
+  if (pl >= ppi) return;
+  const int g = ci / cpg;
+  float a[V], b[V];
+  {
+    const float mean = s_mean[g], rstd = s_rstd[g];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float ga = gamma[ci * V + i], be = beta[ci * V + i];
+      const float rvi = RV ? rowvec[(int64_t)n * ld_rowvec + ci * V + i] : 0.f;
+      a[i] = ga * rstd;
+      b[i] = be + (rvi - mean) * a[i];
+    }
+  }
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, HW);
+  const bf16* xb = xs + ci * V;
+  bf16* yb = y + (int64_t)n * HW * ldy + ci * V;
+  const bf16* rb = res ? res + (int64_t)n * HW * ldres + ci * V : nullptr;
+  auto emit = [&](const uint4& rw, const uint4& rr, int p) {
+    float w[V];
+    unpack(rw, w);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float o = fmaf(w[i], a[i], b[i]);
+      if (silu) o = silu_fast(o);
+      w[i] = o;
+    }
+    if (rb) {
+      float r[V];
+      unpack(rr, r);
+#pragma unroll
+      for (int i = 0; i < V; ++i) w[i] += r[i];
+    }
+    store_chunk(yb + (int64_t)p * ldy, w);
+  };
+  int p = p0 + pl;
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  for (; p + 3 * ppi < p1; p += 4 * ppi) {
+    uint4 r0 = load_raw(xb + (int64_t)p * ldx), r1 = load_raw(xb + (int64_t)(p + ppi) * ldx);
+    uint4 r2 = load_raw(xb + (int64_t)(p + 2 * ppi) * ldx), r3 = load_raw(xb + (int64_t)(p + 3 * ppi) * ldx);
+    uint4 q0 = z4, q1 = z4, q2 = z4, q3 = z4;
+    if (rb) {
+      q0 = load_raw(rb + (int64_t)p * ldres); q1 = load_raw(rb + (int64_t)(p + ppi) * ldres);
+      q2 = load_raw(rb + (int64_t)(p + 2 * ppi) * ldres); q3 = load_raw(rb + (int64_t)(p + 3 * ppi) * ldres);
+    }
+    emit(r0, q0, p); emit(r1, q1, p + ppi); emit(r2, q2, p + 2 * ppi); emit(r3, q3, p + 3 * ppi);
+  }
+  for (; p < p1; p += ppi) emit(load_raw(xb + (int64_t)p * ldx), rb ? load_raw(rb + (int64_t)p * ldres) : z4, p);
+}
+
+int gcd_i2(int a, int b) { return b ? gcd_i2(b, a % b) : a; }
+
+int gn_stream_launch(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
+                     const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
+                     float eps, int silu, void* workspace, cudaStream_t st) {
+  const int cpp = channels / 8;
+  const int unit = cpp / gcd_i2(cpp, 32) * 32;
+  int threads = GS_THREADS / unit * unit;
+  if (threads < unit) threads = unit;  // unit <= 1024 guaranteed by the caller; <= 256 for the reference widths
+  LDM_REQUIRE(threads <= GS_THREADS, "group_norm: %d channels need the one-CTA-per-sample kernel", channels);
+  const int ppi = threads / cpp;
+  // slab sizes depend only on the per-sample geometry (never on the batch): a sample's bits are the same however
+  // the batch is sharded
+  int splits = hw / (ppi * 8);
+  if (splits > GS_MAX_SPLITS) splits = GS_MAX_SPLITS;
+  if (splits < 1) splits = 1;
+  const int pps = (hw + splits - 1) / splits;
+  float2* part = (float2*)workspace;
+  if (rowvec)
+    gn_stats_kernel<true><<<dim3(splits, batch), threads, 0, st>>>((const bf16*)x, ldx, rowvec, ld_rowvec, part, hw, channels, groups, pps);
+  else
+    gn_stats_kernel<false><<<dim3(splits, batch), threads, 0, st>>>((const bf16*)x, ldx, rowvec, ld_rowvec, part, hw, channels, groups, pps);
+  LDM_LAUNCHED("gn_stats");
+  int ppb = ppi * 8;
+  if (ppb > hw) ppb = hw;
+  const dim3 grid((hw + ppb - 1) / ppb, batch);
+  if (rowvec)
+    gn_apply_kernel<true><<<grid, threads, 0, st>>>((const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)res, ldres, gamma, beta,
+                                                    rowvec, ld_rowvec, part, splits, hw, channels, groups, eps, silu, ppb);
+  else
+    gn_apply_kernel<false><<<grid, threads, 0, st>>>((const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)res, ldres, gamma, beta,
+                                                     rowvec, ld_rowvec, part, splits, hw, channels, groups, eps, silu, ppb);
+  LDM_LAUNCHED("gn_apply");
+  return 0;
+}
+
 int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
 template <typename T>
@@ -209,8 +393,7 @@ int gn_launch(const void* x, int ldx, void* y, int ldy, const void* res, int ldr
 }  // namespace
 
 int64_t k_group_norm_ws_bytes(int batch, int groups) {
-  (void)batch; (void)groups;
-  return 1024;  // the single-pass kernel needs no scratch; kept for ABI stability
+  return (int64_t)batch * GS_MAX_SPLITS * groups * sizeof(float2) + 1024;
 }
 
 int k_group_norm(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
@@ -223,7 +406,6 @@ int k_group_norm(const void* x, int ldx, void* y, int ldy, const void* res, int 
 int k_group_norm_rv(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
                     const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
                     float eps, int silu, int dtype, void* workspace, cudaStream_t st) {
-  (void)workspace;
   const int V = dtype == LDM_DT_BF16 ? 8 : 4;
   LDM_REQUIRE(groups >= 1 && groups <= GN_MAX_GROUPS, "group_norm: groups=%d unsupported", groups);
   LDM_REQUIRE(channels % groups == 0 && (channels / groups) % V == 0,
@@ -231,6 +413,10 @@ int k_group_norm_rv(const void* x, int ldx, void* y, int ldy, const void* res, i
   LDM_REQUIRE(ldx % V == 0 && ldy % V == 0 && (res == nullptr || ldres % V == 0), "group_norm: unaligned stride");
   LDM_REQUIRE(channels / V <= 1024, "group_norm: too many channels (%d)", channels);
   if (batch == 0 || hw == 0) return 0;
+  if (dtype == LDM_DT_BF16 && workspace != nullptr && channels / 8 <= GS_THREADS && batch <= 65535 &&
+      getenv("LDM_GN_ONE_CTA") == nullptr)
+    return gn_stream_launch(x, ldx, y, ldy, res, ldres, gamma, beta, rowvec, ld_rowvec, batch, hw, channels, groups, eps,
+                            silu, workspace, st);
   if (dtype == LDM_DT_BF16)
     return gn_launch<bf16>(x, ldx, y, ldy, res, ldres, gamma, beta, rowvec, ld_rowvec, batch, hw, channels, groups, eps, silu, st);
   return gn_launch<float>(x, ldx, y, ldy, res, ldres, gamma, beta, rowvec, ld_rowvec, batch, hw, channels, groups, eps, silu, st);

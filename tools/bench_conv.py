@@ -10,8 +10,8 @@ x = torch.randn(B, R, R, cin, device=dev).bfloat16()
 w = torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5
 w2 = torch.randn(cout, second, 1, 1, device=dev) if second else None
 x2 = torch.randn(B, R, R, second, device=dev).bfloat16() if second else None
-b = torch.randn(cout, device=dev)
-rv = torch.randn(B, cout, device=dev)
+b = torch.randn(cout, device=dev) if not os.environ.get("NOBIAS") else None
+rv = torch.randn(B, cout, device=dev) if os.environ.get("ROWVEC") else None
 wp = ops.pack_conv_weight(w, "bf16", w2)
 out = torch.empty(B, R, R, cout, device=dev, dtype=torch.bfloat16)
 for _ in range(3): ops.conv2d(x, wp, k, bias=b, x2=x2, rowvec=rv, out=out)
@@ -36,4 +36,15 @@ if int(os.environ.get("LDM_HALO_DEBUG", "0")) & 4:
     t0 = buf[0]
     names = {0: "mma:pre_tempty", 1: "mma:got_tempty", 2: "mma:got_afull", 3: "mma:committed", 4: "epi:pre_tfull", 5: "epi:got_tfull", 6: "epi:arrived", 8: "prod:pre_aempty", 9: "prod:got_aempty"}
     for it in range(12):
+        print(f"tile {it}: " + "  ".join(f"{names[k]}={buf[it*16+k]-t0}" for k in sorted(names)))
+
+if int(os.environ.get("LDM_TC_DEBUG", "0")):
+    import ctypes as C
+    from ldm_b200 import _lib
+    lib = _lib.load()
+    buf = (C.c_ulonglong * 1024)()
+    lib.ldm_debug_read_tc(buf, 1024)
+    t0 = buf[0]
+    names = {0: "mma:pre_tempty", 1: "mma:got_tempty", 2: "mma:got_full0", 3: "mma:committed", 4: "epi:pre_tfull", 5: "epi:got_tfull", 6: "epi:arrived"}
+    for it in range(20, 28):
         print(f"tile {it}: " + "  ".join(f"{names[k]}={buf[it*16+k]-t0}" for k in sorted(names)))
