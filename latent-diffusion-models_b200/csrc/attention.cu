@@ -437,6 +437,279 @@ __global__ void __launch_bounds__(128) linattn_mma_kernel(const bf16* __restrict
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------------------
+// LinearAttention with the to_qkv 1x1 convolution fused in (C = 64 input channels: the two full-resolution sites,
+// where the 384-channel qkv tensor is 0.4 GB per pass -- 150 us to write at HBM write speed and 80 us to read back).
+//   xn [B][N][64] (the PreNorm output) -> out [B][N][128];  wqkv [384][64] bf16 (row = output channel, no bias)
+// One CTA per sample, one warp per head, private cp.async double buffer of x tiles per warp (x is tiny: 128 KB per
+// sample, the 4x re-read comes from L2).  All GEMMs on mma.sync m16n8k16 with operand roles chosen so that every
+// accumulator fragment is directly the next GEMM's operand fragment (no shared-memory round trips in the loop):
+//   K^T[d x tok] = Wk[d x c] X^T[c x tok]   (A = Wk rows, in registers; B = x tile via ldmatrix)
+//   V^T[e x tok] = Wv[e x c] X^T
+//   P^T = exp(K^T - rowmax) (online, fp32)   -> C fragment == A fragment of  ctx[d x e] += P^T[d x tok] V[tok x e]
+//                                               and the V^T C fragment     == B fragment of the same MMA
+//   Q[tok x d] = X[tok x c] Wq^T[c x d]      -> softmax over d inside a quad -> C fragment == A fragment of
+//   out[tok x e] = q~[tok x d] ctx[d x e]    (ctx through shared memory once per sample: it needs a transpose)
+namespace {
+
+__global__ void __launch_bounds__(128, 3) linattn_qkv_fused_kernel(const bf16* __restrict__ xn, int ldx,
+                                                               const bf16* __restrict__ wqkv,
+                                                               bf16* __restrict__ out, int N) {
+  constexpr int C = 64;
+  constexpr int XROW = 128;              // bytes per token row of the x tile (64 bf16)
+  constexpr int XBUF = LM_TILE * XROW;   // 4 KB
+  __shared__ __align__(128) uint8_t smem[4][2][XBUF];   // per warp: two x-tile stages
+  __shared__ __align__(128) uint8_t smem_aux[4][3072];  // per warp: ctx (2 KB) + 16-token output staging tile (1 KB)
+  const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const bf16* xb = xn + (int64_t)b * N * ldx;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&smem[h][0][0]);
+  const uint32_t ctx_s = (uint32_t)__cvta_generic_to_shared(&smem_aux[h][0]);
+  const uint32_t stg = ctx_s + 2048;
+  // 16-byte chunk c (0..7) of row r in a [rows][128 B] tile, XOR-swizzled (conflict-free ldmatrix)
+  auto xoff = [](int r, int c) { return (uint32_t)(r * XROW + ((c ^ (r & 7)) << 4)); };
+  auto load_x = [&](int tile, int stage) {
+    const int tok0 = tile * LM_TILE;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i, r = c >> 3, ch = c & 7;
+      if (tok0 + r < N) cp_async16(sbase + stage * XBUF + xoff(r, ch), xb + (int64_t)(tok0 + r) * ldx + ch * 8);
+    }
+  };
+  const int steps = N >> 4, tiles = (steps + 1) >> 1;
+  load_x(0, 0);
+  cp_async_commit();
+  if (tiles > 1) load_x(1, 1);
+  cp_async_commit();
+
+  // A fragments of a 32 x 64 weight block (rows = d or e): frag[mt][ks] = {(g, 2tq), (g+8, 2tq), (g, 2tq+8), (g+8, 2tq+8)}
+  auto load_w_a = [&](const bf16* w, uint32_t (&f)[2][4][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const bf16* p0 = w + (mt * 16 + g) * C + ks * 16 + 2 * tq;
+        f[mt][ks][0] = *reinterpret_cast<const uint32_t*>(p0);
+        f[mt][ks][1] = *reinterpret_cast<const uint32_t*>(p0 + 8 * C);
+        f[mt][ks][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+        f[mt][ks][3] = *reinterpret_cast<const uint32_t*>(p0 + 8 * C + 8);
+      }
+  };
+  uint32_t wk[2][4][4], wv[2][4][4];
+  load_w_a(wqkv + (int64_t)(128 + h * LA_D) * C, wk);
+  load_w_a(wqkv + (int64_t)(256 + h * LA_D) * C, wv);
+
+  float acc[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+  float m_run[2][2], z[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) { m_run[mt][hf] = -INFINITY; z[mt][hf] = 0.f; }
+
+  // ---------------- phase 1
+  for (int t = 0; t < tiles; ++t) {
+    cp_async_wait<1>();
+    __syncwarp();
+    const uint32_t xs = sbase + (t & 1) * XBUF;
+    const int nst = min(2, steps - 2 * t);
+    for (int st = 0; st < nst; ++st) {
+      // B fragments of X^T for the 16 tokens of this step: xf[ks] = {b0,b1 of tokens 0-7, b0,b1 of tokens 8-15}
+      uint32_t xf[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int r = st * 16 + ((lane >> 4) << 3) + (lane & 7);
+        const int ch = ks * 2 + ((lane >> 3) & 1);
+        ldsm_x4(xf[ks], xs + xoff(r, ch));
+      }
+      float kc[2][2][4], vc[2][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { kc[mt][nt][i] = 0.f; vc[mt][nt][i] = 0.f; }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            hmma_bf16(kc[mt][nt], wk[mt][ks], xf[ks][2 * nt], xf[ks][2 * nt + 1]);
+            hmma_bf16(vc[mt][nt], wv[mt][ks], xf[ks][2 * nt], xf[ks][2 * nt + 1]);
+          }
+        }
+      // online softmax over tokens, per channel row d = mt*16 + hf*8 + g
+      uint32_t pa[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float mx = fmaxf(fmaxf(kc[mt][0][2 * hf], kc[mt][0][2 * hf + 1]), fmaxf(kc[mt][1][2 * hf], kc[mt][1][2 * hf + 1]));
+          mx = quad_max(mx);
+          const float nm = fmaxf(m_run[mt][hf], mx);
+          const float sc = ex2f((m_run[mt][hf] - nm) * LOG2E);
+          m_run[mt][hf] = nm;
+          const float ml2 = nm * LOG2E;
+          const float p00 = ex2f(fmaf(kc[mt][0][2 * hf], LOG2E, -ml2)), p01 = ex2f(fmaf(kc[mt][0][2 * hf + 1], LOG2E, -ml2));
+          const float p10 = ex2f(fmaf(kc[mt][1][2 * hf], LOG2E, -ml2)), p11 = ex2f(fmaf(kc[mt][1][2 * hf + 1], LOG2E, -ml2));
+          z[mt][hf] = z[mt][hf] * sc + (p00 + p01 + p10 + p11);
+          pa[mt][hf] = pack_bf2(p00, p01);        // a0 / a1: tokens 2tq,2tq+1
+          pa[mt][hf + 2] = pack_bf2(p10, p11);    // a2 / a3: tokens 8+2tq, 8+2tq+1
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) { acc[mt][nt][2 * hf] *= sc; acc[mt][nt][2 * hf + 1] *= sc; }
+        }
+      // ctx[d x e] += P^T[d x tok] V[tok x e]:  B fragment of n-tile j (e = 8j + g) comes from V^T rows 8j + g
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int mv = j >> 1, hf = j & 1;
+        const uint32_t b0 = pack_bf2(vc[mv][0][2 * hf], vc[mv][0][2 * hf + 1]);
+        const uint32_t b1 = pack_bf2(vc[mv][1][2 * hf], vc[mv][1][2 * hf + 1]);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) hmma_bf16(acc[mt][j], pa[mt], b0, b1);
+      }
+    }
+    __syncwarp();
+    if (t + 2 < tiles) load_x(t + 2, t & 1);
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+
+  // ---------------- ctx -> bf16 in shared memory (64-byte rows, lm_off swizzle), scaled by 32^-1/2 / Z[d]
+  // (phase 2's first x tiles are requested now, so their latency hides behind the ctx hand-over)
+  load_x(0, 0);
+  cp_async_commit();
+  if (tiles > 1) load_x(1, 1);
+  cp_async_commit();
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const float f = 0.17677669529663687f / quad_sum(z[mt][hf]);
+      const int d = mt * 16 + hf * 8 + g;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const uint32_t v = pack_bf2(acc[mt][nt][hf * 2] * f, acc[mt][nt][hf * 2 + 1] * f);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(ctx_s + lm_off(d, nt) + tq * 4), "r"(v) : "memory");
+      }
+    }
+  __syncwarp();
+  uint32_t bc[2][2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int jp = 0; jp < 2; ++jp) {
+      const int r = ks * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+      const int ch = jp * 2 + (lane >> 4);
+      ldsm_x4_t(bc[ks][jp], ctx_s + lm_off(r, ch));
+    }
+  __syncwarp();
+  // B fragments of Wq^T (k = c, n = d): wq[ks][nt] = {Wq[d = 8nt + g][c = 16ks + 2tq..], [.. + 8]}
+  uint32_t wq[4][4][2];
+  {
+    const bf16* w = wqkv + (int64_t)(h * LA_D) * C;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const bf16* p0 = w + (nt * 8 + g) * C + ks * 16 + 2 * tq;
+        wq[ks][nt][0] = *reinterpret_cast<const uint32_t*>(p0);
+        wq[ks][nt][1] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+      }
+  }
+
+  // ---------------- phase 2: the same double-buffered x stream, now as the A operand of Q = X Wq^T
+  bf16* obase = out + (int64_t)b * N * 128 + h * LA_D;
+  for (int t = 0; t < tiles; ++t) {
+    cp_async_wait<1>();
+    __syncwarp();
+    const uint32_t xs = sbase + (t & 1) * XBUF;
+    const int nst = min(2, steps - 2 * t);
+    for (int mi = 0; mi < nst; ++mi) {
+      uint32_t xa[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        // A fragments of X: a0 (tok 0-7, chunk 2ks), a1 (tok 8-15, 2ks), a2 (tok 0-7, 2ks+1), a3 (tok 8-15, 2ks+1)
+        const int r = mi * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+        const int ch = ks * 2 + (lane >> 4);
+        ldsm_x4(xa[ks], xs + xoff(r, ch));
+      }
+      float qc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        qc[nt][0] = qc[nt][1] = qc[nt][2] = qc[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) hmma_bf16(qc[nt], xa[ks], wq[ks][nt][0], wq[ks][nt][1]);
+      }
+      // softmax over d (32 columns of a token row): rows g (regs 0,1) and g+8 (regs 2,3)
+      uint32_t qa[2][4];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mx = fmaxf(mx, fmaxf(qc[nt][2 * hf], qc[nt][2 * hf + 1]));
+        mx = quad_max(mx) * LOG2E;
+        float s = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          qc[nt][2 * hf] = ex2f(fmaf(qc[nt][2 * hf], LOG2E, -mx));
+          qc[nt][2 * hf + 1] = ex2f(fmaf(qc[nt][2 * hf + 1], LOG2E, -mx));
+          s += qc[nt][2 * hf] + qc[nt][2 * hf + 1];
+        }
+        const float inv = 1.0f / quad_sum(s);
+        // A fragment of q~ for k-step ks (d in [16ks, 16ks+16)): n-tiles 2ks (cols 2tq..) and 2ks+1 (cols 8+2tq..)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          qa[ks][hf] = pack_bf2(qc[2 * ks][2 * hf] * inv, qc[2 * ks][2 * hf + 1] * inv);
+          qa[ks][hf + 2] = pack_bf2(qc[2 * ks + 1][2 * hf] * inv, qc[2 * ks + 1][2 * hf + 1] * inv);
+        }
+      }
+      float o[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) hmma_bf16(o[nt], qa[ks], bc[ks][nt >> 1][(nt & 1) * 2], bc[ks][nt >> 1][(nt & 1) * 2 + 1]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + lm_off(g, nt) + tq * 4), "r"(pack_bf2(o[nt][0], o[nt][1])) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + lm_off(g + 8, nt) + tq * 4), "r"(pack_bf2(o[nt][2], o[nt][3])) : "memory");
+      }
+      __syncwarp();
+      const int tok0 = t * LM_TILE + mi * 16;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = lane + 32 * i, r = c >> 2, ch = c & 3;
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(stg + lm_off(r, ch)));
+        *reinterpret_cast<uint4*>(obase + (int64_t)(tok0 + r) * 128 + ch * 8) = v;
+      }
+      __syncwarp();
+    }
+    if (t + 2 < tiles) load_x(t + 2, t & 1);
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+}
+
+}  // namespace
+
+int k_linear_attention_qkv(const void* xn, int ldx, int cin, const void* wqkv, void* out, int batch, int n_tokens,
+                           int dtype, cudaStream_t st) {
+  LDM_REQUIRE(dtype == LDM_DT_BF16 && cin == 64 && n_tokens % 16 == 0 && ldx % 8 == 0,
+              "linear_attention_qkv: needs bf16, 64 input channels and a multiple of 16 tokens");
+  if (batch == 0 || n_tokens == 0) return 0;
+  linattn_qkv_fused_kernel<<<batch, 128, 0, st>>>((const bf16*)xn, ldx, (const bf16*)wqkv, (bf16*)out, n_tokens);
+  LDM_LAUNCHED("linear_attention_qkv");
+  return 0;
+}
+bool k_linear_attention_qkv_applicable(int cin, int n_tokens, int dtype) {
+  return dtype == LDM_DT_BF16 && cin == 64 && n_tokens % 16 == 0 && getenv("LDM_LINATTN_UNFUSED") == nullptr;
+}
+
 int k_linear_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, cudaStream_t st) {
   if (batch == 0 || n_tokens == 0) return 0;
   int grid = batch * LA_HEADS;

@@ -60,6 +60,11 @@ int k_group_norm_rv(const void* x, int ldx, void* y, int ldy, const void* res, i
 
 // ---- attention.cu
 int k_linear_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, cudaStream_t st);
+// LinearAttention with the to_qkv 1x1 convolution fused in (src/UNet.py:145,149-163): xn [B,N,cin] -> out [B,N,128];
+// wqkv = packed [384][cin] bf16 (no bias).  Only cin == 64, bf16, N % 16 == 0 (the full-resolution sites).
+bool k_linear_attention_qkv_applicable(int cin, int n_tokens, int dtype);
+int k_linear_attention_qkv(const void* xn, int ldx, int cin, const void* wqkv, void* out, int batch, int n_tokens,
+                           int dtype, cudaStream_t st);
 int k_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, cudaStream_t st);
 
 // ---- conv (conv_simt.cu / conv_tc.cu)

@@ -480,6 +480,16 @@ struct Fwd {
   int attn_block(const AttnW& a, const void* d, int ldd, void* out, int ldo, int R) {
     void* qkv = ws + plan.qkv;
     RC(gn(d, ldd, s(0), a.dim, nullptr, 0, a.ng, a.nb, R, a.dim, 1, 0));
+    if (a.linear && impl == 0 && k_linear_attention_qkv_applicable(a.dim, R * R, dt)) {
+      // to_qkv + both softmaxes + both einsums in one kernel: the 384-channel qkv tensor never exists
+      const double N = (double)R * R;
+      PROF(LDM_FAM_LINEAR_ATTENTION, (double)B * (2.0 * N * 3 * HIDDEN * a.dim + 4 * 2 * 2.0 * N * 32 * 32),
+           (double)B * N * (a.dim + HIDDEN) * es,
+           k_linear_attention_qkv(s(0), a.dim, a.dim, a.wqkv, qkv, B, R * R, dt, st));
+      RC(conv(qkv, HIDDEN, HIDDEN, nullptr, 0, 0, a.wout, a.bout, nullptr, 0, nullptr, 0, s(1), a.dim, a.dim, R, 1));
+      RC(gn(s(1), a.dim, out, ldo, d, ldd, a.og, a.ob, R, a.dim, 1, 0));  // x + GroupNorm(1,C)(to_out(...))
+      return 0;
+    }
     RC(conv(s(0), a.dim, a.dim, nullptr, 0, 0, a.wqkv, nullptr, nullptr, 0, nullptr, 0, qkv, 3 * HIDDEN, 3 * HIDDEN, R, 1));
     if (a.linear) {
       // 2 GEMMs of 32x32xN per head (ctx = k v^T, out = ctx^T q): 2 * 2*N*32*32 * 4 heads
