@@ -226,6 +226,66 @@ int ldm_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype
 int ldm_nchw_to_nhwc(const float* x, void* y, int batch, int channels, int hw, int dtype, void* stream);
 int ldm_nhwc_to_nchw(const void* x, int ldx, float* y, int batch, int channels, int hw, int dtype, void* stream);
 
+/* ---- training step: replaces autograd through src/UNet.py for DiffusionModelTrainer._train_epoch
+ * (src/DiffusionModelTrainer.py:36-67: eps = UNet(xt, t, y); loss = mse(noise, eps); loss.backward()).
+ * Each forward kernel has a backward counterpart; ldm_b200/train.py chains them with torch.autograd.Function so
+ * that loss.backward(), .grad on the 196 live parameters, Adam and wandb.watch keep working.  Activation tensors are
+ * NHWC in `dtype`; parameter gradients are fp32 in the PyTorch parameter layouts.  "accumulated" outputs must be
+ * zero-initialised by the caller (they are written with atomics). */
+
+/* dW[co][ci][kh][kw] (OIHW, accumulated) = sum_{n,h,w} dy[n,h,w,co] x[n,h+kh-p,w+kw-p,ci]; dbias[co] (accumulated) or NULL */
+int ldm_conv2d_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw_oihw, float* dbias,
+                     int batch, int height, int width, int ksize, int dtype, void* stream);
+/* filter for the data gradient: dx = ldm_conv2d(dy, w_dgrad) with the roles of Cin and Cout exchanged.
+ * w_packed [Cin][kh'][kw'][Cout] = w[co][ci][k-1-kh'][k-1-kw'] */
+int ldm_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin, int ksize, void* w_packed, int dtype, void* stream);
+/* out[c] (accumulated) = sum_r a[r][c] */
+int ldm_column_sum(const void* a, int lda, float* out, int rows, int cols, int dtype, void* stream);
+/* GroupNorm of (x + rowvec[n][c]) -- the ResNetBlock time-embedding add folded into block2's norm (src/UNet.py:88-96) */
+int ldm_group_norm_rowvec(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
+                          const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
+                          float eps, int silu, int dtype, void* workspace, void* stream);
+/* backward of y = [silu](GroupNorm(x + rowvec)): dx (overwritten), dgamma/dbeta (accumulated), drowvec [batch][ld] (overwritten) or NULL */
+int ldm_group_norm_backward(const void* x, int ldx, const void* dy, int lddy, const float* gamma, const float* beta,
+                            const float* rowvec, int ld_rowvec, void* dx, int lddx, float* dgamma, float* dbeta,
+                            float* drowvec, int ld_drowvec, int batch, int hw, int channels, int groups, float eps, int silu,
+                            int dtype, void* stream);
+int ldm_max_pool2x2_backward(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int batch, int height,
+                             int width, int channels, int dtype, void* stream);
+/* ConvTranspose2d(k2,s2) backward gather: out[n,h,w,q*C+c] = dy[n,2h+q/2,2w+q%2,c]; then dx / dW are a 1x1 dgrad / wgrad */
+int ldm_pixel_unshuffle2x2(const void* dy, int lddy, void* out, int batch, int height, int width, int channels, int dtype,
+                           void* stream);
+int ldm_linear_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int n_tokens, int dtype, void* stream);
+int ldm_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int n_tokens, int dtype, void* stream);
+/* initial 3x3 conv on the fp32 NCHW input (src/UNet.py:331) and its weight gradient; w_scratch: 9*cin*cout floats */
+int ldm_initial_conv(const float* x_nchw, const float* w_oihw, const float* bias, void* y, int batch, int cin, int cout,
+                     int height, int width, int dtype, float* w_scratch, void* stream);
+int ldm_initial_conv_wgrad(const float* x_nchw, const void* dy, float* dw_oihw, float* dbias, int batch, int cin, int cout,
+                           int height, int width, int dtype, void* stream);
+/* final 1x1 conv to fp32 NCHW (src/UNet.py:347) and its backward (dw/db accumulated, dx overwritten) */
+int ldm_final_conv(const void* x, int ldx, const float* w, const float* bias, float* y_nchw, int batch, int cin, int cout,
+                   int hw, int dtype, void* stream);
+int ldm_final_conv_backward(const float* dout_nchw, const void* x, int ldx, const float* w, void* dx, float* dw, float* db,
+                            int batch, int cin, int cout, int hw, int dtype, void* stream);
+/* time embedding + label embedding (src/UNet.py:23-44,263-268,373-376) and the stacked mlp_t projections (:70-73), fp32;
+ * parameter gradients accumulated */
+int64_t ldm_time_workspace_bytes(int batch, int D, int total);
+int ldm_time_embed(const int64_t* t, const int64_t* y, int y_len, const float* w1, const float* b1, const float* w3,
+                   const float* b3, const float* label_emb, float* temb, int batch, int D, void* workspace, void* stream);
+int ldm_time_embed_backward(const int64_t* t, const int64_t* y, int y_len, const float* w1, const float* b1, const float* w3,
+                            const float* dtemb, float* dw1, float* db1, float* dw3, float* db3, float* dlabel, int batch, int D,
+                            void* workspace, void* stream);
+int ldm_time_proj(const float* temb, const float* w, const float* bias, float* tproj, int batch, int D, int total,
+                  void* workspace, void* stream);
+int ldm_time_proj_backward(const float* temb, const float* w, const float* dtproj, float* dw, float* dbias, float* dtemb,
+                           int batch, int D, int total, void* workspace, void* stream);
+/* residual add and channel concat / split (src/UNet.py:20,99,245) */
+int ldm_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
+int ldm_copy_channels(const void* src, int ld_src, void* dst, int ld_dst, int channels, int64_t rows, int dtype, void* stream);
+/* LinearAttention with to_qkv fused (bf16, 64 input channels; src/UNet.py:145,149-163) */
+int ldm_linear_attention_qkv(const void* xn, int ldx, int cin, const void* wqkv_packed, void* out, int batch, int n_tokens,
+                             int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

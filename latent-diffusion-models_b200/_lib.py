@@ -79,6 +79,32 @@ SIGNATURES = {
     "ldm_max_pool2x2": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_linear_attention": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_attention": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    # ---- training step
+    "ldm_conv2d_wgrad": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, vp]),
+    "ldm_pack_conv_weight_dgrad": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
+    "ldm_column_sum": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_group_norm_rowvec": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp]),
+    "ldm_group_norm_backward": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int,
+                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, vp]),
+    "ldm_max_pool2x2_backward": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, vp]),
+    "ldm_pixel_unshuffle2x2": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_linear_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_initial_conv": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "ldm_initial_conv_wgrad": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_final_conv": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_final_conv_backward": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_time_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "ldm_time_embed": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]),
+    "ldm_time_embed_backward": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]),
+    "ldm_time_proj": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "ldm_time_proj_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "ldm_add": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int, vp]),
+    "ldm_copy_channels": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp]),
+    "ldm_linear_attention_qkv": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_nchw_to_nhwc": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_nhwc_to_nchw": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
 }

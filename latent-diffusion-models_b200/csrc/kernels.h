@@ -106,3 +106,30 @@ int k_copy_f32(const float* src, float* dst, int64_t n, cudaStream_t st);
 int k_pack_initial_weight(const float* w_oihw, int cout, int cin, float* out, cudaStream_t st);
 // dst = a + b (b may be null): fused conv2 + shortcut bias
 int k_add2_f32(const float* a, const float* b, float* dst, int n, cudaStream_t st);
+
+// ---- backward.cu (training step)
+int k_conv_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, float* dbias, int batch,
+                 int H, int W, int ksize, int dtype, cudaStream_t st);
+int k_colsum(const void* a, int lda, float* out, int M, int C, int dtype, cudaStream_t st);
+int k_pack_dgrad_weight(const float* w_oihw, int cout, int cin, int ksize, void* out, int dtype, cudaStream_t st);
+int k_group_norm_backward(const void* x, int ldx, const void* dy, int lddy, const float* gamma, const float* beta,
+                          const float* rowvec, int ld_rowvec, void* dx, int lddx, float* dgamma, float* dbeta,
+                          float* drowvec, int ld_drowvec, int batch, int hw, int channels, int groups, float eps, int silu,
+                          int dtype, cudaStream_t st);
+int k_maxpool2_backward(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int batch, int H, int W, int C,
+                        int dtype, cudaStream_t st);
+int k_unshuffle2(const void* dy, int lddy, void* out, int batch, int H, int W, int C, int dtype, cudaStream_t st);
+int k_linear_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int N, int dtype, cudaStream_t st);
+int k_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int N, int dtype, cudaStream_t st);
+int k_initial_conv_wgrad(const float* x, const void* dy, float* dw, float* dbias, int batch, int cin, int cout, int H, int W,
+                         int dtype, cudaStream_t st);
+int k_final_conv_backward(const float* dout, const void* x, int ldx, const float* w, void* dx, float* dw, float* db, int batch,
+                          int cin, int cout, int hw, int dtype, cudaStream_t st);
+int k_gemm_f32(const float* a, int64_t a_rs, int64_t a_cs, const float* b, int64_t b_rs, int64_t b_cs, float* c, int64_t c_rs,
+               int M, int N, int K, int accumulate, cudaStream_t st);
+int k_sinusoid(const int64_t* t, float* emb, int batch, int Din, cudaStream_t st);
+int k_ew(const float* x, const float* other, float* y, int rows, int cols, int mode, cudaStream_t st);
+int k_rows_scatter_add(const float* src, const int64_t* idx, int idx_len, float* table, int batch, int D, cudaStream_t st);
+int k_rows_gather_add(float* dst, const int64_t* idx, int idx_len, const float* table, int batch, int D, cudaStream_t st);
+int k_add(const void* a, const void* b, void* out, int64_t n, int dtype, cudaStream_t st);
+int k_copy_channels(const void* src, int lds, void* dst, int ldd, int C, int64_t rows, int dtype, cudaStream_t st);

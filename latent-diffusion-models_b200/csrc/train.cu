@@ -1,0 +1,164 @@
+// C ABI of the training-step kernels (declared in include/ldm_b200.h, "training step" section).
+#include "../../include/ldm_b200.h"
+#include "kernels.h"
+
+#define RC(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+
+extern "C" {
+
+int ldm_conv2d_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw_oihw, float* dbias,
+                     int batch, int height, int width, int ksize, int dtype, void* stream) {
+  LDM_REQUIRE(x && dy && dw_oihw, "ldm_conv2d_wgrad: null argument");
+  return k_conv_wgrad(x, ldx, cin, dy, lddy, cout, dw_oihw, dbias, batch, height, width, ksize, dtype, (cudaStream_t)stream);
+}
+int ldm_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin, int ksize, void* w_packed, int dtype, void* stream) {
+  LDM_REQUIRE(w_oihw && w_packed, "ldm_pack_conv_weight_dgrad: null argument");
+  return k_pack_dgrad_weight(w_oihw, cout, cin, ksize, w_packed, dtype, (cudaStream_t)stream);
+}
+int ldm_column_sum(const void* a, int lda, float* out, int rows, int cols, int dtype, void* stream) {
+  LDM_REQUIRE(a && out, "ldm_column_sum: null argument");
+  return k_colsum(a, lda, out, rows, cols, dtype, (cudaStream_t)stream);
+}
+int ldm_group_norm_rowvec(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
+                          const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
+                          float eps, int silu, int dtype, void* workspace, void* stream) {
+  LDM_REQUIRE(x && y && gamma && beta, "ldm_group_norm_rowvec: null argument");
+  return k_group_norm_rv(x, ldx, y, ldy, res, ldres, gamma, beta, rowvec, ld_rowvec, batch, hw, channels, groups, eps, silu,
+                         dtype, workspace, (cudaStream_t)stream);
+}
+int ldm_group_norm_backward(const void* x, int ldx, const void* dy, int lddy, const float* gamma, const float* beta,
+                            const float* rowvec, int ld_rowvec, void* dx, int lddx, float* dgamma, float* dbeta,
+                            float* drowvec, int ld_drowvec, int batch, int hw, int channels, int groups, float eps, int silu,
+                            int dtype, void* stream) {
+  LDM_REQUIRE(x && dy && gamma && beta && dx && dgamma && dbeta, "ldm_group_norm_backward: null argument");
+  return k_group_norm_backward(x, ldx, dy, lddy, gamma, beta, rowvec, ld_rowvec, dx, lddx, dgamma, dbeta, drowvec, ld_drowvec,
+                               batch, hw, channels, groups, eps, silu, dtype, (cudaStream_t)stream);
+}
+int ldm_max_pool2x2_backward(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int batch, int height,
+                             int width, int channels, int dtype, void* stream) {
+  LDM_REQUIRE(x && dy && dx, "ldm_max_pool2x2_backward: null argument");
+  return k_maxpool2_backward(x, ldx, dy, lddy, dx, lddx, batch, height, width, channels, dtype, (cudaStream_t)stream);
+}
+int ldm_pixel_unshuffle2x2(const void* dy, int lddy, void* out, int batch, int height, int width, int channels, int dtype,
+                           void* stream) {
+  LDM_REQUIRE(dy && out, "ldm_pixel_unshuffle2x2: null argument");
+  return k_unshuffle2(dy, lddy, out, batch, height, width, channels, dtype, (cudaStream_t)stream);
+}
+int ldm_linear_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int n_tokens, int dtype, void* stream) {
+  LDM_REQUIRE(qkv && dout && dqkv, "ldm_linear_attention_backward: null argument");
+  return k_linear_attention_backward(qkv, dout, dqkv, batch, n_tokens, dtype, (cudaStream_t)stream);
+}
+int ldm_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int n_tokens, int dtype, void* stream) {
+  LDM_REQUIRE(qkv && dout && dqkv, "ldm_attention_backward: null argument");
+  return k_attention_backward(qkv, dout, dqkv, batch, n_tokens, dtype, (cudaStream_t)stream);
+}
+int ldm_initial_conv(const float* x_nchw, const float* w_oihw, const float* bias, void* y, int batch, int cin, int cout, int height,
+                     int width, int dtype, float* w_scratch, void* stream) {
+  LDM_REQUIRE(x_nchw && w_oihw && bias && y && w_scratch, "ldm_initial_conv: null argument");
+  RC(k_pack_initial_weight(w_oihw, cout, cin, w_scratch, (cudaStream_t)stream));
+  return k_initial_conv(x_nchw, batch, w_scratch, bias, y, batch, cin, cout, height, width, dtype, (cudaStream_t)stream);
+}
+int ldm_initial_conv_wgrad(const float* x_nchw, const void* dy, float* dw_oihw, float* dbias, int batch, int cin, int cout, int height,
+                           int width, int dtype, void* stream) {
+  LDM_REQUIRE(x_nchw && dy && dw_oihw, "ldm_initial_conv_wgrad: null argument");
+  return k_initial_conv_wgrad(x_nchw, dy, dw_oihw, dbias, batch, cin, cout, height, width, dtype, (cudaStream_t)stream);
+}
+int ldm_final_conv(const void* x, int ldx, const float* w, const float* bias, float* y_nchw, int batch, int cin, int cout, int hw,
+                   int dtype, void* stream) {
+  LDM_REQUIRE(x && w && bias && y_nchw, "ldm_final_conv: null argument");
+  return k_final_conv(x, ldx, w, bias, y_nchw, batch, cin, cout, hw, dtype, (cudaStream_t)stream);
+}
+int ldm_final_conv_backward(const float* dout_nchw, const void* x, int ldx, const float* w, void* dx, float* dw, float* db, int batch,
+                            int cin, int cout, int hw, int dtype, void* stream) {
+  LDM_REQUIRE(dout_nchw && x && w && dx && dw && db, "ldm_final_conv_backward: null argument");
+  return k_final_conv_backward(dout_nchw, x, ldx, w, dx, dw, db, batch, cin, cout, hw, dtype, (cudaStream_t)stream);
+}
+
+// ---- time embedding (src/UNet.py:23-44,263-268,373-376) and the mlp_t projections (:70-73,90-93), fp32
+int64_t ldm_time_workspace_bytes(int batch, int D, int total) {
+  return (int64_t)batch * (D / 4 + 4 * (int64_t)D + total) * 4 + 1024;
+}
+static void time_ws(float* ws, int batch, int D, float*& emb, float*& pre1, float*& h1, float*& t0, float*& t1) {
+  emb = ws; pre1 = emb + (int64_t)batch * (D / 4); h1 = pre1 + (int64_t)batch * D; t0 = h1 + (int64_t)batch * D;
+  t1 = t0 + (int64_t)batch * D;
+}
+int ldm_time_embed(const int64_t* t, const int64_t* y, int y_len, const float* w1, const float* b1, const float* w3,
+                   const float* b3, const float* label_emb, float* temb, int batch, int D, void* workspace, void* stream) {
+  LDM_REQUIRE(t && w1 && b1 && w3 && b3 && temb && workspace, "ldm_time_embed: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  float *emb, *pre1, *h1, *t0, *t1;
+  time_ws((float*)workspace, batch, D, emb, pre1, h1, t0, t1);
+  const int Din = D / 4;
+  RC(k_sinusoid(t, emb, batch, Din, st));
+  RC(k_gemm_f32(emb, Din, 1, w1, 1, Din, pre1, D, batch, D, Din, 0, st));   // pre1 = emb w1^T
+  RC(k_ew(pre1, b1, h1, batch, D, 1, st));                                  // h1 = gelu(pre1 + b1)
+  RC(k_gemm_f32(h1, D, 1, w3, 1, D, temb, D, batch, D, D, 0, st));          // temb = h1 w3^T
+  RC(k_ew(temb, b3, temb, batch, D, 0, st));
+  if (y && y_len > 0) RC(k_rows_gather_add(temb, y, y_len, label_emb, batch, D, st));
+  return 0;
+}
+// gradients are ACCUMULATED into dw1/db1/dw3/db3/dlabel (zero them first)
+int ldm_time_embed_backward(const int64_t* t, const int64_t* y, int y_len, const float* w1, const float* b1, const float* w3,
+                            const float* dtemb, float* dw1, float* db1, float* dw3, float* db3, float* dlabel, int batch, int D,
+                            void* workspace, void* stream) {
+  LDM_REQUIRE(t && w1 && b1 && w3 && dtemb && dw1 && db1 && dw3 && db3 && workspace, "ldm_time_embed_backward: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  float *emb, *pre1, *h1, *t0, *t1;
+  time_ws((float*)workspace, batch, D, emb, pre1, h1, t0, t1);
+  const int Din = D / 4;
+  RC(k_sinusoid(t, emb, batch, Din, st));
+  RC(k_gemm_f32(emb, Din, 1, w1, 1, Din, pre1, D, batch, D, Din, 0, st));
+  RC(k_ew(pre1, b1, h1, batch, D, 1, st));                                   // h1 = gelu(pre1 + b1)
+  RC(k_ew(pre1, b1, pre1, batch, D, 0, st));                                 // pre1 += b1 (the GELU's input)
+  // label embedding rows, output bias, second Linear
+  if (y && y_len > 0 && dlabel) RC(k_rows_scatter_add(dtemb, y, y_len, dlabel, batch, D, st));
+  RC(k_colsum(dtemb, D, db3, batch, D, LDM_DT_F32, st));
+  RC(k_gemm_f32(dtemb, 1, D, h1, D, 1, dw3, D, D, D, batch, 1, st));         // dw3[o][k] += sum_b dtemb[b][o] h1[b][k]
+  RC(k_gemm_f32(dtemb, D, 1, w3, D, 1, t0, D, batch, D, D, 0, st));          // dh1 = dtemb w3
+  RC(k_ew(pre1, t0, t1, batch, D, 3, st));                                   // dpre1 = dh1 * gelu'(pre1)
+  RC(k_colsum(t1, D, db1, batch, D, LDM_DT_F32, st));
+  RC(k_gemm_f32(t1, 1, D, emb, Din, 1, dw1, Din, D, Din, batch, 1, st));     // dw1[o][i] += sum_b dpre1[b][o] emb[b][i]
+  return 0;
+}
+
+// tproj = SiLU(temb) w^T + bias   with w = the mlp_t weights of all blocks stacked: [total][D]
+int ldm_time_proj(const float* temb, const float* w, const float* bias, float* tproj, int batch, int D, int total,
+                  void* workspace, void* stream) {
+  LDM_REQUIRE(temb && w && bias && tproj && workspace, "ldm_time_proj: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* s = (float*)workspace;
+  RC(k_ew(temb, nullptr, s, batch, D, 2, st));
+  RC(k_gemm_f32(s, D, 1, w, 1, D, tproj, total, batch, total, D, 0, st));
+  RC(k_ew(tproj, bias, tproj, batch, total, 0, st));
+  return 0;
+}
+// dw / dbias are ACCUMULATED; dtemb is overwritten
+int ldm_time_proj_backward(const float* temb, const float* w, const float* dtproj, float* dw, float* dbias, float* dtemb,
+                           int batch, int D, int total, void* workspace, void* stream) {
+  LDM_REQUIRE(temb && w && dtproj && dw && dbias && dtemb && workspace, "ldm_time_proj_backward: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* s = (float*)workspace;
+  float* ds = s + (int64_t)batch * D;
+  RC(k_ew(temb, nullptr, s, batch, D, 2, st));
+  RC(k_colsum(dtproj, total, dbias, batch, total, LDM_DT_F32, st));
+  RC(k_gemm_f32(dtproj, 1, total, s, D, 1, dw, D, total, D, batch, 1, st));  // dw[o][k] += sum_b dtproj[b][o] s[b][k]
+  RC(k_gemm_f32(dtproj, total, 1, w, D, 1, ds, D, batch, D, total, 0, st));  // ds = dtproj w
+  RC(k_ew(temb, ds, dtemb, batch, D, 4, st));                                // dtemb = ds * silu'(temb)
+  return 0;
+}
+
+int ldm_linear_attention_qkv(const void* xn, int ldx, int cin, const void* wqkv_packed, void* out, int batch, int n_tokens,
+                             int dtype, void* stream) {
+  LDM_REQUIRE(xn && wqkv_packed && out, "ldm_linear_attention_qkv: null argument");
+  return k_linear_attention_qkv(xn, ldx, cin, wqkv_packed, out, batch, n_tokens, dtype, (cudaStream_t)stream);
+}
+int ldm_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream) {
+  LDM_REQUIRE(a && b && out, "ldm_add: null argument");
+  return k_add(a, b, out, n, dtype, (cudaStream_t)stream);
+}
+int ldm_copy_channels(const void* src, int ld_src, void* dst, int ld_dst, int channels, int64_t rows, int dtype, void* stream) {
+  LDM_REQUIRE(src && dst, "ldm_copy_channels: null argument");
+  return k_copy_channels(src, ld_src, dst, ld_dst, channels, rows, dtype, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,8 +1,413 @@
-"""Training-step path (autograd bridge).  Filled in by the backward kernels; see DESIGN.md."""
+"""Training-step path: ``UNet.forward`` with gradients (src/DiffusionModelTrainer.py:36-67).
+
+The reference gets its backward pass from autograd over ATen/cuDNN.  Here every forward kernel of the C ABI has a
+hand-written backward kernel (csrc/backward.cu) and the two are tied together by ``torch.autograd.Function`` -- autograd
+is used for what it is (the graph, saved tensors, gradient fan-in at the residual / concat joins); every tensor
+operation on the path is a kernel of libldm_b200.so.  Activations are NHWC in the model's compute dtype, parameters stay
+the fp32 ``nn.Parameter``s of the 200-key ``state_dict`` and receive fp32 ``.grad`` (so Adam, GradScaler-free bf16
+training, ``wandb.watch`` and checkpointing behave as in the reference).  The four dead ``bottleneck.res{1,2}.mlp_t``
+tensors get no gradient, exactly as in the reference.
+"""
 from __future__ import annotations
 
+from typing import Optional
 
-def unet_autograd_forward(model, x, t, y):
-    raise NotImplementedError(
-        "ldm_b200.UNet: the backward kernels are not built into this library; call under torch.no_grad() "
-        "for eps-prediction / sampling")
+import torch
+from torch.autograd import Function
+
+from . import _lib, ops
+
+_HIDDEN = 128
+_EPS = 1e-5
+
+
+def _st():
+    return _lib.stream_ptr()
+
+
+def _lb():
+    return _lib.load()
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class _Conv(Function):
+    """F.conv2d (3x3 pad 1 / 1x1) on NHWC; dgrad = the same implicit-GEMM kernel with the flipped, transposed filter."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, impl):
+        k = w.shape[2]
+        dt = "bf16" if x.dtype == torch.bfloat16 else "fp32"
+        wp = ops.pack_conv_weight(w.detach(), dt)
+        y = ops.conv2d(x, wp, k, bias=b.detach() if b is not None else None, impl=impl)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias, ctx.impl, ctx.dt = b is not None, impl, dt
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _c(dy)
+        cout, cin, k, _ = w.shape
+        B, H, W, _ = x.shape
+        lib = _lb()
+        wd = torch.empty(cin, k * k * cout, dtype=x.dtype, device=x.device)
+        _lib.check(lib.ldm_pack_conv_weight_dgrad(w.data_ptr(), cout, cin, k, wd.data_ptr(), ops._dt(x), _st()))
+        dx = ops.conv2d(dy, wd, k, impl=ctx.impl)
+        dw = torch.zeros_like(w)
+        db = torch.zeros(cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+        _lib.check(lib.ldm_conv2d_wgrad(x.data_ptr(), x.stride(2), cin, dy.data_ptr(), dy.stride(2), cout, dw.data_ptr(),
+                                        _lib.ptr(db), B, H, W, k, ops._dt(x), _st()))
+        return dx, dw, db, None
+
+
+class _GroupNorm(Function):
+    """[SiLU](GroupNorm(x + rowvec)); rowvec is the ResNetBlock's time-embedding projection (src/UNet.py:88-96)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, silu, rowvec):
+        B, H, W, Cc = x.shape
+        y = torch.empty_like(x)
+        lib = _lb()
+        ws = torch.empty(lib.ldm_group_norm_workspace_bytes(B, groups), dtype=torch.uint8, device=x.device)
+        rv = rowvec.detach() if rowvec is not None else None
+        _lib.check(lib.ldm_group_norm_rowvec(x.data_ptr(), x.stride(2), y.data_ptr(), y.stride(2), None, 0, gamma.data_ptr(),
+                                             beta.data_ptr(), _lib.ptr(rv), rv.stride(0) if rv is not None else 0, B, H * W,
+                                             Cc, groups, _EPS, int(silu), ops._dt(x), ws.data_ptr(), _st()))
+        ctx.save_for_backward(x, gamma, beta, rowvec if rowvec is not None else torch.empty(0))
+        ctx.groups, ctx.silu, ctx.has_rv = groups, silu, rowvec is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, rowvec = ctx.saved_tensors
+        dy = _c(dy)
+        B, H, W, Cc = x.shape
+        dx = torch.empty_like(x)
+        dg = torch.zeros_like(gamma)
+        db = torch.zeros_like(beta)
+        rv = rowvec if ctx.has_rv else None
+        drv = torch.empty(B, Cc, dtype=torch.float32, device=x.device) if ctx.has_rv else None
+        _lib.check(_lb().ldm_group_norm_backward(x.data_ptr(), x.stride(2), dy.data_ptr(), dy.stride(2), gamma.data_ptr(),
+                                                 beta.data_ptr(), _lib.ptr(rv), rv.stride(0) if rv is not None else 0,
+                                                 dx.data_ptr(), dx.stride(2), dg.data_ptr(), db.data_ptr(), _lib.ptr(drv),
+                                                 Cc, B, H * W, Cc, ctx.groups, _EPS, int(ctx.silu), ops._dt(x), _st()))
+        return dx, dg, db, None, None, drv
+
+
+class _MaxPool(Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.max_pool2x2(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = _c(dy)
+        B, H, W, Cc = x.shape
+        dx = torch.empty_like(x)
+        _lib.check(_lb().ldm_max_pool2x2_backward(x.data_ptr(), x.stride(2), dy.data_ptr(), dy.stride(2), dx.data_ptr(),
+                                                  dx.stride(2), B, H, W, Cc, ops._dt(x), _st()))
+        return dx
+
+
+class _ConvT(Function):
+    """ConvTranspose2d(k2, s2): forward = [M, 4*Cout] GEMM + pixel shuffle; backward = gather + 1x1 dgrad / wgrad."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, impl):
+        ctx.save_for_backward(x, w)
+        ctx.impl = impl
+        return ops.conv_transpose2x2(x, w.detach(), b.detach(), impl=impl)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _c(dy)
+        B, H, W, cin = x.shape
+        cout = w.shape[1]
+        lib = _lb()
+        dyq = torch.empty(B, H, W, 4 * cout, dtype=x.dtype, device=x.device)
+        _lib.check(lib.ldm_pixel_unshuffle2x2(dy.data_ptr(), dy.stride(2), dyq.data_ptr(), B, H, W, cout, ops._dt(x), _st()))
+        # dx[m][ci] = sum_{q,co} dyq[m][q*Cout+co] w[ci][co][q]: a 1x1 conv whose packed filter is [ci][(q,co)]
+        wd = w.detach().permute(0, 2, 3, 1).reshape(cin, 4 * cout).to(x.dtype).contiguous()   # layout only
+        dx = ops.conv2d(dyq, wd, 1, impl=ctx.impl)
+        # dW'[(q,co)][ci] = sum_m dyq[m][(q,co)] x[m][ci]  -> back to the IOHW parameter layout
+        dwq = torch.zeros(4 * cout, cin, dtype=torch.float32, device=x.device)
+        _lib.check(lib.ldm_conv2d_wgrad(x.data_ptr(), x.stride(2), cin, dyq.data_ptr(), 4 * cout, 4 * cout, dwq.data_ptr(),
+                                        None, B, H, W, 1, ops._dt(x), _st()))
+        dw = dwq.view(2, 2, cout, cin).permute(3, 2, 0, 1).contiguous()                        # layout only
+        db = torch.zeros(cout, dtype=torch.float32, device=x.device)
+        _lib.check(lib.ldm_column_sum(dy.data_ptr(), dy.stride(2), db.data_ptr(), B * 4 * H * W, cout, ops._dt(x), _st()))
+        return dx, dw, db, None
+
+
+class _LinAttn(Function):
+    @staticmethod
+    def forward(ctx, qkv):
+        ctx.save_for_backward(qkv)
+        return ops.linear_attention(qkv)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (qkv,) = ctx.saved_tensors
+        dout = _c(dout)
+        B, H, W, _ = qkv.shape
+        dqkv = torch.empty_like(qkv)
+        _lib.check(_lb().ldm_linear_attention_backward(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, H * W,
+                                                       ops._dt(qkv), _st()))
+        return dqkv
+
+
+class _Attn(Function):
+    @staticmethod
+    def forward(ctx, qkv):
+        ctx.save_for_backward(qkv)
+        return ops.attention(qkv)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (qkv,) = ctx.saved_tensors
+        dout = _c(dout)
+        B, H, W, _ = qkv.shape
+        dqkv = torch.empty_like(qkv)
+        _lib.check(_lb().ldm_attention_backward(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, H * W, ops._dt(qkv), _st()))
+        return dqkv
+
+
+class _InitialConv(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, dtype):
+        B, Cin, H, W = x.shape
+        cout = w.shape[0]
+        y = torch.empty(B, H, W, cout, dtype=ops._TORCH_DT[dtype], device=x.device)
+        scratch = torch.empty(9 * Cin * cout, dtype=torch.float32, device=x.device)
+        _lib.check(_lb().ldm_initial_conv(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), B, Cin, cout, H, W,
+                                          ops._dt(y), scratch.data_ptr(), _st()))
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _c(dy)
+        B, Cin, H, W = x.shape
+        cout = w.shape[0]
+        dw = torch.zeros_like(w)
+        db = torch.zeros(cout, dtype=torch.float32, device=x.device)
+        _lib.check(_lb().ldm_initial_conv_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), B, Cin, cout, H, W,
+                                                ops._dt(dy), _st()))
+        return None, dw, db, None     # the noised image x_t needs no gradient (src/DDPM.py:133-149)
+
+
+class _FinalConv(Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        B, H, W, cin = x.shape
+        cout = w.shape[0]
+        y = torch.empty(B, cout, H, W, dtype=torch.float32, device=x.device)
+        _lib.check(_lb().ldm_final_conv(x.data_ptr(), x.stride(2), w.data_ptr(), b.data_ptr(), y.data_ptr(), B, cin, cout,
+                                        H * W, ops._dt(x), _st()))
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        dout = _c(dout.to(torch.float32))
+        B, H, W, cin = x.shape
+        cout = w.shape[0]
+        dx = torch.empty_like(x)
+        dw = torch.zeros_like(w)
+        db = torch.zeros(cout, dtype=torch.float32, device=x.device)
+        _lib.check(_lb().ldm_final_conv_backward(dout.data_ptr(), x.data_ptr(), x.stride(2), w.data_ptr(), dx.data_ptr(),
+                                                 dw.data_ptr(), db.data_ptr(), B, cin, cout, H * W, ops._dt(x), _st()))
+        return dx, dw, db
+
+
+def _time_ws(B, D, total, dev):
+    return torch.empty(_lb().ldm_time_workspace_bytes(B, D, total), dtype=torch.uint8, device=dev)
+
+
+class _TimeEmbed(Function):
+    @staticmethod
+    def forward(ctx, t, y, w1, b1, w3, b3, label):
+        B, D = t.numel(), w3.shape[0]
+        temb = torch.empty(B, D, dtype=torch.float32, device=w1.device)
+        ws = _time_ws(B, D, 0, w1.device)
+        _lib.check(_lb().ldm_time_embed(t.data_ptr(), _lib.ptr(y), y.numel() if y is not None else 0, w1.data_ptr(),
+                                        b1.data_ptr(), w3.data_ptr(), b3.data_ptr(), _lib.ptr(label), temb.data_ptr(), B, D,
+                                        ws.data_ptr(), _st()))
+        ctx.save_for_backward(t, y if y is not None else torch.empty(0), w1, b1, w3, label if label is not None else torch.empty(0))
+        ctx.has_y = y is not None
+        return temb
+
+    @staticmethod
+    def backward(ctx, dtemb):
+        t, y, w1, b1, w3, label = ctx.saved_tensors
+        dtemb = _c(dtemb)
+        B, D = dtemb.shape
+        dw1, db1, dw3 = torch.zeros_like(w1), torch.zeros_like(b1), torch.zeros_like(w3)
+        db3 = torch.zeros(D, dtype=torch.float32, device=w1.device)
+        dlabel = torch.zeros_like(label) if ctx.has_y else None
+        ws = _time_ws(B, D, 0, w1.device)
+        yy = y if ctx.has_y else None
+        _lib.check(_lb().ldm_time_embed_backward(t.data_ptr(), _lib.ptr(yy), yy.numel() if yy is not None else 0,
+                                                 w1.data_ptr(), b1.data_ptr(), w3.data_ptr(), dtemb.data_ptr(),
+                                                 dw1.data_ptr(), db1.data_ptr(), dw3.data_ptr(), db3.data_ptr(),
+                                                 _lib.ptr(dlabel), B, D, ws.data_ptr(), _st()))
+        return None, None, dw1, db1, dw3, db3, dlabel
+
+
+class _TimeProj(Function):
+    @staticmethod
+    def forward(ctx, temb, w, b):
+        B, D = temb.shape
+        total = w.shape[0]
+        out = torch.empty(B, total, dtype=torch.float32, device=temb.device)
+        ws = _time_ws(B, D, total, temb.device)
+        _lib.check(_lb().ldm_time_proj(temb.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), B, D, total,
+                                       ws.data_ptr(), _st()))
+        ctx.save_for_backward(temb, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        temb, w = ctx.saved_tensors
+        dout = _c(dout)
+        B, D = temb.shape
+        total = w.shape[0]
+        dw = torch.zeros_like(w)
+        db = torch.zeros(total, dtype=torch.float32, device=temb.device)
+        dtemb = torch.empty_like(temb)
+        ws = _time_ws(B, D, total, temb.device)
+        _lib.check(_lb().ldm_time_proj_backward(temb.data_ptr(), w.data_ptr(), dout.data_ptr(), dw.data_ptr(), db.data_ptr(),
+                                                dtemb.data_ptr(), B, D, total, ws.data_ptr(), _st()))
+        return dtemb, dw, db
+
+
+class _Add(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        out = torch.empty_like(a)
+        _lib.check(_lb().ldm_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), ops._dt(a), _st()))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+class _Cat(Function):
+    """torch.cat((a, b), channel) on NHWC (src/UNet.py:245)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        B, H, W, ca = a.shape
+        cb = b.shape[3]
+        out = torch.empty(B, H, W, ca + cb, dtype=a.dtype, device=a.device)
+        lib, rows = _lb(), B * H * W
+        _lib.check(lib.ldm_copy_channels(a.data_ptr(), ca, out.data_ptr(), ca + cb, ca, rows, ops._dt(a), _st()))
+        _lib.check(lib.ldm_copy_channels(b.data_ptr(), cb, out.data_ptr() + ca * a.element_size(), ca + cb, cb, rows,
+                                         ops._dt(a), _st()))
+        ctx.ca, ctx.cb = ca, cb
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _c(g)
+        B, H, W, ct = g.shape
+        ca, cb = ctx.ca, ctx.cb
+        da = torch.empty(B, H, W, ca, dtype=g.dtype, device=g.device)
+        db = torch.empty(B, H, W, cb, dtype=g.dtype, device=g.device)
+        lib, rows = _lb(), B * H * W
+        _lib.check(lib.ldm_copy_channels(g.data_ptr(), ct, da.data_ptr(), ca, ca, rows, ops._dt(g), _st()))
+        _lib.check(lib.ldm_copy_channels(g.data_ptr() + ca * g.element_size(), ct, db.data_ptr(), cb, cb, rows, ops._dt(g), _st()))
+        return da, db
+
+
+# ------------------------------------------------------------------------------------------------ the network
+def _resblock(p, x, tproj_slice, impl):
+    """ResNetBlock.forward, src/UNet.py:85-99."""
+    h = _GroupNorm.apply(x, p.block1.norm.weight, p.block1.norm.bias, 8, True, None)
+    h = _Conv.apply(h, p.block1.conv2d.weight, p.block1.conv2d.bias, impl)
+    h = _GroupNorm.apply(h, p.block2.norm.weight, p.block2.norm.bias, 8, True, tproj_slice)   # h + mlp_t(t), then block2
+    h = _Conv.apply(h, p.block2.conv2d.weight, p.block2.conv2d.bias, impl)
+    sc = _Conv.apply(x, p.shortcut.weight, p.shortcut.bias, impl) if hasattr(p, "shortcut") else x
+    return _Add.apply(h, sc)
+
+
+def _attn_site(site, x, linear, impl):
+    """Residual(PreNorm(dim, LinearAttention | Attention)), src/UNet.py:14-20,102-164."""
+    pre, att = site.fn, site.fn.fn
+    xn = _GroupNorm.apply(x, pre.norm.weight, pre.norm.bias, 1, False, None)
+    qkv = _Conv.apply(xn, att.to_qkv.weight, None, impl)
+    if linear:
+        o = _LinAttn.apply(qkv)
+        o = _Conv.apply(o, att.to_out[0].weight, att.to_out[0].bias, impl)
+        o = _GroupNorm.apply(o, att.to_out[1].weight, att.to_out[1].bias, 1, False, None)
+    else:
+        o = _Attn.apply(qkv)
+        o = _Conv.apply(o, att.to_out.weight, att.to_out.bias, impl)
+    return _Add.apply(o, x)
+
+
+def unet_autograd_forward(model, x_noisy: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor]):
+    """UNet.forward (src/UNet.py:361-389) with gradients to every live parameter."""
+    dev = x_noisy.device
+    for prm in model.parameters():
+        if prm.device != dev or prm.dtype != torch.float32:
+            raise _lib.LdmError("UNet parameters must be fp32 tensors on the input's CUDA device (call model.to(device))")
+    dt, impl = model.compute_dtype, model.conv_impl
+    dt = "bf16" if _lib.DTYPES[dt] == _lib.BF16 else "fp32"
+    x = _c(x_noisy.detach().to(torch.float32))
+    t = _c(t.detach().to(device=dev, dtype=torch.int64))
+    if y is not None:
+        if model.num_classes is None:
+            raise ValueError("labels given but num_classes is None")
+        y = _c(y.detach().to(device=dev, dtype=torch.int64))
+        if y.numel() not in (1, x.shape[0]):
+            raise ValueError("labels must have 1 or batch entries (src/UNet.py:375-376)")
+    L = len(model.channel_multipliers)
+    if x.shape[2] % (1 << L) != 0 or x.shape[2] != x.shape[3]:
+        raise _lib.LdmError(f"image size {tuple(x.shape[2:])} is not divisible by 2^{L} (the reference fails at torch.cat)")
+    tproj, offs = None, {}
+    if model.with_time_emb:
+        tm = model.time_emb.time_mlp
+        temb = _TimeEmbed.apply(t, y, tm[1].weight, tm[1].bias, tm[3].weight, tm[3].bias,
+                                model.label_emb.weight if (y is not None) else None)
+        blocks = [lvl[0] for lvl in model.encoder.downs] + [lvl[0] for lvl in model.decoder.ups]   # BottleNeck never gets t
+        off = 0
+        for bl in blocks:
+            offs[id(bl)] = (off, off + bl.mlp_t[1].weight.shape[0])
+            off += bl.mlp_t[1].weight.shape[0]
+        wcat = torch.cat([bl.mlp_t[1].weight for bl in blocks], 0)     # parameter plumbing (differentiable views)
+        bcat = torch.cat([bl.mlp_t[1].bias for bl in blocks], 0)
+        tproj = _TimeProj.apply(temb, wcat, bcat)
+
+    def tslice(bl):
+        if tproj is None:
+            return None
+        a, b = offs[id(bl)]
+        return tproj[:, a:b]
+
+    h = _InitialConv.apply(x, model.initial_conv.weight, model.initial_conv.bias, dt)
+    skips = []
+    for res, attn in model.encoder.downs:
+        h = _resblock(res, h, tslice(res), impl)
+        h = _attn_site(attn, h, True, impl)
+        skips.append(h)
+        h = _MaxPool.apply(h)
+    h = _resblock(model.bottleneck.res1, h, None, impl)
+    h = _attn_site(model.bottleneck.attn, h, False, impl)
+    h = _resblock(model.bottleneck.res2, h, None, impl)
+    for res, attn, up in model.decoder.ups:
+        h = _ConvT.apply(h, up.weight, up.bias, impl)
+        h = _Cat.apply(h, skips.pop())
+        h = _resblock(res, h, tslice(res), impl)
+        h = _attn_site(attn, h, True, impl)
+    h = _resblock(model.final_conv[0], h, None, impl)
+    return _FinalConv.apply(h, model.final_conv[1].weight.view(model.out_channels, model.channels), model.final_conv[1].bias)

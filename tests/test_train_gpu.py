@@ -1,0 +1,129 @@
+"""GPU: the training step (q_sample -> UNet eps -> MSE -> backward) against autograd over the CPU oracle and the
+gradient fingerprints of the unmodified reference (golden G5)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel_l2
+from test_unet_gpu import make_model, dev
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _oracle_grads(sd, xt, t, y, noise):
+    from oracle import unet_oracle as U
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    eps = U.unet_forward(p, xt, t, y)
+    loss = torch.nn.functional.mse_loss(noise, eps)
+    loss.backward()
+    return float(loss), eps.detach(), {k: v.grad for k, v in p.items()}
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-3), ("bf16", 8e-2)])
+def test_train_step_gradients_vs_reference(dtype, tol):
+    """Golden G5: same inputs as the reference run; loss, eps and per-parameter gradient fingerprints."""
+    g = golden("g5_train_grads.npz")
+    m, sd = make_model(dtype, seed=int(g["weight_seed"]))
+    m.train()
+    xt, t, y, noise = (T(g[k]).to(dev()) for k in ("xt", "t", "y", "noise"))
+    eps = m(xt, t, y)
+    assert eps.requires_grad and eps.dtype == torch.float32
+    loss = torch.nn.functional.mse_loss(noise, eps)     # src/DiffusionModelTrainer.py:48 (input=noise, target=pred)
+    loss.backward()
+    assert rel_l2(eps, T(g["eps"])) < (1e-4 if dtype == "fp32" else 2e-2)
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < (1e-4 if dtype == "fp32" else 2e-2)
+    names = [str(n) for n in g["names"]]
+    params = dict(m.named_parameters())
+    assert list(params) == names
+    worst = 0.0
+    for i, n in enumerate(names):
+        p = params[n]
+        if not g["has_grad"][i]:
+            assert p.grad is None, f"{n} is dead in the reference (BottleNeck never passes t) and must stay without grad"
+            continue
+        assert p.grad is not None and p.grad.shape == p.shape and p.grad.dtype == torch.float32, n
+        want = float(g["grad_norm"][i])
+        got = float(p.grad.double().norm())
+        err = abs(got - want) / max(want, 1e-12)
+        worst = max(worst, err)
+        assert err < tol, f"|grad| of {n}: {got} vs {want}"
+        if dtype == "fp32":
+            head = p.grad.reshape(-1)[:4].cpu().numpy()
+            ref = g["grad_head"][i][:head.size]
+            assert np.allclose(head, ref, rtol=5e-3, atol=5e-3 * want / max(p.numel() ** 0.5, 1.0) + 1e-7), n
+    print("worst |grad| error", worst)
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-3), ("bf16", 1e-1)])
+def test_full_gradients_vs_oracle_autograd(dtype, tol):
+    """Every gradient tensor, element-wise, against autograd through the CPU oracle (broadcast label, batch 2)."""
+    m, sd = make_model(dtype, seed=3)
+    gen = torch.Generator().manual_seed(11)
+    xt = torch.randn(2, 3, 32, 32, generator=gen)
+    noise = torch.randn(2, 3, 32, 32, generator=gen)
+    t = torch.tensor([17, 903])
+    y = torch.tensor([4])
+    loss_ref, eps_ref, grads = _oracle_grads(sd, xt, t, y, noise)
+    eps = m(xt.to(dev()), t.to(dev()), y.to(dev()))
+    loss = torch.nn.functional.mse_loss(noise.to(dev()), eps)
+    loss.backward()
+    assert abs(float(loss) - loss_ref) / loss_ref < tol
+    bad = []
+    for n, p in m.named_parameters():
+        ref = grads[n]
+        if ref is None:
+            assert p.grad is None, n
+            continue
+        e = rel_l2(p.grad, ref)
+        if e > tol:
+            bad.append((n, e))
+    assert not bad, bad[:10]
+
+
+def test_unconditional_and_no_label_paths():
+    m, sd = make_model("fp32", seed=1)
+    gen = torch.Generator().manual_seed(2)
+    xt = torch.randn(2, 3, 32, 32, generator=gen)
+    noise = torch.randn(2, 3, 32, 32, generator=gen)
+    t = torch.tensor([5, 500])
+    _, _, grads = _oracle_grads(sd, xt, t, None, noise)      # targets = None: the trainer's 10 % label drop (:44-46)
+    loss = torch.nn.functional.mse_loss(noise.to(dev()), m(xt.to(dev()), t.to(dev())))
+    loss.backward()
+    assert m.label_emb.weight.grad is None
+    for n, p in m.named_parameters():
+        if grads[n] is not None:
+            assert rel_l2(p.grad, grads[n]) < 2e-3, n
+
+
+def test_adam_steps_reduce_the_loss():
+    """Trainer._get_optimizer (src/Trainer.py:68-71): Adam(lr) on the fp32 parameters, bf16 kernels."""
+    import ldm_b200
+    m, _ = make_model("bf16", seed=0)
+    d = ldm_b200.Diffusion(1000, dev())
+    opt = torch.optim.Adam(m.parameters(), lr=5e-4)
+    gen = torch.Generator().manual_seed(0)
+    x0 = (torch.rand(8, 3, 32, 32, generator=gen) * 2 - 1).to(dev())
+    y = torch.randint(0, 10, (8,), generator=gen).to(dev())
+    noise = torch.randn(8, 3, 32, 32, generator=gen).to(dev())
+    t = torch.randint(0, 1000, (8,), generator=gen).to(dev())
+    losses = []
+    for _ in range(8):
+        xt = d.q_sample(x0, t, eps=noise)
+        loss = torch.nn.functional.mse_loss(noise, m(xt, t, y))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < 0.7 * losses[0], losses
+    # the re-packed weights follow the optimiser: an eval-mode forward sees the updated parameters
+    with torch.no_grad():
+        e1 = m(xt, t, y)
+    assert abs(float(torch.nn.functional.mse_loss(noise, e1)) - losses[-1]) < 0.5 * losses[0]
