@@ -158,7 +158,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, batch, world):
@@ -167,6 +167,56 @@ def workload_config(args, batch, world):
             "batch_per_gpu": batch, "global_batch": batch * world, "n_steps": args.n_steps, "cfg_scale": args.cfg_scale,
             "image": [3, 32, 32], "parallelism": f"batch-sharded x{world}, no collectives",
             "weights": "random init, torch.manual_seed(42)"}
+
+
+def train_leg(args, dev, rank, world, stream):
+    """images/sec of DiffusionModelTrainer._train_epoch's body (src/DiffusionModelTrainer.py:36-67) on synthetic data."""
+    import torch
+    import ldm_b200
+    from ldm_b200 import dist as ldist
+    import torch.distributed as tdist
+    B = args.train_batch
+    torch.manual_seed(42)
+    model = ldm_b200.UNet(3, 3, 64, (1, 2, 4, 8), True, 10, dtype=args.dtype).to(dev)
+    diffusion = ldm_b200.Diffusion(args.n_steps, dev)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    g = torch.Generator().manual_seed(rank)
+    x0 = (torch.rand(B, 3, 32, 32, generator=g) * 2 - 1).pin_memory()
+    y = torch.randint(0, 10, (B,), generator=g).pin_memory()
+    bucket = None
+
+    def step():
+        nonlocal bucket
+        data, targets = x0.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+        noise, xt, t = diffusion(data)
+        loss = torch.nn.functional.mse_loss(noise, model(xt, t, targets))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        bucket = ldist.sync_gradients(model.parameters(), bucket)
+        opt.step()
+        return loss
+
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            tdist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        n = 5
+        for _ in range(n):
+            loss = step()
+        lv = float(loss.detach())  # the reference's loss.item() (:67), once at the end of the timed region
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            tdist.barrier()
+    ms = ldist.max_over_ranks(e0.elapsed_time(e1), dev)
+    return {"metric": "cifar10_ddpm_train_images_per_sec", "value": B * world * n / (ms / 1e3), "unit": "images/s",
+            "batch_per_gpu": B, "steps": n, "ms_per_step": ms / n, "loss": lv,
+            "note": "q_sample + UNet fwd + MSE + bwd (FFMA wgrad, tcgen05 fwd/dgrad) + grad all-reduce + torch Adam; "
+                    "4.536 GFLOP/image"}
 
 
 def run_ours(args):
@@ -258,6 +308,11 @@ def run_ours(args):
                         a[kk] += v[kk]
             prof = {k: {kk: vv / reps for kk, vv in v.items()} for k, v in acc.items()}
 
+    # ---- secondary: the training step of the reference config (batch 64 per GPU, q_sample + fwd + bwd + grad
+    # all-reduce + Adam), reported beside the headline, never instead of it
+    train = None
+    if not args.no_train:
+        train = train_leg(args, dev, rank, world, stream)
     if rank != 0:
         return
     peaks = load_peaks()
@@ -311,12 +366,30 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_T_host.numel() * 4 + classes_host.numel() * 8,
                 "d2h_bytes_per_step": x_T_host.numel() * 4, "steps": e2e_steps},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_rec,
-        "unet_tflops": unet_tflops,
+        "unet_tflops": unet_tflops, "train": train,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL banners, library chatter) was
+    re-routed to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
@@ -327,9 +400,11 @@ def main():
     ap.add_argument("--cfg-scale", type=float, default=3.0)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--e2e-steps", type=int, default=1)
-    ap.add_argument("--cpu-batch", type=int, default=8)
-    ap.add_argument("--cpu-timesteps", type=int, default=3)
+    ap.add_argument("--cpu-batch", type=int, default=64)
+    ap.add_argument("--cpu-timesteps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
+    ap.add_argument("--train-batch", type=int, default=64)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -452,9 +452,16 @@ __global__ void __launch_bounds__(128) linattn_mma_kernel(const bf16* __restrict
 //   out[tok x e] = q~[tok x d] ctx[d x e]    (ctx through shared memory once per sample: it needs a transpose)
 namespace {
 
+// FOLD: x is the raw PreNorm input; GroupNorm(1,C) is applied algebraically:  W (r (x - mu) gamma + beta)
+//   = r (W diag(gamma)) x  +  (W beta - r mu rowsum(W diag(gamma)))  -- one scale r and one per-channel constant.
+//   K: the constant is uniform along the softmax (token) axis and cancels; V: it passes through the normalised
+//   ctx unchanged (sum_n softmax = 1); Q: added before the softmax over d.
+template <bool FOLD>
 __global__ void __launch_bounds__(128, 3) linattn_qkv_fused_kernel(const bf16* __restrict__ xn, int ldx,
                                                                const bf16* __restrict__ wqkv,
-                                                               bf16* __restrict__ out, int N) {
+                                                               const float* __restrict__ uv,
+                                                               const float2* __restrict__ gn_part, int gn_splits,
+                                                               float gn_eps, bf16* __restrict__ out, int N) {
   constexpr int C = 64;
   constexpr int XROW = 128;              // bytes per token row of the x tile (64 bf16)
   constexpr int XBUF = LM_TILE * XROW;   // 4 KB
@@ -481,6 +488,23 @@ __global__ void __launch_bounds__(128, 3) linattn_qkv_fused_kernel(const bf16* _
   cp_async_commit();
   if (tiles > 1) load_x(1, 1);
   cp_async_commit();
+
+  // per-sample GroupNorm(1, C) statistics from the slab partials (fixed order), see gn_apply_kernel
+  float gr = 1.f, gmu = 0.f;
+  if (FOLD) {
+    float a = 0.f, bsum = 0.f;
+    for (int sp = 0; sp < gn_splits; ++sp) {
+      const float2 v = gn_part[(int64_t)b * gn_splits + sp];
+      a += v.x; bsum += v.y;
+    }
+    const float K = __bfloat162float(xb[0]);
+    const float inv_n = 1.0f / ((float)N * (float)C);
+    const float m1 = a * inv_n;
+    const float var = fmaxf(bsum * inv_n - m1 * m1, 0.f);
+    gmu = K + m1;
+    gr = 1.0f / sqrtf(var + gn_eps);
+  }
+  const float kscale = gr * LOG2E;   // softmax over tokens of r*k: the scale folds into the exp2 argument
 
   // A fragments of a 32 x 64 weight block (rows = d or e): frag[mt][ks] = {(g, 2tq), (g+8, 2tq), (g, 2tq+8), (g+8, 2tq+8)}
   auto load_w_a = [&](const bf16* w, uint32_t (&f)[2][4][4]) {
@@ -549,11 +573,11 @@ __global__ void __launch_bounds__(128, 3) linattn_qkv_fused_kernel(const bf16* _
           float mx = fmaxf(fmaxf(kc[mt][0][2 * hf], kc[mt][0][2 * hf + 1]), fmaxf(kc[mt][1][2 * hf], kc[mt][1][2 * hf + 1]));
           mx = quad_max(mx);
           const float nm = fmaxf(m_run[mt][hf], mx);
-          const float sc = ex2f((m_run[mt][hf] - nm) * LOG2E);
+          const float sc = ex2f((m_run[mt][hf] - nm) * kscale);
           m_run[mt][hf] = nm;
-          const float ml2 = nm * LOG2E;
-          const float p00 = ex2f(fmaf(kc[mt][0][2 * hf], LOG2E, -ml2)), p01 = ex2f(fmaf(kc[mt][0][2 * hf + 1], LOG2E, -ml2));
-          const float p10 = ex2f(fmaf(kc[mt][1][2 * hf], LOG2E, -ml2)), p11 = ex2f(fmaf(kc[mt][1][2 * hf + 1], LOG2E, -ml2));
+          const float ml2 = nm * kscale;
+          const float p00 = ex2f(fmaf(kc[mt][0][2 * hf], kscale, -ml2)), p01 = ex2f(fmaf(kc[mt][0][2 * hf + 1], kscale, -ml2));
+          const float p10 = ex2f(fmaf(kc[mt][1][2 * hf], kscale, -ml2)), p11 = ex2f(fmaf(kc[mt][1][2 * hf + 1], kscale, -ml2));
           z[mt][hf] = z[mt][hf] * sc + (p00 + p01 + p10 + p11);
           pa[mt][hf] = pack_bf2(p00, p01);        // a0 / a1: tokens 2tq,2tq+1
           pa[mt][hf + 2] = pack_bf2(p10, p11);    // a2 / a3: tokens 8+2tq, 8+2tq+1
@@ -587,11 +611,18 @@ __global__ void __launch_bounds__(128, 3) linattn_qkv_fused_kernel(const bf16* _
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
-      const float f = 0.17677669529663687f / quad_sum(z[mt][hf]);
+      const float zinv = 1.0f / quad_sum(z[mt][hf]);
+      const float f = 0.17677669529663687f * zinv * gr;     // 32^-1/2 (q scale) / Z[d] * GroupNorm scale of v
       const int d = mt * 16 + hf * 8 + g;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        const uint32_t v = pack_bf2(acc[mt][nt][hf * 2] * f, acc[mt][nt][hf * 2 + 1] * f);
+        float c0v = acc[mt][nt][hf * 2] * f, c1v = acc[mt][nt][hf * 2 + 1] * f;
+        if (FOLD) {  // v's per-channel constant passes through the normalised ctx (sum_n softmax_n(k) = 1)
+          const int e = 256 + h * LA_D + nt * 8 + 2 * tq;
+          c0v += 0.17677669529663687f * (uv[384 + e] - gr * gmu * uv[e]);
+          c1v += 0.17677669529663687f * (uv[384 + e + 1] - gr * gmu * uv[e + 1]);
+        }
+        const uint32_t v = pack_bf2(c0v, c1v);
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(ctx_s + lm_off(d, nt) + tq * 4), "r"(v) : "memory");
       }
     }
@@ -606,6 +637,15 @@ __global__ void __launch_bounds__(128, 3) linattn_qkv_fused_kernel(const bf16* _
       ldsm_x4_t(bc[ks][jp], ctx_s + lm_off(r, ch));
     }
   __syncwarp();
+  // q's per-channel constants (columns d = 8nt + 2tq, +1 of this thread's C fragment)
+  float qoff[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int o = h * LA_D + nt * 8 + 2 * tq + u;
+      qoff[nt][u] = FOLD ? uv[384 + o] - gr * gmu * uv[o] : 0.f;
+    }
   // B fragments of Wq^T (k = c, n = d): wq[ks][nt] = {Wq[d = 8nt + g][c = 16ks + 2tq..], [.. + 8]}
   uint32_t wq[4][4][2];
   {
@@ -647,6 +687,13 @@ __global__ void __launch_bounds__(128, 3) linattn_qkv_fused_kernel(const bf16* _
       uint32_t qa[2][4];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
+        if (FOLD) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            qc[nt][2 * hf] = fmaf(qc[nt][2 * hf], gr, qoff[nt][0]);
+            qc[nt][2 * hf + 1] = fmaf(qc[nt][2 * hf + 1], gr, qoff[nt][1]);
+          }
+        }
         float mx = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) mx = fmaxf(mx, fmaxf(qc[nt][2 * hf], qc[nt][2 * hf + 1]));
@@ -702,8 +749,42 @@ int k_linear_attention_qkv(const void* xn, int ldx, int cin, const void* wqkv, v
   LDM_REQUIRE(dtype == LDM_DT_BF16 && cin == 64 && n_tokens % 16 == 0 && ldx % 8 == 0,
               "linear_attention_qkv: needs bf16, 64 input channels and a multiple of 16 tokens");
   if (batch == 0 || n_tokens == 0) return 0;
-  linattn_qkv_fused_kernel<<<batch, 128, 0, st>>>((const bf16*)xn, ldx, (const bf16*)wqkv, (bf16*)out, n_tokens);
+  linattn_qkv_fused_kernel<false><<<batch, 128, 0, st>>>((const bf16*)xn, ldx, (const bf16*)wqkv, nullptr, nullptr, 0, 0.f,
+                                                        (bf16*)out, n_tokens);
   LDM_LAUNCHED("linear_attention_qkv");
+  return 0;
+}
+int k_linear_attention_qkv_prenorm(const void* x, int ldx, int cin, const void* wfold, const float* uv, const void* gn_part,
+                                   int gn_splits, float eps, void* out, int batch, int n_tokens, int dtype, cudaStream_t st) {
+  LDM_REQUIRE(dtype == LDM_DT_BF16 && cin == 64 && n_tokens % 16 == 0 && ldx % 8 == 0 && uv && gn_part && gn_splits >= 1,
+              "linear_attention_qkv_prenorm: needs bf16, 64 input channels, a multiple of 16 tokens and GroupNorm statistics");
+  if (batch == 0 || n_tokens == 0) return 0;
+  linattn_qkv_fused_kernel<true><<<batch, 128, 0, st>>>((const bf16*)x, ldx, (const bf16*)wfold, uv, (const float2*)gn_part,
+                                                       gn_splits, eps, (bf16*)out, n_tokens);
+  LDM_LAUNCHED("linear_attention_qkv_prenorm");
+  return 0;
+}
+
+// wfold[o][c] = bf16(w[o][c] gamma[c]);  uv[o] = sum_c float(wfold[o][c]);  uv[384 + o] = sum_c w[o][c] beta[c]
+__global__ void fold_prenorm_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    int cin, bf16* __restrict__ wfold, float* __restrict__ uv) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= 384) return;
+  float u = 0.f, v = 0.f;
+  for (int c = 0; c < cin; ++c) {
+    const float wv = w[(int64_t)o * cin + c];
+    const bf16 f = __float2bfloat16_rn(wv * gamma[c]);
+    wfold[(int64_t)o * cin + c] = f;
+    u += __bfloat162float(f);
+    v = fmaf(wv, beta[c], v);
+  }
+  uv[o] = u;
+  uv[384 + o] = v;
+}
+int k_fold_prenorm_qkv(const float* wqkv, const float* gamma, const float* beta, int cin, void* wfold, float* uv,
+                       cudaStream_t st) {
+  fold_prenorm_kernel<<<3, 128, 0, st>>>(wqkv, gamma, beta, cin, (bf16*)wfold, uv);
+  LDM_LAUNCHED("fold_prenorm_qkv");
   return 0;
 }
 bool k_linear_attention_qkv_applicable(int cin, int n_tokens, int dtype) {

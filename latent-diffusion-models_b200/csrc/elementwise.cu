@@ -477,24 +477,61 @@ time_table_kernel(const int64_t* __restrict__ t_scalar, const float* __restrict_
     emb[i] = i < half ? sinf(arg) : cosf(arg);
   }
   __syncthreads();
-  for (int j = warp; j < D; j += nwarps) {
-    float a = 0.f;
-    for (int i = lane; i < Din; i += 32) a = fmaf(emb[i], w1[(int64_t)j * Din + i], a);
-    a = warp_sum(a);
-    if (lane == 0) {
-      const float v = a + b1[j];
-      h1[j] = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+  // Each warp owns D/nwarps outputs; ALL of its weight loads are issued before the first reduction, so the layer
+  // costs one memory round trip instead of one per output.
+  constexpr int TT_MAX = 8;   // outputs per warp (D <= 8 * nwarps)
+  {
+    float a[TT_MAX];
+#pragma unroll
+    for (int u = 0; u < TT_MAX; ++u) {
+      const int j = warp + u * nwarps;
+      a[u] = 0.f;
+      if (j < D)
+        for (int i = lane; i < Din; i += 32) a[u] = fmaf(emb[i], __ldg(w1 + (int64_t)j * Din + i), a[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < TT_MAX; ++u) {
+      const int j = warp + u * nwarps;
+      const float s = warp_sum(a[u]);
+      if (lane == 0 && j < D) {
+        const float v = s + b1[j];
+        h1[j] = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+      }
     }
   }
   __syncthreads();
-  for (int j = warp; j < D; j += nwarps) {
-    float a = 0.f;
-    for (int k = lane * 4; k < D; k += 128) {
-      const float4 w4 = *reinterpret_cast<const float4*>(w3 + (int64_t)j * D + k);
-      a = fmaf(h1[k], w4.x, a); a = fmaf(h1[k + 1], w4.y, a); a = fmaf(h1[k + 2], w4.z, a); a = fmaf(h1[k + 3], w4.w, a);
+  {
+    float4 wv[TT_MAX][2];
+#pragma unroll
+    for (int u = 0; u < TT_MAX; ++u) {
+      const int j = warp + u * nwarps;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int k = lane * 4 + q * 128;
+        wv[u][q] = (j < D && k < D) ? __ldg(reinterpret_cast<const float4*>(w3 + (int64_t)j * D + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-    a = warp_sum(a);
-    if (lane == 0) tt[j] = a + b3[j];
+#pragma unroll
+    for (int u = 0; u < TT_MAX; ++u) {
+      const int j = warp + u * nwarps;
+      float a = 0.f;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int k = lane * 4 + q * 128;
+        if (k < D) {
+          a = fmaf(h1[k], wv[u][q].x, a); a = fmaf(h1[k + 1], wv[u][q].y, a);
+          a = fmaf(h1[k + 2], wv[u][q].z, a); a = fmaf(h1[k + 3], wv[u][q].w, a);
+        }
+      }
+      for (int k = lane * 4 + 256; k < D; k += 128) {   // D > 256: remaining columns the slow way
+        if (j < D) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(w3 + (int64_t)j * D + k));
+          a = fmaf(h1[k], w4.x, a); a = fmaf(h1[k + 1], w4.y, a); a = fmaf(h1[k + 2], w4.z, a); a = fmaf(h1[k + 3], w4.w, a);
+        }
+      }
+      a = warp_sum(a);
+      if (lane == 0 && j < D) tt[j] = a + b3[j];
+    }
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < R * D; idx += blockDim.x) {
@@ -513,21 +550,31 @@ time_proj_table_kernel(const float* __restrict__ s_tab, const float* __restrict_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o = blockIdx.x * (blockDim.x >> 5) + warp;
   if (o >= total) return;
+  float4 wv[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int k = lane * 4 + q * 128;
+    wv[q] = k < D ? __ldg(reinterpret_cast<const float4*>(w + (int64_t)o * D + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float bo = bias[o];
   for (int r = 0; r < R; ++r) {
     float a = 0.f;
-    for (int k = lane * 4; k < D; k += 128) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + (int64_t)o * D + k));
-      const float4 s4 = *reinterpret_cast<const float4*>(s + r * D + k);
-      a = fmaf(s4.x, w4.x, a); a = fmaf(s4.y, w4.y, a); a = fmaf(s4.z, w4.z, a); a = fmaf(s4.w, w4.w, a);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int k = lane * 4 + q * 128;
+      if (k < D) {
+        const float4 s4 = *reinterpret_cast<const float4*>(s + r * D + k);
+        a = fmaf(s4.x, wv[q].x, a); a = fmaf(s4.y, wv[q].y, a); a = fmaf(s4.z, wv[q].z, a); a = fmaf(s4.w, wv[q].w, a);
+      }
     }
     a = warp_sum(a);
-    if (lane == 0) tproj_tab[(int64_t)r * total + o] = a + bias[o];
+    if (lane == 0) tproj_tab[(int64_t)r * total + o] = a + bo;
   }
 }
 int k_time_table(const int64_t* t_scalar, const float* w1, const float* b1, const float* w3, const float* b3,
                  const float* label_emb, const float* tproj_w, const float* tproj_b, float* s_tab, float* tproj_tab,
                  int R, int n_classes, int D, int total, cudaStream_t st) {
-  LDM_REQUIRE(D % 128 == 0 && D <= 1024, "time_table: unsupported embedding width %d", D);
+  LDM_REQUIRE(D % 128 == 0 && D <= 256, "time_table: unsupported embedding width %d", D);
   LDM_REQUIRE((size_t)R * D * 4 <= 48 * 1024, "time_table: %d table rows do not fit shared memory", R);
   time_table_kernel<<<1, 1024, (size_t)(D / 4 + 2 * D) * sizeof(float), st>>>(t_scalar, w1, b1, w3, b3, label_emb, s_tab,
                                                                            R, n_classes, D);

@@ -326,6 +326,19 @@ gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int l
 
 int gcd_i2(int a, int b) { return b ? gcd_i2(b, a % b) : a; }
 
+// geometry shared by the stats producer and its consumers (gn_apply, the fused attention kernel)
+void gn_stream_geometry(int hw, int channels, int& threads, int& ppi, int& splits, int& pps) {
+  const int cpp = channels / 8;
+  const int unit = cpp / gcd_i2(cpp, 32) * 32;
+  threads = GS_THREADS / unit * unit;
+  if (threads < unit) threads = unit;
+  ppi = threads / cpp;
+  splits = hw / (ppi * 8);
+  if (splits > GS_MAX_SPLITS) splits = GS_MAX_SPLITS;
+  if (splits < 1) splits = 1;
+  pps = (hw + splits - 1) / splits;
+}
+
 int gn_stream_launch(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
                      const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
                      float eps, int silu, void* workspace, cudaStream_t st) {
@@ -391,6 +404,22 @@ int gn_launch(const void* x, int ldx, void* y, int ldy, const void* res, int ldr
 }
 
 }  // namespace
+
+// Statistics only (bf16, no rowvec): part[(n*splits + s)*groups + g] = {sum(x-K), sum((x-K)^2)} with the pivot
+// K = x[n][pixel 0][first channel of group g].  Consumers rebuild mean / rstd from it (see gn_apply_kernel).
+int k_group_norm_stats(const void* x, int ldx, int batch, int hw, int channels, int groups, void* workspace, int* splits_out,
+                       cudaStream_t st) {
+  LDM_REQUIRE(channels % groups == 0 && (channels / groups) % 8 == 0 && ldx % 8 == 0 && channels / 8 <= GS_THREADS && workspace,
+              "group_norm_stats: unsupported shape");
+  int threads, ppi, splits, pps;
+  gn_stream_geometry(hw, channels, threads, ppi, splits, pps);
+  *splits_out = splits;
+  if (batch == 0) return 0;
+  gn_stats_kernel<false><<<dim3(splits, batch), threads, 0, st>>>((const bf16*)x, ldx, nullptr, 0, (float2*)workspace, hw, channels,
+                                                                 groups, pps);
+  LDM_LAUNCHED("gn_stats");
+  return 0;
+}
 
 int64_t k_group_norm_ws_bytes(int batch, int groups) {
   return (int64_t)batch * GS_MAX_SPLITS * groups * sizeof(float2) + 1024;

@@ -58,6 +58,9 @@ int k_group_norm_rv(const void* x, int ldx, void* y, int ldy, const void* res, i
                     const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
                     float eps, int silu, int dtype, void* workspace, cudaStream_t st);
 
+int k_group_norm_stats(const void* x, int ldx, int batch, int hw, int channels, int groups, void* workspace, int* splits_out,
+                       cudaStream_t st);
+
 // ---- attention.cu
 int k_linear_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, cudaStream_t st);
 // LinearAttention with the to_qkv 1x1 convolution fused in (src/UNet.py:145,149-163): xn [B,N,cin] -> out [B,N,128];
@@ -65,6 +68,13 @@ int k_linear_attention(const void* qkv, void* out, int batch, int n_tokens, int 
 bool k_linear_attention_qkv_applicable(int cin, int n_tokens, int dtype);
 int k_linear_attention_qkv(const void* xn, int ldx, int cin, const void* wqkv, void* out, int batch, int n_tokens,
                            int dtype, cudaStream_t st);
+// Same with the PreNorm GroupNorm(1, C) folded in (src/UNet.py:106-110): x is the RAW block input, wfold = wqkv diag(gamma)
+// (bf16 [384][cin]), uv = {row sums of wfold, wqkv beta} (fp32 [2][384], see k_fold_prenorm_qkv), gn_part / gn_splits the
+// statistics left by k_group_norm_stats (groups = 1).
+int k_linear_attention_qkv_prenorm(const void* x, int ldx, int cin, const void* wfold, const float* uv, const void* gn_part,
+                                   int gn_splits, float eps, void* out, int batch, int n_tokens, int dtype, cudaStream_t st);
+int k_fold_prenorm_qkv(const float* wqkv /*[384][cin] fp32*/, const float* gamma, const float* beta, int cin, void* wfold,
+                       float* uv, cudaStream_t st);
 int k_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, cudaStream_t st);
 
 // ---- conv (conv_simt.cu / conv_tc.cu)

@@ -37,6 +37,7 @@ struct AttnW {
   bool linear = true;
   int p_qkv = -1, p_ow = -1, p_ob = -1, p_ogw = -1, p_ogb = -1, p_nw = -1, p_nb = -1;
   void* wqkv = nullptr; void* wout = nullptr; float* bout = nullptr;
+  void* wfold = nullptr; float* uv = nullptr;  // to_qkv with the PreNorm GroupNorm folded in (fused attention kernel)
   float *og = nullptr, *ob = nullptr, *ng = nullptr, *nb = nullptr;
 };
 struct UpW {
@@ -145,6 +146,7 @@ void layout_res(Bump& b, ResW& r, int es) {
 void layout_attn(Bump& b, AttnW& a, int es) {
   b.take(a.wqkv, (int64_t)3 * HIDDEN * a.dim * es);
   b.take(a.wout, (int64_t)a.dim * HIDDEN * es);
+  if (a.linear) { b.take(a.wfold, (int64_t)3 * HIDDEN * a.dim * 2); b.take(a.uv, (int64_t)2 * 3 * HIDDEN * 4); }
   b.take(a.bout, a.dim * 4);
   if (a.linear) { b.take(a.og, a.dim * 4); b.take(a.ob, a.dim * 4); }
   b.take(a.ng, a.dim * 4); b.take(a.nb, a.dim * 4);
@@ -337,6 +339,7 @@ int pack_attn(ldm_unet* h, AttnW& a, const float* const* P, cudaStream_t st) {
   RC(k_copy_f32(P[a.p_ob], a.bout, a.dim, st));
   if (a.linear) { RC(k_copy_f32(P[a.p_ogw], a.og, a.dim, st)); RC(k_copy_f32(P[a.p_ogb], a.ob, a.dim, st)); }
   RC(k_copy_f32(P[a.p_nw], a.ng, a.dim, st)); RC(k_copy_f32(P[a.p_nb], a.nb, a.dim, st));
+  if (a.linear) RC(k_fold_prenorm_qkv(P[a.p_qkv], P[a.p_nw], P[a.p_nb], a.dim, a.wfold, a.uv, st));
   return 0;
 }
 }  // namespace
@@ -479,17 +482,20 @@ struct Fwd {
   // Residual(PreNorm(dim, LinearAttention | Attention))  src/UNet.py:14-20,102-164.  d must not alias s0/s1/out.
   int attn_block(const AttnW& a, const void* d, int ldd, void* out, int ldo, int R) {
     void* qkv = ws + plan.qkv;
-    RC(gn(d, ldd, s(0), a.dim, nullptr, 0, a.ng, a.nb, R, a.dim, 1, 0));
     if (a.linear && impl == 0 && k_linear_attention_qkv_applicable(a.dim, R * R, dt)) {
-      // to_qkv + both softmaxes + both einsums in one kernel: the 384-channel qkv tensor never exists
+      // PreNorm statistics, then to_qkv + both softmaxes + both einsums in one kernel that reads the RAW block input:
+      // neither the normalised tensor nor the 384-channel qkv tensor ever exists
       const double N = (double)R * R;
+      int splits = 1;
+      PROF(LDM_FAM_GROUP_NORM, 0, (double)B * N * a.dim * es, k_group_norm_stats(d, ldd, B, R * R, a.dim, 1, gnws(), &splits, st));
       PROF(LDM_FAM_LINEAR_ATTENTION, (double)B * (2.0 * N * 3 * HIDDEN * a.dim + 4 * 2 * 2.0 * N * 32 * 32),
            (double)B * N * (a.dim + HIDDEN) * es,
-           k_linear_attention_qkv(s(0), a.dim, a.dim, a.wqkv, qkv, B, R * R, dt, st));
+           k_linear_attention_qkv_prenorm(d, ldd, a.dim, a.wfold, a.uv, gnws(), splits, GN_EPS, qkv, B, R * R, dt, st));
       RC(conv(qkv, HIDDEN, HIDDEN, nullptr, 0, 0, a.wout, a.bout, nullptr, 0, nullptr, 0, s(1), a.dim, a.dim, R, 1));
       RC(gn(s(1), a.dim, out, ldo, d, ldd, a.og, a.ob, R, a.dim, 1, 0));  // x + GroupNorm(1,C)(to_out(...))
       return 0;
     }
+    RC(gn(d, ldd, s(0), a.dim, nullptr, 0, a.ng, a.nb, R, a.dim, 1, 0));
     RC(conv(s(0), a.dim, a.dim, nullptr, 0, 0, a.wqkv, nullptr, nullptr, 0, nullptr, 0, qkv, 3 * HIDDEN, 3 * HIDDEN, R, 1));
     if (a.linear) {
       // 2 GEMMs of 32x32xN per head (ctx = k v^T, out = ctx^T q): 2 * 2*N*32*32 * 4 heads
@@ -581,7 +587,7 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
     const int64_t* yy = (y && y_len > 0) ? y : nullptr;
     const int yr = y_rows > 0 ? y_rows : batch;
     const bool table = t == nullptr && h->tproj_total > 0 && !(h->tap.out && h->tap.name == "temb") &&
-                       h->D % 128 == 0 && (int64_t)(h->d.num_classes + 1) * h->D * 4 <= 48 * 1024;
+                       h->D % 128 == 0 && h->D <= 256 && (int64_t)(h->d.num_classes + 1) * h->D * 4 <= 48 * 1024;
     if (table) {
       // Batch-constant timestep (the sampler): at most num_classes + 1 distinct embedding rows exist, so the two
       // MLPs run on that table and a gather expands the projection to the batch (src/UNet.py:373-376,90-93).

@@ -100,3 +100,17 @@ def unflatten_grads(params: Iterable[torch.nn.Parameter], flat: torch.Tensor, sk
         elif not skip_none:
             p.grad = flat[off:off + k].view_as(p).clone()
         off += k
+
+
+def sync_gradients(params: Iterable[torch.nn.Parameter], bucket: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Data-parallel step between ``loss.backward()`` and ``optimizer.step()``: pack every gradient into one flat fp32
+    bucket (zeros for parameters without a gradient -- the reference's four dead bottleneck mlp_t tensors -- so that all
+    ranks reduce the same length), one all-reduce(sum) over NCCL / NVLink, scale by 1/world, unpack.  Returns the bucket so
+    the caller can reuse it next step.  No-op on a single process."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return bucket
+    params = list(params)
+    bucket = flatten_grads(params, bucket)
+    allreduce_mean_(bucket)
+    unflatten_grads(params, bucket)
+    return bucket
