@@ -212,6 +212,8 @@ __global__ void __launch_bounds__(128) linattn_mma_kernel(const bf16* __restrict
 
   const int steps = N >> 4;              // 16-token k-steps
   const int tiles = (steps + 1) >> 1;    // 32-token pipeline tiles (the last one may hold a single step)
+  pdl_wait();
+  pdl_trigger();
 
   // ---------------- phase 1: ctx[d][e] = sum_n exp(k[n][d] - m[d]) v[n][e]
   auto load_kv = [&](int tile, int stage) {
@@ -484,6 +486,8 @@ __global__ void __launch_bounds__(128, 3) linattn_qkv_fused_kernel(const bf16* _
     }
   };
   const int steps = N >> 4, tiles = (steps + 1) >> 1;
+  pdl_wait();
+  pdl_trigger();
   load_x(0, 0);
   cp_async_commit();
   if (tiles > 1) load_x(1, 1);
@@ -749,8 +753,8 @@ int k_linear_attention_qkv(const void* xn, int ldx, int cin, const void* wqkv, v
   LDM_REQUIRE(dtype == LDM_DT_BF16 && cin == 64 && n_tokens % 16 == 0 && ldx % 8 == 0,
               "linear_attention_qkv: needs bf16, 64 input channels and a multiple of 16 tokens");
   if (batch == 0 || n_tokens == 0) return 0;
-  linattn_qkv_fused_kernel<false><<<batch, 128, 0, st>>>((const bf16*)xn, ldx, (const bf16*)wqkv, nullptr, nullptr, 0, 0.f,
-                                                        (bf16*)out, n_tokens);
+  LDM_CUDA(ldm_launch_pdl(linattn_qkv_fused_kernel<false>, dim3(batch), dim3(128), 0, st, (const bf16*)xn, ldx, (const bf16*)wqkv,
+                          (const float*)nullptr, (const float2*)nullptr, 0, 0.f, (bf16*)out, n_tokens));
   LDM_LAUNCHED("linear_attention_qkv");
   return 0;
 }
@@ -759,8 +763,8 @@ int k_linear_attention_qkv_prenorm(const void* x, int ldx, int cin, const void* 
   LDM_REQUIRE(dtype == LDM_DT_BF16 && cin == 64 && n_tokens % 16 == 0 && ldx % 8 == 0 && uv && gn_part && gn_splits >= 1,
               "linear_attention_qkv_prenorm: needs bf16, 64 input channels, a multiple of 16 tokens and GroupNorm statistics");
   if (batch == 0 || n_tokens == 0) return 0;
-  linattn_qkv_fused_kernel<true><<<batch, 128, 0, st>>>((const bf16*)x, ldx, (const bf16*)wfold, uv, (const float2*)gn_part,
-                                                       gn_splits, eps, (bf16*)out, n_tokens);
+  LDM_CUDA(ldm_launch_pdl(linattn_qkv_fused_kernel<true>, dim3(batch), dim3(128), 0, st, (const bf16*)x, ldx, (const bf16*)wfold, uv,
+                          (const float2*)gn_part, gn_splits, eps, (bf16*)out, n_tokens));
   LDM_LAUNCHED("linear_attention_qkv_prenorm");
   return 0;
 }
@@ -795,7 +799,7 @@ int k_linear_attention(const void* qkv, void* out, int batch, int n_tokens, int 
   if (batch == 0 || n_tokens == 0) return 0;
   int grid = batch * LA_HEADS;
   if (dtype == LDM_DT_BF16 && n_tokens % 16 == 0 && getenv("LDM_LINATTN_SIMT") == nullptr)
-    linattn_mma_kernel<<<batch, 128, 0, st>>>((const bf16*)qkv, (bf16*)out, n_tokens);
+    LDM_CUDA(ldm_launch_pdl(linattn_mma_kernel, dim3(batch), dim3(128), 0, st, (const bf16*)qkv, (bf16*)out, n_tokens));
   else if (dtype == LDM_DT_BF16) linattn_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)qkv, (bf16*)out, n_tokens);
   else linattn_kernel<float><<<grid, 256, 0, st>>>((const float*)qkv, (float*)out, n_tokens);
   LDM_LAUNCHED("linear_attention");
@@ -806,6 +810,8 @@ int k_linear_attention(const void* qkv, void* out, int batch, int n_tokens, int 
 template <typename T>
 __global__ void attn_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N) {
   extern __shared__ __align__(16) float sm[];  // k[N][LA_LD], v[N][LA_LD]
+  pdl_wait();
+  pdl_trigger();
   float* sk = sm;
   float* sv = sm + (size_t)N * LA_LD;
   const int b = blockIdx.x / LA_HEADS, h = blockIdx.x % LA_HEADS;
@@ -870,7 +876,7 @@ int k_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, 
   if (dtype == LDM_DT_BF16) {
     if (smem > 48 * 1024)
       LDM_CUDA(cudaFuncSetAttribute(attn_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_kernel<bf16><<<grid, threads, smem, st>>>((const bf16*)qkv, (bf16*)out, n_tokens);
+    LDM_CUDA(ldm_launch_pdl(attn_kernel<bf16>, dim3(grid), dim3(threads), smem, st, (const bf16*)qkv, (bf16*)out, n_tokens));
   } else {
     if (smem > 48 * 1024)
       LDM_CUDA(cudaFuncSetAttribute(attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -36,6 +36,25 @@ extern std::atomic<long long> g_ldm_launches;
     }                                                                                      \
   } while (0)
 
+// Programmatic dependent launch: kernels of the per-timestep chain are launched with the programmatic-stream-
+// serialization attribute, call pdl_wait() before touching anything their predecessor wrote and pdl_trigger() right
+// after it, so that the successor's launch latency, block scheduling and (for the conv kernels) barrier / TMEM /
+// descriptor set-up overlap the predecessor's tail.  Opt-in with LDM_PDL=1 (without the attribute the device calls are
+// no-ops); see api.cu for the measurement that keeps it off by default.
+extern int g_ldm_pdl;
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ldm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_ldm_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t align_up64(int64_t a, int64_t b) { return ceil_div64(a, b) * b; }
 
@@ -44,6 +63,9 @@ static inline int dtype_size(int dtype) { return dtype == LDM_DT_BF16 ? 2 : 4; }
 
 // ---------------------------------------------------------------- device side
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 template <typename T>
 struct VecTraits;

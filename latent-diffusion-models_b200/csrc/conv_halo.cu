@@ -100,6 +100,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();      // everything above overlapped the previous kernel's tail; its outputs are visible from here on
+  pdl_trigger();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const bool resident = p.b_stages >= p.n_kb;
   const int PL_rows = p.H + 2;
@@ -511,8 +513,8 @@ int k_conv_halo(const ConvArgs& a, cudaStream_t st) {
   }
   if (int rc = make_filter_map(&mb, a.w, a.cout, p.n_kb * BLOCK_K, a.cout)) return rc;
   const int grid = p.num_tiles < g_num_sms_h ? p.num_tiles : g_num_sms_h;
-  if (a.cout == 64) conv_halo_kernel<64><<<grid, 320, smem, st>>>(ma, ma2, mb, p);
-  else conv_halo_kernel<128><<<grid, 320, smem, st>>>(ma, ma2, mb, p);
+  if (a.cout == 64) LDM_CUDA(ldm_launch_pdl(conv_halo_kernel<64>, dim3(grid), dim3(320), (size_t)smem, st, ma, ma2, mb, p));
+  else LDM_CUDA(ldm_launch_pdl(conv_halo_kernel<128>, dim3(grid), dim3(320), (size_t)smem, st, ma, ma2, mb, p));
   LDM_LAUNCHED("conv_halo");
   return 0;
 }

@@ -120,6 +120,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();      // everything above overlapped the previous kernel's tail; its outputs are visible from here on
+  pdl_trigger();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -396,7 +398,7 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& 
   using Cfg = TcCfg<BLOCK_N>;
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  conv_tc_kernel<BLOCK_N><<<grid, 320, Cfg::SMEM_BYTES, st>>>(ma, ma2, mb, p);
+  LDM_CUDA(ldm_launch_pdl(conv_tc_kernel<BLOCK_N>, dim3(grid), dim3(320), (size_t)Cfg::SMEM_BYTES, st, ma, ma2, mb, p));
   LDM_LAUNCHED("conv_tc");
   return 0;
 }

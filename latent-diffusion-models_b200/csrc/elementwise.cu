@@ -50,6 +50,8 @@ int k_nhwc_to_nchw(const void* x, int ldx, float* y, int batch, int channels, in
 template <typename T>
 __global__ void maxpool2_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int H, int W,
                                 int C, int64_t total_chunks) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int V = VecTraits<T>::N;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total_chunks) return;
@@ -79,7 +81,7 @@ int k_maxpool2(const void* x, int ldx, void* y, int ldy, int batch, int height, 
   if (total == 0) return 0;
   int grid = (int)ceil_div64(total, 256);
   if (dtype == LDM_DT_BF16)
-    maxpool2_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, ldx, (bf16*)y, ldy, height, width, channels, total);
+    LDM_CUDA(ldm_launch_pdl(maxpool2_kernel<bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)x, ldx, (bf16*)y, ldy, height, width, channels, total));
   else
     maxpool2_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ldx, (float*)y, ldy, height, width, channels, total);
   LDM_LAUNCHED("maxpool2");
@@ -178,6 +180,8 @@ __global__ void p_sample_kernel(const float4* __restrict__ xt, const float4* __r
                                 int t_stride, const float4* __restrict__ coef, int T, const float* __restrict__ noise,
                                 int64_t noise_t_stride, uint64_t seed, uint64_t sample_offset,
                                 float4* __restrict__ out, int64_t n4, int64_t total4) {
+  pdl_wait();
+  pdl_trigger();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   // the reference gathers alpha/alpha_bar per sample but takes the noise branch on t[0] (src/DDPM.py:74-85)
@@ -215,22 +219,26 @@ int k_p_sample(const float* xt, const float* eps_c, const float* eps_u, float cf
   LDM_REQUIRE(n_per_sample % 4 == 0, "p_sample: n_per_sample must be a multiple of 4");
   int64_t n4 = n_per_sample / 4, total4 = n4 * batch;
   if (total4 == 0) return 0;
-  p_sample_kernel<<<(int)ceil_div64(total4, 256), 256, 0, st>>>(
-      (const float4*)xt, (const float4*)eps_c, (const float4*)eps_u, cfg_scale, t_dev, t_stride, (const float4*)coef,
-      n_steps, noise, noise_t_stride, seed, sample_offset, (float4*)out, n4, total4);
+  LDM_CUDA(ldm_launch_pdl(p_sample_kernel, dim3((unsigned)ceil_div64(total4, 256)), dim3(256), 0, st, (const float4*)xt,
+                          (const float4*)eps_c, (const float4*)eps_u, cfg_scale, t_dev, t_stride, (const float4*)coef, n_steps, noise,
+                          noise_t_stride, seed, sample_offset, (float4*)out, n4, total4));
   LDM_LAUNCHED("p_sample");
   return 0;
 }
 
 __global__ void set_i64_kernel(int64_t* p, int64_t v) { *p = v; }
-__global__ void add_i64_kernel(int64_t* p, int64_t v) { *p += v; }
+__global__ void add_i64_kernel(int64_t* p, int64_t v) {
+  pdl_wait();
+  pdl_trigger();
+  *p += v;
+}
 int k_set_i64(int64_t* p, int64_t v, cudaStream_t st) {
   set_i64_kernel<<<1, 1, 0, st>>>(p, v);
   LDM_LAUNCHED("set_i64");
   return 0;
 }
 int k_add_i64(int64_t* p, int64_t v, cudaStream_t st) {
-  add_i64_kernel<<<1, 1, 0, st>>>(p, v);
+  LDM_CUDA(ldm_launch_pdl(add_i64_kernel, dim3(1), dim3(1), 0, st, p, v));
   LDM_LAUNCHED("add_i64");
   return 0;
 }
@@ -369,6 +377,8 @@ template <typename T, int CIN>
 __global__ void __launch_bounds__(128)
 initial_conv_kernel(const float* __restrict__ x, int x_batch, int reps, const float* __restrict__ w,
                     const float* __restrict__ bias, T* __restrict__ y, int Cout, int H, int W, int64_t total) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) float sw[];  // [9*CIN][Cout] weights, then Cout bias
   for (int i = threadIdx.x; i < 9 * CIN * Cout; i += blockDim.x) sw[i] = w[i];
   float* sb = sw + 9 * CIN * Cout;
@@ -427,7 +437,7 @@ static int initial_conv_launch(const float* x, int x_batch, const float* w, cons
   const int64_t total = (int64_t)x_batch * (height / 2) * width;
   const int reps = batch / x_batch;
   const int grid = (int)ceil_div64(total, 128);
-#define IC_GO(C) initial_conv_kernel<T, C><<<grid, 128, smem, st>>>(x, x_batch, reps, w, bias, y, cout, height, width, total)
+#define IC_GO(C) LDM_CUDA(ldm_launch_pdl(initial_conv_kernel<T, C>, dim3(grid), dim3(128), smem, st, x, x_batch, reps, w, bias, y, cout, height, width, total))
   switch (cin) {
     case 1: IC_GO(1); break;
     case 2: IC_GO(2); break;
@@ -463,6 +473,8 @@ __global__ void __launch_bounds__(1024)
 time_table_kernel(const int64_t* __restrict__ t_scalar, const float* __restrict__ w1, const float* __restrict__ b1,
                   const float* __restrict__ w3, const float* __restrict__ b3, const float* __restrict__ label_emb,
                   float* __restrict__ s_tab, int R, int n_classes, int D) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   const int Din = D / 4, half = D / 8;
   float* emb = sm;             // [Din]
@@ -544,6 +556,8 @@ time_table_kernel(const int64_t* __restrict__ t_scalar, const float* __restrict_
 __global__ void __launch_bounds__(256)
 time_proj_table_kernel(const float* __restrict__ s_tab, const float* __restrict__ w, const float* __restrict__ bias,
                        float* __restrict__ tproj_tab, int R, int D, int total) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float s[];  // [R][D]
   for (int i = threadIdx.x; i < R * D; i += blockDim.x) s[i] = s_tab[i];
   __syncthreads();
@@ -576,11 +590,11 @@ int k_time_table(const int64_t* t_scalar, const float* w1, const float* b1, cons
                  int R, int n_classes, int D, int total, cudaStream_t st) {
   LDM_REQUIRE(D % 128 == 0 && D <= 256, "time_table: unsupported embedding width %d", D);
   LDM_REQUIRE((size_t)R * D * 4 <= 48 * 1024, "time_table: %d table rows do not fit shared memory", R);
-  time_table_kernel<<<1, 1024, (size_t)(D / 4 + 2 * D) * sizeof(float), st>>>(t_scalar, w1, b1, w3, b3, label_emb, s_tab,
-                                                                           R, n_classes, D);
+  LDM_CUDA(ldm_launch_pdl(time_table_kernel, dim3(1), dim3(1024), (size_t)(D / 4 + 2 * D) * sizeof(float), st, t_scalar, w1, b1, w3, b3,
+                          label_emb, s_tab, R, n_classes, D));
   LDM_LAUNCHED("time_table");
-  time_proj_table_kernel<<<(total + 7) / 8, 256, (size_t)R * D * sizeof(float), st>>>(s_tab, tproj_w, tproj_b,
-                                                                                    tproj_tab, R, D, total);
+  LDM_CUDA(ldm_launch_pdl(time_proj_table_kernel, dim3((total + 7) / 8), dim3(256), (size_t)R * D * sizeof(float), st, (const float*)s_tab,
+                          tproj_w, tproj_b, tproj_tab, R, D, total));
   LDM_LAUNCHED("time_proj_table");
   return 0;
 }
@@ -588,6 +602,8 @@ int k_time_table(const int64_t* t_scalar, const float* w1, const float* b1, cons
 // tproj[b][:] = tab[class(b)][:]: expands the per-class table of a batch-constant timestep (sampler) to batch rows.
 __global__ void tproj_gather_kernel(const float4* __restrict__ tab, const int64_t* __restrict__ y, int y_len,
                                     int y_rows, int n_classes, float4* __restrict__ tproj, int batch, int total4) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;
   int row = n_classes;  // unlabeled
   if (y && y_len > 0 && b < y_rows) row = (int)(y_len == 1 ? y[0] : y[b]);
@@ -598,8 +614,8 @@ int k_tproj_gather(const float* tab, const int64_t* y, int y_len, int y_rows, in
                    int total, cudaStream_t st) {
   LDM_REQUIRE(total % 4 == 0, "tproj_gather: width %d not a multiple of 4", total);
   if (batch == 0 || total == 0) return 0;
-  tproj_gather_kernel<<<dim3((total / 4 + 127) / 128, batch), 128, 0, st>>>(
-      (const float4*)tab, y, y_len, y_rows, n_classes, (float4*)tproj, batch, total / 4);
+  LDM_CUDA(ldm_launch_pdl(tproj_gather_kernel, dim3((total / 4 + 127) / 128, batch), dim3(128), 0, st, (const float4*)tab, y, y_len,
+                          y_rows, n_classes, (float4*)tproj, batch, total / 4));
   LDM_LAUNCHED("tproj_gather");
   return 0;
 }

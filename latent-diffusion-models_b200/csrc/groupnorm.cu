@@ -197,6 +197,8 @@ gn_stats_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ r
                 float2* __restrict__ part, int HW, int C, int G, int pix_per_split) {
   constexpr int V = 8;
   __shared__ float part_s[GS_THREADS], part_q[GS_THREADS];
+  pdl_wait();
+  pdl_trigger();
   const int n = blockIdx.y, split = blockIdx.x;
   const int cpp = C / V, cpg = cpp / G;
   const int ci = threadIdx.x % cpp, pl = threadIdx.x / cpp, ppi = blockDim.x / cpp;
@@ -255,6 +257,8 @@ gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int l
                 int C, int G, float eps, int silu, int pix_per_block) {
   constexpr int V = 8;
   __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  pdl_wait();
+  pdl_trigger();
   const int n = blockIdx.y;
   const int cpp = C / V, cpg = cpp / G;
   const bf16* xs = x + (int64_t)n * HW * ldx;
@@ -356,19 +360,19 @@ int gn_stream_launch(const void* x, int ldx, void* y, int ldy, const void* res, 
   const int pps = (hw + splits - 1) / splits;
   float2* part = (float2*)workspace;
   if (rowvec)
-    gn_stats_kernel<true><<<dim3(splits, batch), threads, 0, st>>>((const bf16*)x, ldx, rowvec, ld_rowvec, part, hw, channels, groups, pps);
+    LDM_CUDA(ldm_launch_pdl(gn_stats_kernel<true>, dim3(splits, batch), dim3(threads), 0, st, (const bf16*)x, ldx, rowvec, ld_rowvec, part, hw, channels, groups, pps));
   else
-    gn_stats_kernel<false><<<dim3(splits, batch), threads, 0, st>>>((const bf16*)x, ldx, rowvec, ld_rowvec, part, hw, channels, groups, pps);
+    LDM_CUDA(ldm_launch_pdl(gn_stats_kernel<false>, dim3(splits, batch), dim3(threads), 0, st, (const bf16*)x, ldx, rowvec, ld_rowvec, part, hw, channels, groups, pps));
   LDM_LAUNCHED("gn_stats");
   int ppb = ppi * 8;
   if (ppb > hw) ppb = hw;
   const dim3 grid((hw + ppb - 1) / ppb, batch);
   if (rowvec)
-    gn_apply_kernel<true><<<grid, threads, 0, st>>>((const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)res, ldres, gamma, beta,
-                                                    rowvec, ld_rowvec, part, splits, hw, channels, groups, eps, silu, ppb);
+    LDM_CUDA(ldm_launch_pdl(gn_apply_kernel<true>, grid, dim3(threads), 0, st, (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)res,
+                            ldres, gamma, beta, rowvec, ld_rowvec, (const float2*)part, splits, hw, channels, groups, eps, silu, ppb));
   else
-    gn_apply_kernel<false><<<grid, threads, 0, st>>>((const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)res, ldres, gamma, beta,
-                                                     rowvec, ld_rowvec, part, splits, hw, channels, groups, eps, silu, ppb);
+    LDM_CUDA(ldm_launch_pdl(gn_apply_kernel<false>, grid, dim3(threads), 0, st, (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)res,
+                            ldres, gamma, beta, rowvec, ld_rowvec, (const float2*)part, splits, hw, channels, groups, eps, silu, ppb));
   LDM_LAUNCHED("gn_apply");
   return 0;
 }
@@ -415,8 +419,8 @@ int k_group_norm_stats(const void* x, int ldx, int batch, int hw, int channels, 
   gn_stream_geometry(hw, channels, threads, ppi, splits, pps);
   *splits_out = splits;
   if (batch == 0) return 0;
-  gn_stats_kernel<false><<<dim3(splits, batch), threads, 0, st>>>((const bf16*)x, ldx, nullptr, 0, (float2*)workspace, hw, channels,
-                                                                 groups, pps);
+  LDM_CUDA(ldm_launch_pdl(gn_stats_kernel<false>, dim3(splits, batch), dim3(threads), 0, st, (const bf16*)x, ldx, (const float*)nullptr,
+                          0, (float2*)workspace, hw, channels, groups, pps));
   LDM_LAUNCHED("gn_stats");
   return 0;
 }
