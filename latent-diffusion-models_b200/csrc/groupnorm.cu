@@ -446,7 +446,10 @@ int k_group_norm_rv(const void* x, int ldx, void* y, int ldy, const void* res, i
   LDM_REQUIRE(ldx % V == 0 && ldy % V == 0 && (res == nullptr || ldres % V == 0), "group_norm: unaligned stride");
   LDM_REQUIRE(channels / V <= 1024, "group_norm: too many channels (%d)", channels);
   if (batch == 0 || hw == 0) return 0;
-  if (dtype == LDM_DT_BF16 && workspace != nullptr && channels / 8 <= GS_THREADS && batch <= 65535 &&
+  // tiny samples (the 2x2 bottleneck): one CTA per sample holds everything in registers -- one launch and one round trip
+  // instead of two of each
+  const bool tiny = (int64_t)hw * channels <= 2048;
+  if (dtype == LDM_DT_BF16 && workspace != nullptr && channels / 8 <= GS_THREADS && batch <= 65535 && !tiny &&
       getenv("LDM_GN_ONE_CTA") == nullptr)
     return gn_stream_launch(x, ldx, y, ldy, res, ldres, gamma, beta, rowvec, ld_rowvec, batch, hw, channels, groups, eps,
                             silu, workspace, st);

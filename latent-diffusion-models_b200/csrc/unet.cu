@@ -78,6 +78,10 @@ struct ldm_unet {
   int64_t arena_bytes = 0;
   bool loaded = false;
   Tap tap;
+  // The time-embedding kernels depend only on t / y, not on the image: they run on a side stream (a parallel branch
+  // of the captured graph) and join the main chain where the first ResNetBlock needs the projection.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int es() const { return dtype_size(d.dtype); }
 };
 
@@ -297,6 +301,12 @@ extern "C" int ldm_unet_create(const ldm_unet_desc* desc, ldm_unet** out) {
     return ldm_set_error("cudaMalloc(%lld bytes of packed weights) failed: %s", (long long)h->arena_bytes, cudaGetErrorString(e));
   }
   layout_all(h, h->arena);
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    ldm_unet_destroy(h);
+    return ldm_set_error("ldm_unet_create: could not create the side stream / events: %s", cudaGetErrorString(cudaGetLastError()));
+  }
   *out = h;
   return 0;
 }
@@ -304,6 +314,9 @@ extern "C" int ldm_unet_create(const ldm_unet_desc* desc, ldm_unet** out) {
 extern "C" void ldm_unet_destroy(ldm_unet* h) {
   if (!h) return;
   if (h->arena) cudaFree(h->arena);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side) cudaStreamDestroy(h->side);
   delete h;
 }
 extern "C" int ldm_unet_num_params(const ldm_unet* h) { return h ? (int)h->params.size() : 0; }
@@ -429,6 +442,7 @@ struct Fwd {
   Plan plan;
   const float* tproj;
   Prof* prof = nullptr;
+  cudaEvent_t join_event = nullptr;  // side-stream time embedding: waited for right before its first consumer
   const float* fin_w = nullptr; const float* fin_b = nullptr; float* fin_out = nullptr; int fin_cout = 0;
   void* s(int i) { return ws + plan.s[i]; }
   void* gnws() { return ws + plan.gnws; }
@@ -472,6 +486,10 @@ struct Fwd {
     // block2's GroupNorm loads h (one 8-float vector per thread), not in the conv epilogue
     const float* rv = (use_t && r.tproj_off >= 0) ? tproj + r.tproj_off : nullptr;
     RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3));
+    if (rv && join_event) {
+      LDM_CUDA(cudaStreamWaitEvent(st, join_event, 0));
+      join_event = nullptr;
+    }
     RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1, rv, h->tproj_total));
     if (r.has_sc)  // 1x1 shortcut conv K-concatenated into the second 3x3 GEMM
       RC(conv(s(0), r.cout, r.cout, x, ldx, r.cin, r.w2, r.b2, nullptr, 0, nullptr, 0, out, ldo, r.cout, R, 3));
@@ -582,6 +600,7 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
   float* temb = (float*)(f.ws + f.plan.temb);
   float* tproj = (float*)(f.ws + f.plan.tproj);
   f.tproj = tproj;
+  bool time_forked = false;
   if (h->d.with_time_emb) {
     Prof* prof = f.prof;
     const int64_t* yy = (y && y_len > 0) ? y : nullptr;
@@ -594,12 +613,20 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
       const int ncls = yy ? h->d.num_classes : 0, R = ncls + 1;
       float* temb_tab = (float*)(f.ws + f.plan.temb_tab);
       float* tproj_tab = (float*)(f.ws + f.plan.tproj_tab);
+      cudaStream_t ts = f.st;
+      if (!prof) {  // fork: these three launches overlap the initial conv and the first GroupNorm + conv
+        LDM_CUDA(cudaEventRecord(h->ev_fork, f.st));
+        LDM_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        ts = h->side;
+        time_forked = true;
+      }
       PROF(LDM_FAM_OTHER, 2.0 * (h->D / 4 + h->D) * h->D + 2.0 * R * h->D * h->tproj_total,
            ((double)(h->D / 4 + h->D) * h->D + (double)h->D * h->tproj_total + (double)R * (h->D + h->tproj_total)) * 4,
            k_time_table(t_dev_scalar, h->w1, h->b1, h->w3, h->b3, h->label, h->tproj_w, h->tproj_b, temb_tab, tproj_tab, R,
-                        ncls, h->D, h->tproj_total, f.st));
+                        ncls, h->D, h->tproj_total, ts));
       PROF(LDM_FAM_OTHER, 0, (double)batch * h->tproj_total * 4,
-           k_tproj_gather(tproj_tab, yy, y_len, yr, ncls, tproj, batch, h->tproj_total, f.st));
+           k_tproj_gather(tproj_tab, yy, y_len, yr, ncls, tproj, batch, h->tproj_total, ts));
+      if (time_forked) LDM_CUDA(cudaEventRecord(h->ev_join, h->side));
     } else {
       PROF(LDM_FAM_OTHER, 2.0 * batch * (h->D / 4 + h->D) * h->D, ((double)(h->D / 4 + h->D) * h->D + 2.0 * batch * h->D) * 4,
            k_time_embed(t, t_dev_scalar, yy, y_len, yr, h->w1t, h->b1, h->w3t, h->b3, h->label, temb, batch, h->D, 0, f.st));
@@ -619,6 +646,7 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
        (double)batch * S * S * (h->d.in_channels * 4 + h->dims[0] * f.es),
        k_initial_conv(x, x_batch, h->init_w, h->init_b, hin0, batch, h->d.in_channels, h->dims[0], S, S, f.dt, f.st));
   RC(f.tap("initial", hin0, h->dims[0], h->dims[0], S));
+  f.join_event = time_forked ? h->ev_join : nullptr;
   // ---- encoder  src/UNet.py:200-209
   for (int i = 0; i < L; ++i) {
     const int R = S >> i, cout = h->dims[i + 1];
@@ -633,6 +661,10 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
     RC(f.tap(("enc" + std::to_string(i) + ".attn").c_str(), skip, catc, cout, R));
     PROF(LDM_FAM_OTHER, 0, (double)batch * R * R * cout * f.es * 1.25,
          k_maxpool2(skip, catc, f.ws + f.plan.hin[i + 1], cout, batch, R, R, cout, f.dt, f.st));
+  }
+  if (f.join_event) {  // no encoder block consumed the projection (cannot happen with L >= 1, but a fork must always join)
+    LDM_CUDA(cudaStreamWaitEvent(f.st, f.join_event, 0));
+    f.join_event = nullptr;
   }
   // ---- bottleneck (no time embedding)  src/UNet.py:287-290
   {
