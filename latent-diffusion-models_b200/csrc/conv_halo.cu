@@ -60,6 +60,7 @@ struct HaloParams {
   int a_stages, b_stages;  // ring depths; b_stages >= n_kb means the filter is resident
   int cout;                // == BLOCK_N (one N tile)
   int a_tx_bytes, w_start; // TMA box bytes, first W coordinate (-1)
+  int res_mod;             // > 0: residual image index = n % res_mod
   int debug;               // profiling knob (LDM_HALO_DEBUG bit 0: no epilogue memory traffic, bit 1: no MMAs)
   int base_offset_mode;    // experiment knob: 0 = descriptor base_offset 0, 1 = (start >> 7) & 7
   const float* bias;
@@ -270,6 +271,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const float* const fin_w = p.fin_w;
     float* const fin_out = p.fin_out;
     const bool no_mem = p.debug & 1;
+    const int res_mod = p.res_mod;
     float* s_fin = s_bias + 768;  // [128][8] cross-warp sums of the fused projection (offset 3 KB in the 7 KB region)
     // the bias vector is read by every row of every tile: stage it in shared memory once (the CTA runs with the
     // maximum shared-memory carve-out, so L1 is tiny and a __ldg per tile would pay L2 latency each time)
@@ -295,7 +297,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // residual row: requested BEFORE waiting for the accumulator, so its latency hides behind the MMAs
       uint4 rr[COLS / 8];
       if (res && valid) {
-        const uint4* rp = reinterpret_cast<const uint4*>(res + m * ldres + cw);
+        const int64_t mr = res_mod > 0 ? (int64_t)(n % res_mod) * hw + pix : m;
+        const uint4* rp = reinterpret_cast<const uint4*>(res + mr * ldres + cw);
 #pragma unroll
         for (int j = 0; j < COLS / 8; ++j) rr[j] = __ldg(rp + j);
       }
@@ -491,7 +494,7 @@ int k_conv_halo(const ConvArgs& a, cudaStream_t st) {
     p.a_tx_bytes = bw * bh * 128;
   }
   p.bias = a.bias; p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec;
-  p.res = (const bf16*)a.res; p.ldres = a.ldres;
+  p.res = (const bf16*)a.res; p.ldres = a.ldres; p.res_mod = a.res_mod;
   p.y = (bf16*)a.y; p.ldy = a.ldy;
   p.fin_w = a.fin_w; p.fin_b = a.fin_b; p.fin_out = a.fin_out; p.fin_cout = a.fin_cout;
   // shared-memory plan: filter resident if it leaves room for >= 2 slabs, else a streaming ring of 8 tiles

@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvSimtParams p) 
 
 static int conv_check(const ConvArgs& a) {
   LDM_REQUIRE(a.ksize == 1 || a.ksize == 3, "conv2d: kernel size %d unsupported (1 or 3)", a.ksize);
+  LDM_REQUIRE(a.res_mod == 0, "conv2d: residual row aliasing is only implemented in the halo kernel");
   LDM_REQUIRE(a.cin % 16 == 0 && (a.x2 == nullptr || a.cin2 % 16 == 0), "conv2d: Cin must be a multiple of 16");
   LDM_REQUIRE(a.cout % 4 == 0, "conv2d: Cout must be a multiple of 4");
   LDM_REQUIRE(!a.up2 || (a.ksize == 1 && a.x2 == nullptr && a.res == nullptr && a.rowvec == nullptr),

@@ -413,6 +413,7 @@ int k_conv_tc_prepare() {
 int k_conv_tc(const ConvArgs& a, cudaStream_t st) {
   if (int rc = tc_init()) return rc;
   LDM_REQUIRE(a.dtype == LDM_DT_BF16, "conv_tc: bf16 only");
+  LDM_REQUIRE(a.res_mod == 0, "conv_tc: residual row aliasing is only implemented in the halo kernel");
   LDM_REQUIRE(a.ksize == 1 || a.ksize == 3, "conv_tc: kernel size %d unsupported", a.ksize);
   LDM_REQUIRE(a.cin % BLOCK_K == 0 && (a.x2 == nullptr || a.cin2 % BLOCK_K == 0),
               "conv_tc: Cin (%d/%d) must be a multiple of 64", a.cin, a.cin2);

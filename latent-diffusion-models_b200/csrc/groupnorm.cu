@@ -194,7 +194,7 @@ constexpr int GS_MAX_SPLITS = 16;
 template <bool RV>
 __global__ void __launch_bounds__(GS_THREADS)
 gn_stats_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ rowvec, int ld_rowvec,
-                float2* __restrict__ part, int HW, int C, int G, int pix_per_split) {
+                float2* __restrict__ part, int HW, int C, int G, int pix_per_split, int x_mod) {
   constexpr int V = 8;
   __shared__ float part_s[GS_THREADS], part_q[GS_THREADS];
   pdl_wait();
@@ -203,7 +203,9 @@ gn_stats_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ r
   const int cpp = C / V, cpg = cpp / G;
   const int ci = threadIdx.x % cpp, pl = threadIdx.x / cpp, ppi = blockDim.x / cpp;
   const int g = ci / cpg;
-  const bf16* xs = x + (int64_t)n * HW * ldx;
+  // x_mod > 0: sample n reads image n % x_mod (the sampler's cond / uncond halves share everything up to the first
+  // time-embedding add, so that prefix is computed once)
+  const bf16* xs = x + (int64_t)(x_mod > 0 ? n % x_mod : n) * HW * ldx;
   float rv[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) rv[i] = RV ? rowvec[(int64_t)n * ld_rowvec + ci * V + i] : 0.f;
@@ -254,14 +256,14 @@ __global__ void __launch_bounds__(GS_THREADS)
 gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, const bf16* __restrict__ res,
                 int ldres, const float* __restrict__ gamma, const float* __restrict__ beta,
                 const float* __restrict__ rowvec, int ld_rowvec, const float2* __restrict__ part, int splits, int HW,
-                int C, int G, float eps, int silu, int pix_per_block) {
+                int C, int G, float eps, int silu, int pix_per_block, int x_mod) {
   constexpr int V = 8;
   __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
   pdl_wait();
   pdl_trigger();
   const int n = blockIdx.y;
   const int cpp = C / V, cpg = cpp / G;
-  const bf16* xs = x + (int64_t)n * HW * ldx;
+  const bf16* xs = x + (int64_t)(x_mod > 0 ? n % x_mod : n) * HW * ldx;
   if (threadIdx.x < G) {
     const int gg = threadIdx.x;
     float a = 0.f, b = 0.f;
@@ -345,7 +347,7 @@ void gn_stream_geometry(int hw, int channels, int& threads, int& ppi, int& split
 
 int gn_stream_launch(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
                      const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
-                     float eps, int silu, void* workspace, cudaStream_t st) {
+                     float eps, int silu, void* workspace, int x_mod, cudaStream_t st) {
   const int cpp = channels / 8;
   const int unit = cpp / gcd_i2(cpp, 32) * 32;
   int threads = GS_THREADS / unit * unit;
@@ -360,19 +362,19 @@ int gn_stream_launch(const void* x, int ldx, void* y, int ldy, const void* res, 
   const int pps = (hw + splits - 1) / splits;
   float2* part = (float2*)workspace;
   if (rowvec)
-    LDM_CUDA(ldm_launch_pdl(gn_stats_kernel<true>, dim3(splits, batch), dim3(threads), 0, st, (const bf16*)x, ldx, rowvec, ld_rowvec, part, hw, channels, groups, pps));
+    LDM_CUDA(ldm_launch_pdl(gn_stats_kernel<true>, dim3(splits, batch), dim3(threads), 0, st, (const bf16*)x, ldx, rowvec, ld_rowvec, part, hw, channels, groups, pps, x_mod));
   else
-    LDM_CUDA(ldm_launch_pdl(gn_stats_kernel<false>, dim3(splits, batch), dim3(threads), 0, st, (const bf16*)x, ldx, rowvec, ld_rowvec, part, hw, channels, groups, pps));
+    LDM_CUDA(ldm_launch_pdl(gn_stats_kernel<false>, dim3(splits, batch), dim3(threads), 0, st, (const bf16*)x, ldx, rowvec, ld_rowvec, part, hw, channels, groups, pps, x_mod));
   LDM_LAUNCHED("gn_stats");
   int ppb = ppi * 8;
   if (ppb > hw) ppb = hw;
   const dim3 grid((hw + ppb - 1) / ppb, batch);
   if (rowvec)
     LDM_CUDA(ldm_launch_pdl(gn_apply_kernel<true>, grid, dim3(threads), 0, st, (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)res,
-                            ldres, gamma, beta, rowvec, ld_rowvec, (const float2*)part, splits, hw, channels, groups, eps, silu, ppb));
+                            ldres, gamma, beta, rowvec, ld_rowvec, (const float2*)part, splits, hw, channels, groups, eps, silu, ppb, x_mod));
   else
     LDM_CUDA(ldm_launch_pdl(gn_apply_kernel<false>, grid, dim3(threads), 0, st, (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)res,
-                            ldres, gamma, beta, rowvec, ld_rowvec, (const float2*)part, splits, hw, channels, groups, eps, silu, ppb));
+                            ldres, gamma, beta, rowvec, ld_rowvec, (const float2*)part, splits, hw, channels, groups, eps, silu, ppb, x_mod));
   LDM_LAUNCHED("gn_apply");
   return 0;
 }
@@ -411,6 +413,10 @@ int gn_launch(const void* x, int ldx, void* y, int ldy, const void* res, int ldr
 
 // Statistics only (bf16, no rowvec): part[(n*splits + s)*groups + g] = {sum(x-K), sum((x-K)^2)} with the pivot
 // K = x[n][pixel 0][first channel of group g].  Consumers rebuild mean / rstd from it (see gn_apply_kernel).
+bool k_group_norm_streams(int hw, int channels, int dtype) {
+  return dtype == LDM_DT_BF16 && channels / 8 <= GS_THREADS && (int64_t)hw * channels > 2048 && getenv("LDM_GN_ONE_CTA") == nullptr;
+}
+
 int k_group_norm_stats(const void* x, int ldx, int batch, int hw, int channels, int groups, void* workspace, int* splits_out,
                        cudaStream_t st) {
   LDM_REQUIRE(channels % groups == 0 && (channels / groups) % 8 == 0 && ldx % 8 == 0 && channels / 8 <= GS_THREADS && workspace,
@@ -420,7 +426,7 @@ int k_group_norm_stats(const void* x, int ldx, int batch, int hw, int channels, 
   *splits_out = splits;
   if (batch == 0) return 0;
   LDM_CUDA(ldm_launch_pdl(gn_stats_kernel<false>, dim3(splits, batch), dim3(threads), 0, st, (const bf16*)x, ldx, (const float*)nullptr,
-                          0, (float2*)workspace, hw, channels, groups, pps));
+                          0, (float2*)workspace, hw, channels, groups, pps, 0));
   LDM_LAUNCHED("gn_stats");
   return 0;
 }
@@ -439,6 +445,13 @@ int k_group_norm(const void* x, int ldx, void* y, int ldy, const void* res, int 
 int k_group_norm_rv(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
                     const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
                     float eps, int silu, int dtype, void* workspace, cudaStream_t st) {
+  return k_group_norm_mod(x, ldx, y, ldy, res, ldres, gamma, beta, rowvec, ld_rowvec, batch, hw, channels, groups, eps, silu, dtype,
+                          workspace, 0, st);
+}
+
+int k_group_norm_mod(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
+                     const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
+                     float eps, int silu, int dtype, void* workspace, int x_mod, cudaStream_t st) {
   const int V = dtype == LDM_DT_BF16 ? 8 : 4;
   LDM_REQUIRE(groups >= 1 && groups <= GN_MAX_GROUPS, "group_norm: groups=%d unsupported", groups);
   LDM_REQUIRE(channels % groups == 0 && (channels / groups) % V == 0,
@@ -452,7 +465,8 @@ int k_group_norm_rv(const void* x, int ldx, void* y, int ldy, const void* res, i
   if (dtype == LDM_DT_BF16 && workspace != nullptr && channels / 8 <= GS_THREADS && batch <= 65535 && !tiny &&
       getenv("LDM_GN_ONE_CTA") == nullptr)
     return gn_stream_launch(x, ldx, y, ldy, res, ldres, gamma, beta, rowvec, ld_rowvec, batch, hw, channels, groups, eps,
-                            silu, workspace, st);
+                            silu, workspace, x_mod, st);
+  LDM_REQUIRE(x_mod == 0, "group_norm: row aliasing is only implemented in the streaming bf16 kernels");
   if (dtype == LDM_DT_BF16)
     return gn_launch<bf16>(x, ldx, y, ldy, res, ldres, gamma, beta, rowvec, ld_rowvec, batch, hw, channels, groups, eps, silu, st);
   return gn_launch<float>(x, ldx, y, ldy, res, ldres, gamma, beta, rowvec, ld_rowvec, batch, hw, channels, groups, eps, silu, st);

@@ -61,6 +61,12 @@ int k_group_norm_rv(const void* x, int ldx, void* y, int ldy, const void* res, i
 int k_group_norm_stats(const void* x, int ldx, int batch, int hw, int channels, int groups, void* workspace, int* splits_out,
                        cudaStream_t st);
 
+// same; x_mod > 0: sample n reads image n % x_mod of x (bf16 streaming kernels only)
+int k_group_norm_mod(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
+                     const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
+                     float eps, int silu, int dtype, void* workspace, int x_mod, cudaStream_t st);
+bool k_group_norm_streams(int hw, int channels, int dtype);
+
 // ---- attention.cu
 int k_linear_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, cudaStream_t st);
 // LinearAttention with the to_qkv 1x1 convolution fused in (src/UNet.py:145,149-163): xn [B,N,cin] -> out [B,N,128];
@@ -90,6 +96,7 @@ struct ConvArgs {
   const float* fin_b = nullptr;           // ... + bias, written as fp32 NCHW [batch][fin_cout][H*W] (tcgen05 path only)
   float* fin_out = nullptr;
   int fin_cout = 0;
+  int res_mod = 0;                        // > 0: the residual of image n is read from image n % res_mod (halo kernel only)
   int cout;                               // GEMM N (for up2: 4 * output channels)
   int batch, height, width;
   int ksize;                              // 1 or 3 (pad = ksize/2)

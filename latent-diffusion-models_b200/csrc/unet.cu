@@ -443,6 +443,7 @@ struct Fwd {
   const float* tproj;
   Prof* prof = nullptr;
   cudaEvent_t join_event = nullptr;  // side-stream time embedding: waited for right before its first consumer
+  int res_mod = 0;                   // residual row aliasing for the next conv (shared CFG prefix)
   const float* fin_w = nullptr; const float* fin_b = nullptr; float* fin_out = nullptr; int fin_cout = 0;
   void* s(int i) { return ws + plan.s[i]; }
   void* gnws() { return ws + plan.gnws; }
@@ -456,10 +457,11 @@ struct Fwd {
     return 0;
   }
   int gn(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* g, const float* b, int R,
-         int C, int groups, int silu, const float* rowvec = nullptr, int ld_rowvec = 0) {
+         int C, int groups, int silu, const float* rowvec = nullptr, int ld_rowvec = 0, int x_mod = 0) {
     const double elems = (double)B * R * R * C;
     PROF(LDM_FAM_GROUP_NORM, 0, elems * es * (res ? 3 : 2),
-         k_group_norm_rv(x, ldx, y, ldy, res, ldres, g, b, rowvec, ld_rowvec, B, R * R, C, groups, GN_EPS, silu, dt, gnws(), st));
+         k_group_norm_mod(x, ldx, y, ldy, res, ldres, g, b, rowvec, ld_rowvec, B, R * R, C, groups, GN_EPS, silu, dt, gnws(),
+                          x_mod, st));
     return 0;
   }
   int conv(const void* x, int ldx, int cin, const void* x2, int ldx2, int cin2, const void* w, const float* bias,
@@ -468,7 +470,7 @@ struct Fwd {
     ConvArgs a;
     a.x = x; a.ldx = ldx; a.cin = cin; a.x2 = x2; a.ldx2 = ldx2; a.cin2 = cin2; a.w = w; a.bias = bias;
     a.rowvec = rowvec; a.ld_rowvec = ldrv; a.res = res; a.ldres = ldres; a.y = y; a.ldy = ldy; a.cout = cout;
-    a.batch = B; a.height = R; a.width = R; a.ksize = ksize; a.up2 = up2; a.dtype = dt;
+    a.batch = B; a.height = R; a.width = R; a.ksize = ksize; a.up2 = up2; a.dtype = dt; a.res_mod = res_mod;
     if (y == nullptr) { a.fin_w = fin_w; a.fin_b = fin_b; a.fin_out = fin_out; a.fin_cout = fin_cout; }
     return conv_args(a);
   }
@@ -480,7 +482,26 @@ struct Fwd {
     return 0;
   }
   // ResNetBlock  src/UNet.py:85-99.  x must not alias s0/s1/out.
-  int resblock(const ResW& r, const void* x, int ldx, void* out, int ldo, int R, bool use_t) {
+  // x_rows > 0: x holds only x_rows distinct images and output row n belongs to image n % x_rows (the sampler's cond and
+  // uncond halves are identical up to the first time-embedding add): norm1 + conv1 run once per distinct image.
+  int resblock(const ResW& r, const void* x, int ldx, void* out, int ldo, int R, bool use_t, int x_rows = 0) {
+    if (x_rows > 0) {
+      const int full = B;
+      B = x_rows;
+      RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
+      RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3));
+      B = full;
+      const float* rvm = (use_t && r.tproj_off >= 0) ? tproj + r.tproj_off : nullptr;
+      if (rvm && join_event) {
+        LDM_CUDA(cudaStreamWaitEvent(st, join_event, 0));
+        join_event = nullptr;
+      }
+      RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1, rvm, h->tproj_total, x_rows));
+      res_mod = x_rows;   // identity shortcut read from the shared images
+      int rc = conv(s(0), r.cout, r.cout, nullptr, 0, 0, r.w2, r.b2, nullptr, 0, x, ldx, out, ldo, r.cout, R, 3);
+      res_mod = 0;
+      return rc;
+    }
     RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
     // the time-embedding projection (h = h + mlp_t(t), :88-93) is a per-sample channel vector: it is added where
     // block2's GroupNorm loads h (one 8-float vector per thread), not in the conv epilogue
@@ -642,9 +663,20 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
   Prof* prof = f.prof;
   // initial conv: fp32 NCHW -> NHWC
   void* hin0 = f.ws + f.plan.hin[0];
-  PROF(LDM_FAM_OTHER, 2.0 * batch * S * S * 9 * h->d.in_channels * h->dims[0],
-       (double)batch * S * S * (h->d.in_channels * 4 + h->dims[0] * f.es),
-       k_initial_conv(x, x_batch, h->init_w, h->init_b, hin0, batch, h->d.in_channels, h->dims[0], S, S, f.dt, f.st));
+  // Shared CFG prefix: with aliased input rows (x_batch < batch) the initial conv and the first ResNetBlock's norm1 + conv1
+  // see identical data in every alias group -> computed for x_batch images only.
+  bool share_prefix = false;
+  if (x_batch < batch && f.dt == LDM_DT_BF16 && f.impl == 0 && !h->enc_res[0].has_sc && h->enc_res[0].tproj_off >= 0 &&
+      !(h->tap.out != nullptr) && getenv("LDM_NO_SHARED_PREFIX") == nullptr) {
+    ConvArgs probe;
+    probe.x = hin0; probe.ldx = h->dims[0]; probe.cin = h->dims[0]; probe.x2 = nullptr; probe.ldx2 = 0; probe.cin2 = 0;
+    probe.cout = h->dims[1]; probe.batch = batch; probe.height = S; probe.width = S; probe.ksize = 3; probe.up2 = 0; probe.dtype = f.dt;
+    share_prefix = k_conv_halo_applicable(probe) && k_group_norm_streams(S * S, h->dims[1], f.dt);
+  }
+  const int init_rows = share_prefix ? x_batch : batch;
+  PROF(LDM_FAM_OTHER, 2.0 * init_rows * S * S * 9 * h->d.in_channels * h->dims[0],
+       (double)init_rows * S * S * (h->d.in_channels * 4 + h->dims[0] * f.es),
+       k_initial_conv(x, x_batch, h->init_w, h->init_b, hin0, init_rows, h->d.in_channels, h->dims[0], S, S, f.dt, f.st));
   RC(f.tap("initial", hin0, h->dims[0], h->dims[0], S));
   f.join_event = time_forked ? h->ev_join : nullptr;
   // ---- encoder  src/UNet.py:200-209
@@ -655,7 +687,7 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
     uint8_t* cat = f.ws + f.plan.cat[j];
     void* skip = cat + (int64_t)h->dims[i] * f.es;    // skip occupies channels [dims[i], catc)
     void* hin = f.ws + f.plan.hin[i];
-    RC(f.resblock(h->enc_res[i], hin, h->dims[i], f.s(2), cout, R, true));
+    RC(f.resblock(h->enc_res[i], hin, h->dims[i], f.s(2), cout, R, true, (i == 0 && share_prefix) ? x_batch : 0));
     RC(f.tap(("enc" + std::to_string(i) + ".res").c_str(), f.s(2), cout, cout, R));
     RC(f.attn_block(h->enc_attn[i], f.s(2), cout, skip, catc, R));
     RC(f.tap(("enc" + std::to_string(i) + ".attn").c_str(), skip, catc, cout, R));
