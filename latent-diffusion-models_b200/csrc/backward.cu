@@ -42,7 +42,7 @@ __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + ex
 template <typename T>
 __global__ void __launch_bounds__(256)
 conv_wgrad_kernel(const T* __restrict__ x, int ldx, int cin, const T* __restrict__ dy, int lddy, int cout,
-                  float* __restrict__ dw, int B, int H, int W, int ksize, int m_per_split) {
+                  float* __restrict__ dw, float* __restrict__ dbias, int B, int H, int W, int ksize, int m_per_split) {
   __shared__ __align__(16) float As[16][68];  // dY tile  [m][co]
   __shared__ __align__(16) float Bs[16][68];  // X  tile  [m][ci]
   const int tid = threadIdx.x;
@@ -60,11 +60,16 @@ conv_wgrad_kernel(const T* __restrict__ x, int ldx, int cin, const T* __restrict
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // the bias gradient (column sums of dY) rides along in the CTAs of tap 0 / channel block 0: they stream every dY row
+  // of their (co tile, M split) exactly once
+  const bool do_bias = dbias != nullptr && blockIdx.y == 0;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
   for (int m0 = m_begin; m0 < m_end; m0 += 16) {
     const int m = m0 + lrow;
     float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
     if (m < m_end) {
       ld4<T>(dy + (int64_t)m * lddy + co0 + lc, av);
+      if (do_bias) { bsum[0] += av[0]; bsum[1] += av[1]; bsum[2] += av[2]; bsum[3] += av[3]; }
       const int w_ = m % W, r_ = m / W, h_ = r_ % H, n_ = r_ / H;
       const int hh = h_ + dyy, ww = w_ + dxx;
       if (hh >= 0 && hh < H && ww >= 0 && ww < W) ld4<T>(x + ((int64_t)(n_ * H + hh) * W + ww) * ldx + ci0 + lc, bv);
@@ -91,6 +96,18 @@ conv_wgrad_kernel(const T* __restrict__ x, int ldx, int cin, const T* __restrict
       const int co = co0 + ty * 4 + i, ci = ci0 + tx * 4 + j;
       atomicAdd(dw + ((int64_t)co * cin + ci) * taps + tap, acc[i][j]);
     }
+  if (do_bias) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[lrow][lc + i] = bsum[i];
+    __syncthreads();
+    if (tid < 64) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) t += As[r][tid];
+      atomicAdd(dbias + co0 + tid, t);
+    }
+  }
 }
 
 // column sums: out[c] += sum_m a[m][c]   (bias gradients)
@@ -505,29 +522,47 @@ attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, T* __rest
 }
 
 // ------------------------------------------------------------------ initial conv wgrad (fp32 NCHW input, tiny Cin)
-// grid (9*cin, msplit), 256 threads = 4 pixel lanes x 64 channel lanes (cout looped)
-template <typename T>
+// grid (msplit), 256 threads = 4 pixel lanes x 64 output channels; every thread keeps the 9*CIN partial sums of its
+// channel for its pixels (the input patch values are warp-uniform broadcast loads), then one shared-memory reduction
+// over the pixel lanes and 9*CIN*64 atomics per CTA.  Also accumulates the bias gradient.
+template <typename T, int CIN>
 __global__ void __launch_bounds__(256)
-initial_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int B, int cin, int cout,
-                     int H, int W, int m_per_split) {
-  __shared__ float red[256];
-  const int tap = blockIdx.x / cin, ci = blockIdx.x % cin;
-  const int dyy = tap / 3 - 1, dxx = tap % 3 - 1;
+initial_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, float* __restrict__ dbias,
+                     int B, int cout, int H, int W, int m_per_split) {
+  __shared__ float red[4][64];
   const int M = B * H * W;
-  const int m0 = blockIdx.y * m_per_split, m1 = min(M, m0 + m_per_split);
+  const int m0 = blockIdx.x * m_per_split, m1 = min(M, m0 + m_per_split);
   const int pl = threadIdx.x >> 6, cl = threadIdx.x & 63;
   for (int c0 = 0; c0 < cout; c0 += 64) {
-    float acc = 0.f;
+    float acc[9 * CIN], bs = 0.f;
+#pragma unroll
+    for (int j = 0; j < 9 * CIN; ++j) acc[j] = 0.f;
     for (int m = m0 + pl; m < m1; m += 4) {
       const int w_ = m % W, r_ = m / W, h_ = r_ % H, n_ = r_ / H;
-      const int hh = h_ + dyy, ww = w_ + dxx;
-      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-      acc = fmaf(x[((int64_t)(n_ * cin + ci) * H + hh) * W + ww], ldf(dy + (int64_t)m * cout + c0 + cl), acc);
+      const float g = ldf(dy + (int64_t)m * cout + c0 + cl);
+      bs += g;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int hh = h_ + tap / 3 - 1, ww = w_ + tap % 3 - 1;
+        const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float xv = ok ? __ldg(x + ((int64_t)(n_ * CIN + ci) * H + hh) * W + ww) : 0.f;
+          acc[tap * CIN + ci] = fmaf(xv, g, acc[tap * CIN + ci]);
+        }
+      }
     }
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    if (pl == 0) atomicAdd(dw + ((int64_t)(c0 + cl) * cin + ci) * 9 + tap, red[cl] + red[64 + cl] + red[128 + cl] + red[192 + cl]);
-    __syncthreads();
+#pragma unroll
+    for (int j = 0; j <= 9 * CIN; ++j) {
+      red[pl][cl] = j < 9 * CIN ? acc[j < 9 * CIN ? j : 0] : bs;
+      __syncthreads();
+      if (pl == 0) {
+        const float t = red[0][cl] + red[1][cl] + red[2][cl] + red[3][cl];
+        if (j < 9 * CIN) atomicAdd(dw + ((int64_t)(c0 + cl) * CIN + (j % CIN)) * 9 + (j / CIN), t);
+        else if (dbias) atomicAdd(dbias + c0 + cl, t);
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -685,13 +720,8 @@ int k_conv_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, int 
   if (target < 1) target = 1;
   const int mps = split_for(M, 256, target);
   const dim3 grid(cout / 64, taps * (cin / 64), (M + mps - 1) / mps);
-  DISPATCH_T(dtype, conv_wgrad_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, cin, (const T*)dy, lddy, cout, dw, batch, H, W, ksize, mps));
+  DISPATCH_T(dtype, conv_wgrad_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, cin, (const T*)dy, lddy, cout, dw, dbias, batch, H, W, ksize, mps));
   LDM_LAUNCHED("conv_wgrad");
-  if (dbias) {
-    const int rpb = split_for(M, 64, 4 * 148);
-    DISPATCH_T(dtype, colsum_kernel<T><<<(M + rpb - 1) / rpb, 256, 0, st>>>((const T*)dy, lddy, dbias, M, cout, rpb));
-    LDM_LAUNCHED("colsum");
-  }
   return 0;
 }
 
@@ -779,10 +809,18 @@ int k_initial_conv_wgrad(const float* x, const void* dy, float* dw, float* dbias
   LDM_REQUIRE(cout % 64 == 0, "initial_conv_wgrad: channels must be a multiple of 64");
   const int M = batch * H * W;
   if (M == 0) return 0;
-  const int mps = split_for(M, 256, (4 * 148) / (9 * cin) + 1);
-  DISPATCH_T(dtype, initial_wgrad_kernel<T><<<dim3(9 * cin, (M + mps - 1) / mps), 256, 0, st>>>(x, (const T*)dy, dw, batch, cin, cout, H, W, mps));
+  LDM_REQUIRE(cin >= 1 && cin <= 4, "initial_conv_wgrad: in_channels %d not in [1,4]", cin);
+  const int mps = split_for(M, 64, 2 * 148);
+  const int grid = (M + mps - 1) / mps;
+#define IW_GO(C) DISPATCH_T(dtype, initial_wgrad_kernel<T, C><<<grid, 256, 0, st>>>(x, (const T*)dy, dw, dbias, batch, cout, H, W, mps))
+  switch (cin) {
+    case 1: IW_GO(1); break;
+    case 2: IW_GO(2); break;
+    case 3: IW_GO(3); break;
+    default: IW_GO(4); break;
+  }
+#undef IW_GO
   LDM_LAUNCHED("initial_conv_wgrad");
-  if (dbias) return k_colsum(dy, cout, dbias, M, cout, dtype, st);
   return 0;
 }
 

@@ -56,8 +56,9 @@ class _Conv(Function):
         wd = torch.empty(cin, k * k * cout, dtype=x.dtype, device=x.device)
         _lib.check(lib.ldm_pack_conv_weight_dgrad(w.data_ptr(), cout, cin, k, wd.data_ptr(), ops._dt(x), _st()))
         dx = ops.conv2d(dy, wd, k, impl=ctx.impl)
-        dw = torch.zeros_like(w)
-        db = torch.zeros(cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+        buf = torch.zeros(w.numel() + cout, dtype=torch.float32, device=x.device)   # one fill for dW and db
+        dw = buf[:w.numel()].view_as(w)
+        db = buf[w.numel():] if ctx.has_bias else None
         _lib.check(lib.ldm_conv2d_wgrad(x.data_ptr(), x.stride(2), cin, dy.data_ptr(), dy.stride(2), cout, dw.data_ptr(),
                                         _lib.ptr(db), B, H, W, k, ops._dt(x), _st()))
         return dx, dw, db, None
