@@ -150,3 +150,10 @@ int k_rows_scatter_add(const float* src, const int64_t* idx, int idx_len, float*
 int k_rows_gather_add(float* dst, const int64_t* idx, int idx_len, const float* table, int batch, int D, cudaStream_t st);
 int k_add(const void* a, const void* b, void* out, int64_t n, int dtype, cudaStream_t st);
 int k_copy_channels(const void* src, int lds, void* dst, int ldd, int C, int64_t rows, int dtype, cudaStream_t st);
+
+// ---- wgrad_tc.cu: tcgen05 weight gradient on channel-major (pixel-contiguous) operand copies
+int k_nhwc_to_chw_bf16(const void* x, int ld, void* y, void* y_l, void* y_r, float* colsum, int batch, int C, int hw, int W,
+                       cudaStream_t st);
+bool k_conv_wgrad_tc_applicable(int cin, int cout, int H, int W, int ksize, int dtype);
+int k_conv_wgrad_tc(const void* xT, int cin, const void* dyT, const void* dyT_l, const void* dyT_r, int cout, float* dw,
+                    int batch, int H, int W, int ksize, cudaStream_t st);

@@ -11,6 +11,26 @@ int ldm_conv2d_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, 
   LDM_REQUIRE(x && dy && dw_oihw, "ldm_conv2d_wgrad: null argument");
   return k_conv_wgrad(x, ldx, cin, dy, lddy, cout, dw_oihw, dbias, batch, height, width, ksize, dtype, (cudaStream_t)stream);
 }
+int64_t ldm_conv2d_wgrad_scratch_bytes(int cin, int cout, int batch, int height, int width, int ksize, int dtype) {
+  if (!k_conv_wgrad_tc_applicable(cin, cout, height, width, ksize, dtype)) return 0;
+  return (int64_t)batch * height * width * (cin + (ksize == 3 ? 3 : 1) * (int64_t)cout) * 2 + 4 * 256;
+}
+// Tensor-core weight gradient: scratch (ldm_conv2d_wgrad_scratch_bytes, 256-byte aligned) receives the channel-major
+// copies of x and dy.  Falls back to nothing: returns an error for shapes the tcgen05 kernel does not take.
+int ldm_conv2d_wgrad_tc(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw_oihw, float* dbias,
+                        int batch, int height, int width, int ksize, void* scratch, void* stream) {
+  LDM_REQUIRE(x && dy && dw_oihw && scratch, "ldm_conv2d_wgrad_tc: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int hw = height * width;
+  auto up = [](int64_t v) { return (v + 255) / 256 * 256; };
+  char* xT = (char*)scratch;
+  char* dyT = xT + up((int64_t)batch * hw * cin * 2);
+  char* dyL = ksize == 3 ? dyT + up((int64_t)batch * hw * cout * 2) : nullptr;
+  char* dyR = ksize == 3 ? dyL + up((int64_t)batch * hw * cout * 2) : nullptr;
+  RC(k_nhwc_to_chw_bf16(x, ldx, xT, nullptr, nullptr, nullptr, batch, cin, hw, width, st));
+  RC(k_nhwc_to_chw_bf16(dy, lddy, dyT, dyL, dyR, dbias, batch, cout, hw, width, st));
+  return k_conv_wgrad_tc(xT, cin, dyT, dyL, dyR, cout, dw_oihw, batch, height, width, ksize, st);
+}
 int ldm_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin, int ksize, void* w_packed, int dtype, void* stream) {
   LDM_REQUIRE(w_oihw && w_packed, "ldm_pack_conv_weight_dgrad: null argument");
   return k_pack_dgrad_weight(w_oihw, cout, cin, ksize, w_packed, dtype, (cudaStream_t)stream);

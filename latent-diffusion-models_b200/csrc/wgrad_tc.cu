@@ -1,0 +1,269 @@
+// Convolution weight gradient on tcgen05 (bf16 in, fp32 accumulate in TMEM, fp32 atomics into the OIHW gradient).
+//   dW[co][ci][ky][kx] = sum_{n,p} dy[n,p,co] * x[n, p + (ky-1,kx-1), ci]  =  sum_{n,q} dy[n, q - (ky-1,kx-1), co] * x[n,q,ci]
+// The contraction runs over PIXELS, so both operands are needed pixel-contiguous ("K-major" with K = pixels): the caller
+// hands in channel-major copies xT [B][Cin][H*W], dyT [B][Cout][H*W] (one transpose pass each, k_nhwc_to_nchw_bf16).
+//   GEMM rows   = (tap, co) pairs, 128 per tile (for Cout = 64 a tile holds two taps): A = dyT SHIFTED by the tap.
+//                 A swizzled TMA box needs a 128-byte inner extent (64 pixels contiguous in memory) and a 16-byte
+//                 aligned start, so only the ROW part of the shift goes into the TMA coordinate (flattened pixel index
+//                 - dy*W; rows above / below the image fall outside the pixel dimension and are zero-filled by TMA).
+//                 The column part is baked into two extra transposed copies of dy: shifted by one pixel to the right
+//                 (dx = +1) or to the left (dx = -1) with a zero where the shift would wrap around a row end.
+//   GEMM cols   = ci, BN per tile:  B = xT unshifted
+//   GEMM K      = 64 consecutive pixels of one image per k-block, split over CTAs
+// grid = (row tiles * col tiles, K splits); every CTA accumulates its [128 x BN] slab in TMEM and adds it to dW.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+struct WgParams {
+  int cout, cin, taps;        // taps = 1 or 9
+  int row_tiles, col_tiles;   // (taps*cout + 127)/128, cin / BN
+  int kb_total, kb_per_split; // k-blocks of 64 pixels
+  int kb_per_image;           // H*W / 64
+  int W;
+  float* dw;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_dy_l,
+                const __grid_constant__ CUtensorMap tmap_dy_r, const __grid_constant__ CUtensorMap tmap_x, const WgParams p) {
+  constexpr int STAGES = BN == 256 ? 4 : 6;
+  constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t full_bar = bars, empty_bar = bars + 64, done_bar = bars + 128, tmem_slot = bars + 136;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_dy);
+    prefetch_tmap(&tmap_dy_l);
+    prefetch_tmap(&tmap_dy_r);
+    prefetch_tmap(&tmap_x);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int rt = blockIdx.x / p.col_tiles, ct = blockIdx.x % p.col_tiles;
+  const int kb0 = blockIdx.y * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+  const int ci0 = ct * BN;
+  // the two 64-row halves of the A tile: virtual rows R = 128*rt + 64*half .. +63  ->  (tap, co0)
+  int tap_h[2], co_h[2];
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    const int R = 128 * rt + 64 * hf;
+    tap_h[hf] = R / p.cout;
+    co_h[hf] = R - tap_h[hf] * p.cout;
+  }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int n0 = kb / p.kb_per_image, p0 = (kb - n0 * p.kb_per_image) * 64;
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+        mbar_expect_tx(full_bar + 8 * stage, STAGE_BYTES);
+        const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          int dyy = 0, dxx = 0;
+          const bool live = tap_h[hf] < p.taps;                 // rows past the last tap: any data, never stored
+          if (live && p.taps == 9) { dyy = tap_h[hf] / 3 - 1; dxx = tap_h[hf] % 3 - 1; }
+          // dy[q - (dyy,dxx)]: the column shift is in the copy (dx = +1: right-shifted, dx = -1: left-shifted), the row
+          // shift in the coordinate
+          const CUtensorMap* m = dxx > 0 ? &tmap_dy_r : (dxx < 0 ? &tmap_dy_l : &tmap_dy);
+          tma_load_3d(sa + hf * 8192, m, full_bar + 8 * stage, p0 - dyy * p.W, live ? co_h[hf] : 0, n0);
+        }
+        tma_load_3d(sb, &tmap_x, full_bar + 8 * stage, p0, ci0, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      const uint64_t adesc0 = make_sw128_desc(smem_base), bdesc0 = make_sw128_desc(smem_base + A_BYTES);
+      int stage = 0; uint32_t phase = 0;
+      uint32_t accum = 0u;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar + 8 * stage, phase);
+        tc_fence_after();
+        const uint64_t adesc = adesc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
+        const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
+        umma_bf16(tmem_base, adesc, bdesc, idesc, accum);
+#pragma unroll
+        for (int k = 1; k < BLOCK_K / UMMA_K; ++k) umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+        accum = 1u;
+        umma_commit(empty_bar + 8 * stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    // epilogue: rows of the slab -> (tap, co), columns -> ci; fp32 atomics into the OIHW gradient
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int hf = row >> 6;
+    const int tap = tap_h[hf], co = co_h[hf] + (row & 63);
+    const bool valid = tap < p.taps && kb1 > kb0;
+    if (lane == 0) mbar_wait(done_bar, 0);
+    __syncwarp();
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float* drow = p.dw + ((int64_t)co * p.cin + ci0) * p.taps + tap;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c0, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(drow + (int64_t)(c0 + j) * p.taps, __uint_as_float(r[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// NHWC (pixel stride ld) -> channel-major bf16 [B][C][HW]; optionally two more copies shifted by one pixel along W with
+// zero fill (y_r[h][w] = x[h][w-1], y_l[h][w] = x[h][w+1]) and the column sums (bias gradient)
+__global__ void __launch_bounds__(256)
+nhwc_to_chw_bf16_kernel(const bf16* __restrict__ x, int ld, bf16* __restrict__ y, bf16* __restrict__ y_l, bf16* __restrict__ y_r,
+                        float* __restrict__ colsum, int C, int HW, int W) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows per pass
+  float cs = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = p0 + ty + 8 * i;
+    float v = 0.f;
+    if (p < HW && c0 + tx < C) v = __bfloat162float(x[((int64_t)n * HW + p) * ld + c0 + tx]);
+    tile[ty + 8 * i][tx] = v;
+    cs += v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, p = p0 + tx;
+    if (c < C && p < HW) {
+      const bf16 v = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+      const int64_t o = ((int64_t)n * C + c) * HW + p;
+      y[o] = v;
+      if (y_l) {
+        const int w = p % W;
+        const bf16 z = __float2bfloat16_rn(0.f);
+        if (w != 0) y_l[o - 1] = v; else y_r[o] = z;          // y_l[p-1] = x[p];  y_r has no left neighbour at w = 0
+        if (w != W - 1) y_r[o + 1] = v; else y_l[o] = z;      // y_r[p+1] = x[p];  y_l has no right neighbour at w = W-1
+      }
+    }
+  }
+  if (colsum) {
+    __syncthreads();
+    tile[ty][tx] = cs;
+    __syncthreads();
+    if (ty == 0 && c0 + tx < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += tile[r][tx];
+      atomicAdd(colsum + c0 + tx, t);
+    }
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 g_encode_w = nullptr;
+int wg_init() {
+  if (g_encode_w) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  LDM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  LDM_REQUIRE(qres == cudaDriverEntryPointSuccess && fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  LDM_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (16384 + 64 * 128) + 2048));
+  LDM_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (16384 + 128 * 128) + 2048));
+  LDM_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (16384 + 256 * 128) + 2048));
+  g_encode_w = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return 0;
+}
+// channel-major tensor [B][C][HW] as dims (HW, C, N); box = {64 pixels, `rows` channels, 1 image}: K-major 128-byte rows
+int make_chw_map(CUtensorMap* map, const void* t, int B, int C, int HW, int rows) {
+  cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)HW * 2, (cuuint64_t)C * HW * 2};
+  cuuint32_t box[3] = {64u, (cuuint32_t)rows, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode_w(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(t), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LDM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(wgrad operand) failed with CUresult %d", (int)r);
+  return 0;
+}
+
+}  // namespace
+
+int k_nhwc_to_chw_bf16(const void* x, int ld, void* y, void* y_l, void* y_r, float* colsum, int batch, int C, int hw, int W,
+                       cudaStream_t st) {
+  if (batch == 0 || hw == 0) return 0;
+  nhwc_to_chw_bf16_kernel<<<dim3((hw + 31) / 32, (C + 31) / 32, batch), 256, 0, st>>>((const bf16*)x, ld, (bf16*)y, (bf16*)y_l,
+                                                                                   (bf16*)y_r, colsum, C, hw, W);
+  LDM_LAUNCHED("nhwc_to_chw_bf16");
+  return 0;
+}
+
+bool k_conv_wgrad_tc_applicable(int cin, int cout, int H, int W, int ksize, int dtype) {
+  if (dtype != LDM_DT_BF16 || (ksize != 1 && ksize != 3)) return false;
+  if (cin % 64 != 0 || cout % 64 != 0) return false;
+  if ((H * W) % 64 != 0 || W % 8 != 0) return false;   // k-blocks of 64 consecutive pixels; row shifts 16-byte aligned
+  return getenv("LDM_WGRAD_FFMA") == nullptr;
+}
+
+// xT [B][cin][HW]; dyT, dyT_l, dyT_r [B][cout][HW] (bf16, channel-major; _l / _r: shifted one pixel left / right with zero
+// fill, only read by 3x3 filters); dw OIHW fp32, ACCUMULATED
+int k_conv_wgrad_tc(const void* xT, int cin, const void* dyT, const void* dyT_l, const void* dyT_r, int cout, float* dw,
+                    int batch, int H, int W, int ksize, cudaStream_t st) {
+  if (int rc = wg_init()) return rc;
+  LDM_REQUIRE(k_conv_wgrad_tc_applicable(cin, cout, H, W, ksize, LDM_DT_BF16), "conv_wgrad_tc: unsupported shape");
+  if (batch == 0) return 0;
+  WgParams p;
+  p.cout = cout; p.cin = cin; p.taps = ksize * ksize; p.dw = dw; p.W = W;
+  const int hw = H * W;
+  p.kb_per_image = hw / 64;
+  p.kb_total = batch * p.kb_per_image;
+  int bn = 64;
+  for (int c : {256, 128}) if (cin % c == 0) { bn = c; break; }
+  p.row_tiles = (p.taps * cout + 127) / 128;
+  p.col_tiles = cin / bn;
+  const int tiles = p.row_tiles * p.col_tiles;
+  int splits = (2 * 148 + tiles - 1) / tiles;
+  if (splits > p.kb_total) splits = p.kb_total;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  CUtensorMap mdy, mdl, mdr, mx;
+  if (int rc = make_chw_map(&mdy, dyT, batch, cout, hw, 64)) return rc;
+  if (int rc = make_chw_map(&mdl, dyT_l ? dyT_l : dyT, batch, cout, hw, 64)) return rc;
+  if (int rc = make_chw_map(&mdr, dyT_r ? dyT_r : dyT, batch, cout, hw, 64)) return rc;
+  if (int rc = make_chw_map(&mx, xT, batch, cin, hw, bn)) return rc;
+  const dim3 grid(tiles, splits);
+  switch (bn) {
+    case 256: wgrad_tc_kernel<256><<<grid, 192, 4 * (16384 + 256 * 128) + 2048, st>>>(mdy, mdl, mdr, mx, p); break;
+    case 128: wgrad_tc_kernel<128><<<grid, 192, 6 * (16384 + 128 * 128) + 2048, st>>>(mdy, mdl, mdr, mx, p); break;
+    default: wgrad_tc_kernel<64><<<grid, 192, 6 * (16384 + 64 * 128) + 2048, st>>>(mdy, mdl, mdr, mx, p); break;
+  }
+  LDM_LAUNCHED("conv_wgrad_tc");
+  return 0;
+}

@@ -59,8 +59,14 @@ class _Conv(Function):
         buf = torch.zeros(w.numel() + cout, dtype=torch.float32, device=x.device)   # one fill for dW and db
         dw = buf[:w.numel()].view_as(w)
         db = buf[w.numel():] if ctx.has_bias else None
-        _lib.check(lib.ldm_conv2d_wgrad(x.data_ptr(), x.stride(2), cin, dy.data_ptr(), dy.stride(2), cout, dw.data_ptr(),
-                                        _lib.ptr(db), B, H, W, k, ops._dt(x), _st()))
+        nscr = lib.ldm_conv2d_wgrad_scratch_bytes(cin, cout, B, H, W, k, ops._dt(x)) if ctx.impl == 0 else 0
+        if nscr > 0:   # tcgen05: contraction over pixels on channel-major copies of x and dy
+            scr = torch.empty(nscr, dtype=torch.uint8, device=x.device)
+            _lib.check(lib.ldm_conv2d_wgrad_tc(x.data_ptr(), x.stride(2), cin, dy.data_ptr(), dy.stride(2), cout, dw.data_ptr(),
+                                               _lib.ptr(db), B, H, W, k, scr.data_ptr(), _st()))
+        else:
+            _lib.check(lib.ldm_conv2d_wgrad(x.data_ptr(), x.stride(2), cin, dy.data_ptr(), dy.stride(2), cout, dw.data_ptr(),
+                                            _lib.ptr(db), B, H, W, k, ops._dt(x), _st()))
         return dx, dw, db, None
 
 
