@@ -321,15 +321,37 @@ __global__ void unshuffle2_kernel(const T* __restrict__ dy, int lddy, T* __restr
 
 // ------------------------------------------------------------------ LinearAttention core backward, CTA per (b, head)
 // forward: qs = softmax_d(q) * s ; ks = softmax_n(k) ; ctx = ks^T v ; out = qs ctx      (src/UNet.py:149-163)
+// backward: dctx = qs^T dout ; dqs = dout ctx^T ; dks = v dctx^T ; dv = ks dctx ; then the two softmax backwards.
+// Every product is a 32x32x32 GEMM per 32-token tile; each is computed by 64 threads with 4x4 register blocks from
+// shared-memory operands stored in the orientation that makes both fragments one 16-byte load.
 #define LB_D 32
 #define LB_TILE 32
+#define LB_LD 36
+struct LbSmem {
+  float q_r[LB_TILE][LB_LD], k_r[LB_TILE][LB_LD], v_r[LB_TILE][LB_LD], do_r[LB_TILE][LB_LD];   // [token][channel]
+  float kT[LB_D][LB_LD], vT[LB_D][LB_LD], doT[LB_D][LB_LD];                                     // [channel][token]
+  float ctx[LB_D][LB_LD], ctxT[LB_D][LB_LD], dctx[LB_D][LB_LD], dctxT[LB_D][LB_LD];
+  float o_dqs[LB_TILE][LB_LD], o_dks[LB_TILE][LB_LD], o_dv[LB_TILE][LB_LD];
+  float kmax[LB_D], kzinv[LB_D], colsum[LB_D], red[8][LB_D];
+};
+// out[r0..r0+3][c0..c0+3] += sum_k AT[k][r0..] * B[k][c0..]   (AT, B: [32][LB_LD])
+__device__ __forceinline__ void lb_gemm4x4(const float (*AT)[LB_LD], const float (*B)[LB_LD], int r0, int c0, float (&acc)[4][4]) {
+#pragma unroll 8
+  for (int k = 0; k < 32; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(&AT[k][r0]);
+    const float4 b = *reinterpret_cast<const float4*>(&B[k][c0]);
+    const float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+  }
+}
 template <typename T>
 __global__ void __launch_bounds__(256)
 linattn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, T* __restrict__ dqkv, int N) {
-  __shared__ float ctx[LB_D][LB_D + 1], dctx[LB_D][LB_D + 1];
-  __shared__ float kmax[LB_D], kzinv[LB_D], colsum[LB_D];
-  __shared__ float red[8][LB_D];
-  __shared__ float tq[LB_TILE][LB_D + 1], tk[LB_TILE][LB_D + 1], tv[LB_TILE][LB_D + 1], tdo[LB_TILE][LB_D + 1];
+  extern __shared__ __align__(16) uint8_t lb_raw[];
+  LbSmem& S = *reinterpret_cast<LbSmem*>(lb_raw);
   const float scale = 0.17677669529663687f;
   const int b = blockIdx.x / 4, h = blockIdx.x % 4;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -339,90 +361,104 @@ linattn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, T* __r
   // ---- softmax-over-tokens statistics of k
   float m = -INFINITY;
   for (int n = warp; n < N; n += 8) m = fmaxf(m, ldf(base + (int64_t)n * 384 + 128 + lane));
-  red[warp][lane] = m;
+  S.red[warp][lane] = m;
   __syncthreads();
   if (warp == 0) {
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w][lane]);
-    kmax[lane] = m;
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, S.red[w][lane]);
+    S.kmax[lane] = m;
   }
   __syncthreads();
   float zs = 0.f;
-  for (int n = warp; n < N; n += 8) zs += expf(ldf(base + (int64_t)n * 384 + 128 + lane) - kmax[lane]);
+  for (int n = warp; n < N; n += 8) zs += expf(ldf(base + (int64_t)n * 384 + 128 + lane) - S.kmax[lane]);
   __syncthreads();
-  red[warp][lane] = zs;
+  S.red[warp][lane] = zs;
   __syncthreads();
   if (warp == 0) {
     float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += red[w][lane];
-    kzinv[lane] = 1.0f / t;
-    colsum[lane] = 0.f;
+    for (int w = 0; w < 8; ++w) t += S.red[w][lane];
+    S.kzinv[lane] = 1.0f / t;
+    S.colsum[lane] = 0.f;
   }
   __syncthreads();
-  // tile loader: tq <- softmax_d(q)*s, tk <- softmax_n(k), tv <- v, tdo <- dout   (rows >= N are zero)
+  // tile loader: q_r <- softmax_d(q)*s, k_r/kT <- softmax_n(k), v_r/vT <- v, do_r/doT <- dout   (rows >= N are zero)
   auto load_tile = [&](int n0) {
     for (int idx = tid; idx < LB_TILE * LB_D; idx += 256) {
       const int r = idx / LB_D, c = idx % LB_D, n = n0 + r;
       float qv = 0.f, kv = 0.f, vv = 0.f, dv = 0.f;
       if (n < N) {
         qv = ldf(base + (int64_t)n * 384 + c);
-        kv = expf(ldf(base + (int64_t)n * 384 + 128 + c) - kmax[c]) * kzinv[c];
+        kv = expf(ldf(base + (int64_t)n * 384 + 128 + c) - S.kmax[c]) * S.kzinv[c];
         vv = ldf(base + (int64_t)n * 384 + 256 + c);
         dv = ldf(dob + (int64_t)n * 128 + c);
       }
-      tq[r][c] = qv; tk[r][c] = kv; tv[r][c] = vv; tdo[r][c] = dv;
+      S.q_r[r][c] = qv;
+      S.k_r[r][c] = kv; S.kT[c][r] = kv;
+      S.v_r[r][c] = vv; S.vT[c][r] = vv;
+      S.do_r[r][c] = dv; S.doT[c][r] = dv;
     }
     __syncthreads();
-    // softmax over d for each row of tq (one warp per 4 rows)
-    for (int r = warp; r < LB_TILE; r += 8) {
-      const float v = tq[r][lane];
+    for (int r = warp; r < LB_TILE; r += 8) {   // softmax over d for each row of q_r
+      const float v = S.q_r[r][lane];
       const float mx = warp_max(v);
       const float e = expf(v - mx);
       const float sum = warp_sum(e);
-      tq[r][lane] = (n0 + r < N) ? e / sum * scale : 0.f;
+      S.q_r[r][lane] = (n0 + r < N) ? e / sum * scale : 0.f;
     }
     __syncthreads();
   };
-  // ---- ctx = ks^T v ; dctx = qs^T dout
-  const int d = tid >> 3, e0 = (tid & 7) * 4;
-  float c_acc[4] = {0.f, 0.f, 0.f, 0.f}, dc_acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int grp = tid >> 6, gt = tid & 63;           // four groups of 64 threads
+  const int r0 = (gt >> 3) * 4, c0 = (gt & 7) * 4;   // 4x4 block of a 32x32 output
+  // ---- sweep 1: ctx = ks^T v (group 0), dctx = qs^T dout (group 1)
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int n0 = 0; n0 < N; n0 += LB_TILE) {
     load_tile(n0);
-    for (int r = 0; r < LB_TILE; ++r) {
-      const float kk = tk[r][d], qq = tq[r][d];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        c_acc[j] = fmaf(kk, tv[r][e0 + j], c_acc[j]);
-        dc_acc[j] = fmaf(qq, tdo[r][e0 + j], dc_acc[j]);
-      }
-    }
+    if (grp == 0) lb_gemm4x4(S.k_r, S.v_r, r0, c0, acc);         // out[d][e] += sum_t ks[t][d] v[t][e]
+    else if (grp == 1) lb_gemm4x4(S.q_r, S.do_r, r0, c0, acc);   // out[d][e] += sum_t qs[t][d] dout[t][e]
     __syncthreads();
   }
+  if (grp < 2) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { ctx[d][e0 + j] = c_acc[j]; dctx[d][e0 + j] = dc_acc[j]; }
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (grp == 0) { S.ctx[r0 + i][c0 + j] = acc[i][j]; S.ctxT[c0 + j][r0 + i] = acc[i][j]; }
+        else { S.dctx[r0 + i][c0 + j] = acc[i][j]; S.dctxT[c0 + j][r0 + i] = acc[i][j]; }
+      }
+  }
   __syncthreads();
-  // ---- per token: dq, dv, dks (stored in the dk slot), column sums of ks*dks
-  const int tr = tid >> 3, part = tid & 7;  // 32 rows x 8 parts of 4 channels
+  // ---- sweep 2: per token tile  dqs = dout ctx^T (group 0), dks = v dctx^T (group 1), dv = ks dctx (group 2)
+  const int tr = tid >> 3, part = tid & 7;  // epilogue mapping: 32 rows x 8 parts of 4 channels
   float cs[4] = {0.f, 0.f, 0.f, 0.f};
   for (int n0 = 0; n0 < N; n0 += LB_TILE) {
     load_tile(n0);
+    if (grp < 3) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      float (*O)[LB_LD] = grp == 0 ? S.o_dqs : (grp == 1 ? S.o_dks : S.o_dv);
+      if (grp == 0) lb_gemm4x4(S.doT, S.ctxT, r0, c0, acc);        // out[t][d] = sum_e dout[t][e] ctx[d][e]
+      else if (grp == 1) lb_gemm4x4(S.vT, S.dctxT, r0, c0, acc);   // out[t][d] = sum_e v[t][e] dctx[d][e]
+      else lb_gemm4x4(S.kT, S.dctx, r0, c0, acc);                  // out[t][e] = sum_d ks[t][d] dctx[d][e]
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(&O[r0 + i][c0]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+    __syncthreads();
     const int n = n0 + tr;
-    // dqs[d] = sum_e ctx[d][e] dout[e] ; inner = sum_d qhat[d] dqhat[d] with qs = s*qhat
-    float dqs[4], dks[4], dvv[4];
+    float dqs[4], dks[4], dvv[4], qv[4], kv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int dd = part * 4 + j;
-      float a = 0.f, bsum = 0.f, cacc = 0.f;
-      for (int e = 0; e < LB_D; ++e) {
-        a = fmaf(ctx[dd][e], tdo[tr][e], a);
-        bsum = fmaf(dctx[dd][e], tv[tr][e], bsum);
-        cacc = fmaf(tk[tr][e], dctx[e][dd], cacc);  // dv[e' = dd] = sum_d ks[d] dctx[d][dd]
-      }
-      dqs[j] = a; dks[j] = bsum; dvv[j] = cacc;
+      dqs[j] = S.o_dqs[tr][part * 4 + j]; dks[j] = S.o_dks[tr][part * 4 + j]; dvv[j] = S.o_dv[tr][part * 4 + j];
+      qv[j] = S.q_r[tr][part * 4 + j]; kv[j] = S.k_r[tr][part * 4 + j];
     }
-    // <qs, dqs> over the 32 channels of the row: 8 consecutive threads
-    float inner = 0.f;
+    float inner = 0.f;   // <qs, dqs> over the 32 channels of the row: 8 consecutive threads
 #pragma unroll
-    for (int j = 0; j < 4; ++j) inner = fmaf(tq[tr][part * 4 + j], dqs[j], inner);
+    for (int j = 0; j < 4; ++j) inner = fmaf(qv[j], dqs[j], inner);
     inner += __shfl_xor_sync(0xffffffffu, inner, 1);
     inner += __shfl_xor_sync(0xffffffffu, inner, 2);
     inner += __shfl_xor_sync(0xffffffffu, inner, 4);
@@ -430,26 +466,24 @@ linattn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, T* __r
       float dq[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        // qs = s*qhat, dL/dqhat = s*dqs, dq = qhat*(dL/dqhat - <qhat, dL/dqhat>) = qs*(dqs - inner/s ... ) with inner = <qs,dqs>
-        dq[j] = tq[tr][part * 4 + j] * (dqs[j] - inner / scale);
-        cs[j] = fmaf(tk[tr][part * 4 + j], dks[j], cs[j]);
+        dq[j] = qv[j] * (dqs[j] - inner / scale);   // qs = s*qhat: dq = qs * (dqs - <qs,dqs>/s)
+        cs[j] = fmaf(kv[j], dks[j], cs[j]);
       }
       st4<T>(dbase + (int64_t)n * 384 + part * 4, dq);
-      st4<T>(dbase + (int64_t)n * 384 + 128 + part * 4, dks);
+      st4<T>(dbase + (int64_t)n * 384 + 128 + part * 4, dks);   // dks parked in the dk slot until colsum is known
       st4<T>(dbase + (int64_t)n * 384 + 256 + part * 4, dvv);
     }
     __syncthreads();
   }
-  // colsum[d] = sum_n ks[n][d] dks[n][d]
 #pragma unroll
-  for (int j = 0; j < 4; ++j) atomicAdd(&colsum[part * 4 + j], cs[j]);
+  for (int j = 0; j < 4; ++j) atomicAdd(&S.colsum[part * 4 + j], cs[j]);   // colsum[d] = sum_n ks[n][d] dks[n][d]
   __syncthreads();
   // ---- dk = ks * (dks - colsum)
   for (int idx = tid; idx < N * LB_D; idx += 256) {
     const int n = idx / LB_D, c = idx % LB_D;
-    const float ks = expf(ldf(base + (int64_t)n * 384 + 128 + c) - kmax[c]) * kzinv[c];
+    const float ks = expf(ldf(base + (int64_t)n * 384 + 128 + c) - S.kmax[c]) * S.kzinv[c];
     T* p = dbase + (int64_t)n * 384 + 128 + c;
-    *p = from_float<T>(ks * (to_float(*p) - colsum[c]));
+    *p = from_float<T>(ks * (to_float(*p) - S.colsum[c]));
   }
 }
 
@@ -784,7 +818,13 @@ int k_unshuffle2(const void* dy, int lddy, void* out, int batch, int H, int W, i
 
 int k_linear_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int N, int dtype, cudaStream_t st) {
   if (batch == 0 || N == 0) return 0;
-  DISPATCH_T(dtype, linattn_bwd_kernel<T><<<batch * 4, 256, 0, st>>>((const T*)qkv, (const T*)dout, (T*)dqkv, N));
+  static bool attr_set = false;
+  if (!attr_set) {
+    LDM_CUDA(cudaFuncSetAttribute(linattn_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbSmem)));
+    LDM_CUDA(cudaFuncSetAttribute(linattn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbSmem)));
+    attr_set = true;
+  }
+  DISPATCH_T(dtype, linattn_bwd_kernel<T><<<batch * 4, 256, sizeof(LbSmem), st>>>((const T*)qkv, (const T*)dout, (T*)dqkv, N));
   LDM_LAUNCHED("linear_attention_backward");
   return 0;
 }
