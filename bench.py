@@ -410,6 +410,12 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+        try:
+            import torch.distributed as tdist
+            if tdist.is_initialized():
+                tdist.destroy_process_group()
+        except Exception:
+            pass
 
 
 if __name__ == "__main__":
