@@ -184,12 +184,23 @@ def train_leg(args, dev, rank, world, stream):
     x0 = (torch.rand(B, 3, 32, 32, generator=g) * 2 - 1).pin_memory()
     y = torch.randint(0, 10, (B,), generator=g).pin_memory()
     bucket = None
+    fwd = model
+    graphed = False
+    if not args.train_eager:
+        try:   # forward + backward of the UNet replayed as CUDA graphs (ldm_b200.train.make_graphed)
+            from ldm_b200 import train as ltrain
+            n0, xt0, t0 = diffusion(x0.to(dev))
+            fwd = ltrain.make_graphed(model, xt0, t0, y.to(dev))
+            graphed = True
+        except Exception as exc:   # noqa: BLE001 -- the eager autograd path is always available
+            sys.stderr.write(f"bench: graphed training unavailable ({exc}); using eager autograd\n")
+            fwd = model
 
     def step():
         nonlocal bucket
         data, targets = x0.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
         noise, xt, t = diffusion(data)
-        loss = torch.nn.functional.mse_loss(noise, model(xt, t, targets))
+        loss = torch.nn.functional.mse_loss(noise, fwd(xt, t, targets))
         opt.zero_grad(set_to_none=True)
         loss.backward()
         bucket = ldist.sync_gradients(model.parameters(), bucket)
@@ -214,8 +225,8 @@ def train_leg(args, dev, rank, world, stream):
             tdist.barrier()
     ms = ldist.max_over_ranks(e0.elapsed_time(e1), dev)
     return {"metric": "cifar10_ddpm_train_images_per_sec", "value": B * world * n / (ms / 1e3), "unit": "images/s",
-            "batch_per_gpu": B, "steps": n, "ms_per_step": ms / n, "loss": lv,
-            "note": "q_sample + UNet fwd + MSE + bwd (FFMA wgrad, tcgen05 fwd/dgrad) + grad all-reduce + torch Adam; "
+            "batch_per_gpu": B, "steps": n, "ms_per_step": ms / n, "loss": lv, "cuda_graphs": graphed,
+            "note": "q_sample + UNet fwd + MSE + bwd (tcgen05 fwd/dgrad/wgrad, FFMA below 8x8) + grad all-reduce + torch Adam; "
                     "4.536 GFLOP/image"}
 
 
@@ -405,6 +416,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
     ap.add_argument("--train-batch", type=int, default=64)
+    ap.add_argument("--train-eager", action="store_true", help="do not capture the training forward/backward as CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

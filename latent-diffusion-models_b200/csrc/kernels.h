@@ -155,5 +155,10 @@ int k_copy_channels(const void* src, int lds, void* dst, int ldd, int C, int64_t
 int k_nhwc_to_chw_bf16(const void* x, int ld, void* y, void* y_l, void* y_r, float* colsum, int batch, int C, int hw, int W,
                        cudaStream_t st);
 bool k_conv_wgrad_tc_applicable(int cin, int cout, int H, int W, int ksize, int dtype);
+bool k_conv_wgrad_tc_flat_applicable(int cin, int cout, int batch, int H, int W, int ksize, int dtype);
+int k_nhwc_to_flat_taps_bf16(const void* x, int ld, void* y, float* colsum, int batch, int C, int H, int W, int taps,
+                             cudaStream_t st);
+int k_conv_wgrad_tc_flat(const void* xF, int cin, const void* dyF, int cout, float* dw, int batch, int H, int W, int ksize,
+                         cudaStream_t st);
 int k_conv_wgrad_tc(const void* xT, int cin, const void* dyT, const void* dyT_l, const void* dyT_r, int cout, float* dw,
                     int batch, int H, int W, int ksize, cudaStream_t st);

@@ -12,6 +12,8 @@ int ldm_conv2d_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, 
   return k_conv_wgrad(x, ldx, cin, dy, lddy, cout, dw_oihw, dbias, batch, height, width, ksize, dtype, (cudaStream_t)stream);
 }
 int64_t ldm_conv2d_wgrad_scratch_bytes(int cin, int cout, int batch, int height, int width, int ksize, int dtype) {
+  if (k_conv_wgrad_tc_flat_applicable(cin, cout, batch, height, width, ksize, dtype))
+    return ((int64_t)batch * height * width * (cin + (int64_t)ksize * ksize * cout) * 2 + 255) / 256 * 256 + 256;
   if (!k_conv_wgrad_tc_applicable(cin, cout, height, width, ksize, dtype)) return 0;
   return (int64_t)batch * height * width * (cin + (ksize == 3 ? 3 : 1) * (int64_t)cout) * 2 + 4 * 256;
 }
@@ -23,6 +25,13 @@ int ldm_conv2d_wgrad_tc(const void* x, int ldx, int cin, const void* dy, int ldd
   cudaStream_t st = (cudaStream_t)stream;
   const int hw = height * width;
   auto up = [](int64_t v) { return (v + 255) / 256 * 256; };
+  if (k_conv_wgrad_tc_flat_applicable(cin, cout, batch, height, width, ksize, LDM_DT_BF16)) {
+    char* xF = (char*)scratch;
+    char* dyF = xF + up((int64_t)batch * hw * cin * 2);
+    RC(k_nhwc_to_flat_taps_bf16(x, ldx, xF, nullptr, batch, cin, height, width, 1, st));
+    RC(k_nhwc_to_flat_taps_bf16(dy, lddy, dyF, dbias, batch, cout, height, width, ksize * ksize, st));
+    return k_conv_wgrad_tc_flat(xF, cin, dyF, cout, dw_oihw, batch, height, width, ksize, st);
+  }
   char* xT = (char*)scratch;
   char* dyT = xT + up((int64_t)batch * hw * cin * 2);
   char* dyL = ksize == 3 ? dyT + up((int64_t)batch * hw * cout * 2) : nullptr;

@@ -27,6 +27,7 @@ struct WgParams {
   int kb_total, kb_per_split; // k-blocks of 64 pixels
   int kb_per_image;           // H*W / 64
   int W;
+  int flat;                   // 1: operands are [C][B*HW] (x) and [tap][C][B*HW] (dy, shifted per tap) -- images below 8x8
   float* dw;
 };
 
@@ -78,6 +79,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
         mbar_wait(empty_bar + 8 * stage, phase ^ 1);
         mbar_expect_tx(full_bar + 8 * stage, STAGE_BYTES);
         const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+        if (p.flat) {   // every tap has its own pre-shifted copy; k runs over the pixels of the whole batch
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const bool live = tap_h[hf] < p.taps;
+            tma_load_3d(sa + hf * 8192, &tmap_dy, full_bar + 8 * stage, kb * 64, live ? co_h[hf] : 0, live ? tap_h[hf] : 0);
+          }
+          tma_load_3d(sb, &tmap_x, full_bar + 8 * stage, kb * 64, ci0, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          continue;
+        }
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           int dyy = 0, dxx = 0;
@@ -187,6 +198,57 @@ nhwc_to_chw_bf16_kernel(const bf16* __restrict__ x, int ld, bf16* __restrict__ y
   }
 }
 
+// NHWC rows [M = B*HW][C] -> per-tap shifted channel-major copies y[tap][c][m'] with m' = the pixel one filter offset away
+// (inside the same image; the buffer is zeroed first so positions nobody writes are the conv's zero padding); column
+// sums for the bias gradient.  taps == 1: a plain transpose.
+__global__ void __launch_bounds__(256)
+nhwc_to_flat_taps_kernel(const bf16* __restrict__ x, int ld, bf16* __restrict__ y, float* __restrict__ colsum, int C, int M,
+                         int H, int W, int taps) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.y * 32, m0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float cs = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty + 8 * i;
+    float v = 0.f;
+    if (m < M && c0 + tx < C) v = __bfloat162float(x[(int64_t)m * ld + c0 + tx]);
+    tile[ty + 8 * i][tx] = v;
+    cs += v;
+  }
+  __syncthreads();
+  const int m = m0 + tx;
+  const int HW = H * W;
+  const int n = m / HW, r = m - n * HW, h = r / W, w = r - h * W;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i;
+    if (c < C && m < M) {
+      const bf16 v = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+      if (taps == 1) {
+        y[(int64_t)c * M + m] = v;
+      } else {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+          if (hh >= 0 && hh < H && ww >= 0 && ww < W) y[((int64_t)t * C + c) * M + n * HW + hh * W + ww] = v;
+        }
+      }
+    }
+  }
+  if (colsum) {
+    __syncthreads();
+    tile[ty][tx] = cs;
+    __syncthreads();
+    if (ty == 0 && c0 + tx < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int r2 = 0; r2 < 8; ++r2) t += tile[r2][tx];
+      atomicAdd(colsum + c0 + tx, t);
+    }
+  }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 g_encode_w = nullptr;
 int wg_init() {
   if (g_encode_w) return 0;
@@ -201,7 +263,7 @@ int wg_init() {
   return 0;
 }
 // channel-major tensor [B][C][HW] as dims (HW, C, N); box = {64 pixels, `rows` channels, 1 image}: K-major 128-byte rows
-int make_chw_map(CUtensorMap* map, const void* t, int B, int C, int HW, int rows) {
+int make_chw_map(CUtensorMap* map, const void* t, int B, int C, int64_t HW, int rows) {
   cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
   cuuint64_t gstr[2] = {(cuuint64_t)HW * 2, (cuuint64_t)C * HW * 2};
   cuuint32_t box[3] = {64u, (cuuint32_t)rows, 1u};
@@ -224,12 +286,35 @@ int k_nhwc_to_chw_bf16(const void* x, int ld, void* y, void* y_l, void* y_r, flo
   return 0;
 }
 
+int k_nhwc_to_flat_taps_bf16(const void* x, int ld, void* y, float* colsum, int batch, int C, int H, int W, int taps,
+                             cudaStream_t st) {
+  const int M = batch * H * W;
+  if (M == 0) return 0;
+  if (taps > 1) LDM_CUDA(cudaMemsetAsync(y, 0, (size_t)taps * C * M * 2, st));
+  nhwc_to_flat_taps_kernel<<<dim3((M + 31) / 32, (C + 31) / 32), 256, 0, st>>>((const bf16*)x, ld, (bf16*)y, colsum, C, M, H, W, taps);
+  LDM_LAUNCHED("nhwc_to_flat_taps_bf16");
+  return 0;
+}
+
+// images too small for 64-pixel k-blocks inside one image: k runs over the pixels of the whole batch instead
+bool k_conv_wgrad_tc_flat_applicable(int cin, int cout, int batch, int H, int W, int ksize, int dtype) {
+  if (dtype != LDM_DT_BF16 || (ksize != 1 && ksize != 3)) return false;
+  if (cin % 64 != 0 || cout % 64 != 0) return false;
+  if (k_conv_wgrad_tc_applicable(cin, cout, H, W, ksize, dtype)) return false;
+  const int64_t M = (int64_t)batch * H * W;
+  if (M % 8 != 0 || M < 64 || H * W > 64) return false;   // 16-byte row pitch; 9 shifted copies only pay for small images
+  return getenv("LDM_WGRAD_FFMA") == nullptr;
+}
+
 bool k_conv_wgrad_tc_applicable(int cin, int cout, int H, int W, int ksize, int dtype) {
   if (dtype != LDM_DT_BF16 || (ksize != 1 && ksize != 3)) return false;
   if (cin % 64 != 0 || cout % 64 != 0) return false;
   if ((H * W) % 64 != 0 || W % 8 != 0) return false;   // k-blocks of 64 consecutive pixels; row shifts 16-byte aligned
   return getenv("LDM_WGRAD_FFMA") == nullptr;
 }
+
+static int wg_launch(const void* xT, int cin, const void* dyT, const void* dyT_l, const void* dyT_r, int cout, float* dw,
+                     int batch, int H, int W, int ksize, int flat, cudaStream_t st);
 
 // xT [B][cin][HW]; dyT, dyT_l, dyT_r [B][cout][HW] (bf16, channel-major; _l / _r: shifted one pixel left / right with zero
 // fill, only read by 3x3 filters); dw OIHW fp32, ACCUMULATED
@@ -238,11 +323,25 @@ int k_conv_wgrad_tc(const void* xT, int cin, const void* dyT, const void* dyT_l,
   if (int rc = wg_init()) return rc;
   LDM_REQUIRE(k_conv_wgrad_tc_applicable(cin, cout, H, W, ksize, LDM_DT_BF16), "conv_wgrad_tc: unsupported shape");
   if (batch == 0) return 0;
+  return wg_launch(xT, cin, dyT, dyT_l, dyT_r, cout, dw, batch, H, W, ksize, 0, st);
+}
+
+// xF [cin][B*HW]; dyF [taps][cout][B*HW], copy t shifted by filter offset t (k_nhwc_to_flat_taps_bf16); dw ACCUMULATED
+int k_conv_wgrad_tc_flat(const void* xF, int cin, const void* dyF, int cout, float* dw, int batch, int H, int W, int ksize,
+                         cudaStream_t st) {
+  if (int rc = wg_init()) return rc;
+  LDM_REQUIRE(k_conv_wgrad_tc_flat_applicable(cin, cout, batch, H, W, ksize, LDM_DT_BF16), "conv_wgrad_tc_flat: unsupported shape");
+  return wg_launch(xF, cin, dyF, nullptr, nullptr, cout, dw, batch, H, W, ksize, 1, st);
+}
+
+static int wg_launch(const void* xT, int cin, const void* dyT, const void* dyT_l, const void* dyT_r, int cout, float* dw,
+                     int batch, int H, int W, int ksize, int flat, cudaStream_t st) {
   WgParams p;
-  p.cout = cout; p.cin = cin; p.taps = ksize * ksize; p.dw = dw; p.W = W;
+  p.cout = cout; p.cin = cin; p.taps = ksize * ksize; p.dw = dw; p.W = W; p.flat = flat;
   const int hw = H * W;
-  p.kb_per_image = hw / 64;
-  p.kb_total = batch * p.kb_per_image;
+  const int64_t M = (int64_t)batch * hw;
+  p.kb_per_image = flat ? 1 : hw / 64;
+  p.kb_total = flat ? (int)((M + 63) / 64) : batch * p.kb_per_image;
   int bn = 64;
   for (int c : {256, 128}) if (cin % c == 0) { bn = c; break; }
   p.row_tiles = (p.taps * cout + 127) / 128;
@@ -254,10 +353,16 @@ int k_conv_wgrad_tc(const void* xT, int cin, const void* dyT, const void* dyT_l,
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   CUtensorMap mdy, mdl, mdr, mx;
-  if (int rc = make_chw_map(&mdy, dyT, batch, cout, hw, 64)) return rc;
-  if (int rc = make_chw_map(&mdl, dyT_l ? dyT_l : dyT, batch, cout, hw, 64)) return rc;
-  if (int rc = make_chw_map(&mdr, dyT_r ? dyT_r : dyT, batch, cout, hw, 64)) return rc;
-  if (int rc = make_chw_map(&mx, xT, batch, cin, hw, bn)) return rc;
+  if (flat) {
+    if (int rc = make_chw_map(&mdy, dyT, p.taps, cout, M, 64)) return rc;
+    mdl = mdy; mdr = mdy;
+    if (int rc = make_chw_map(&mx, xT, 1, cin, M, bn)) return rc;
+  } else {
+    if (int rc = make_chw_map(&mdy, dyT, batch, cout, hw, 64)) return rc;
+    if (int rc = make_chw_map(&mdl, dyT_l ? dyT_l : dyT, batch, cout, hw, 64)) return rc;
+    if (int rc = make_chw_map(&mdr, dyT_r ? dyT_r : dyT, batch, cout, hw, 64)) return rc;
+    if (int rc = make_chw_map(&mx, xT, batch, cin, hw, bn)) return rc;
+  }
   const dim3 grid(tiles, splits);
   switch (bn) {
     case 256: wgrad_tc_kernel<256><<<grid, 192, 4 * (16384 + 256 * 128) + 2048, st>>>(mdy, mdl, mdr, mx, p); break;

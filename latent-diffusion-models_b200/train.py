@@ -418,3 +418,12 @@ def unet_autograd_forward(model, x_noisy: torch.Tensor, t: torch.Tensor, y: Opti
         h = _attn_site(attn, h, True, impl)
     h = _resblock(model.final_conv[0], h, None, impl)
     return _FinalConv.apply(h, model.final_conv[1].weight.view(model.out_channels, model.channels), model.final_conv[1].bias)
+
+
+def make_graphed(model, x_noisy: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor]):
+    """Capture the UNet's training forward and backward as CUDA graphs (torch.cuda.make_graphed_callables): the ~500
+    kernel launches of a step are replayed instead of re-issued from Python, which is what bounds small batches.
+    Returns a callable with the model's signature for inputs of exactly these shapes (labels given or not, as captured);
+    gradients land in the same fp32 ``.grad`` tensors.  The four dead bottleneck mlp_t parameters are unused inputs."""
+    args = (x_noisy.detach().clone(), t.detach().clone()) + ((y.detach().clone(),) if y is not None else ())
+    return torch.cuda.make_graphed_callables(model, args, allow_unused_input=True)

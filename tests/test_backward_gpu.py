@@ -38,7 +38,10 @@ def nchw(x):
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("B,cin,cout,R,k,bias", [(2, 64, 128, 16, 3, True), (3, 128, 64, 32, 3, True), (2, 64, 384, 8, 1, False),
-                                                 (5, 512, 512, 2, 3, True), (2, 768, 256, 4, 3, True)])
+                                                 (5, 512, 512, 2, 3, True), (2, 768, 256, 4, 3, True),
+                                                 # below 8x8 with B*H*W % 8 == 0: the batch-flattened tcgen05 wgrad
+                                                 (16, 512, 512, 2, 3, True), (24, 768, 256, 4, 3, True),
+                                                 (10, 256, 1024, 4, 1, False), (6, 128, 192, 4, 3, True)])
 def test_conv_backward(dtype, B, cin, cout, R, k, bias):
     from ldm_b200 import train
     g = torch.Generator().manual_seed(cin + cout + R)
