@@ -179,13 +179,16 @@ def train_leg(args, dev, rank, world, stream):
     torch.manual_seed(42)
     model = ldm_b200.UNet(3, 3, 64, (1, 2, 4, 8), True, 10, dtype=args.dtype).to(dev)
     diffusion = ldm_b200.Diffusion(args.n_steps, dev)
-    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    from ldm_b200 import trainer as ltrainer
+    # Adam with the reference's settings (src/Trainer.py:68-71) over flat buffers: packs the gradients, all-reduces them
+    # (N > 1) and updates all 20.35 M parameters in one launch.  Built before the graph capture: it re-homes p.data.
+    opt = ltrainer.FlatAdam(model.parameters(), lr=5e-4)
     g = torch.Generator().manual_seed(rank)
     x0 = (torch.rand(B, 3, 32, 32, generator=g) * 2 - 1).pin_memory()
     y = torch.randint(0, 10, (B,), generator=g).pin_memory()
-    bucket = None
     fwd = model
     graphed = False
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # the leg runs on the bench's side stream
     if not args.train_eager:
         try:   # forward + backward of the UNet replayed as CUDA graphs (ldm_b200.train.make_graphed)
             from ldm_b200 import train as ltrain
@@ -197,15 +200,8 @@ def train_leg(args, dev, rank, world, stream):
             fwd = model
 
     def step():
-        nonlocal bucket
         data, targets = x0.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
-        noise, xt, t = diffusion(data)
-        loss = torch.nn.functional.mse_loss(noise, fwd(xt, t, targets))
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        bucket = ldist.sync_gradients(model.parameters(), bucket)
-        opt.step()
-        return loss
+        return ltrainer.train_step(model, diffusion, opt, data, targets, forward=fwd)
 
     with torch.cuda.stream(stream):
         for _ in range(3):
@@ -226,7 +222,8 @@ def train_leg(args, dev, rank, world, stream):
     ms = ldist.max_over_ranks(e0.elapsed_time(e1), dev)
     return {"metric": "cifar10_ddpm_train_images_per_sec", "value": B * world * n / (ms / 1e3), "unit": "images/s",
             "batch_per_gpu": B, "steps": n, "ms_per_step": ms / n, "loss": lv, "cuda_graphs": graphed,
-            "note": "q_sample + UNet fwd + MSE + bwd (tcgen05 fwd/dgrad/wgrad, FFMA below 8x8) + grad all-reduce + torch Adam; "
+            "optimizer": "ldm_adam_step over flat buffers (one launch)",
+            "note": "q_sample + UNet fwd + MSE + bwd (tcgen05 fwd / dgrad / wgrad) + flat-gradient all-reduce + Adam; "
                     "4.536 GFLOP/image"}
 
 
@@ -303,6 +300,34 @@ def run_ours(args):
         assert res.device.type == "cpu" and tuple(res.shape) == shape
         e2e_ms = ldist.max_over_ranks(max(s0.elapsed_time(s1), wall_ms), dev)
 
+        # ---- the other two settings SURVEY.md 8(d) asks to be reported beside the headline: T = 400 (the reference YAML's
+        # n_steps) and cfg_scale = 0 (one UNet pass per timestep); plus the e2e call returning uint8 images
+        variants = {}
+        if not args.no_variants:
+            d400 = ldm_b200.Diffusion(400, dev)
+
+            def timed(fn, reps=1):
+                fn()
+                torch.cuda.synchronize(dev)
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(reps):
+                    fn()
+                b.record(stream)
+                torch.cuda.synchronize(dev)
+                barrier()
+                return B * world * reps / (ldist.max_over_ranks(a.elapsed_time(b), dev) / 1e3)
+
+            variants["T400_cfg3_images_per_sec"] = timed(lambda: d400.sample(
+                model, classes_dev, shape, dev, cfg_scale=cfg, seed=5, sample_offset=offset, return_device=True))
+            variants["T1000_cfg0_images_per_sec"] = timed(lambda: diffusion.sample(
+                model, classes_dev, shape, dev, cfg_scale=0, seed=6, sample_offset=offset, return_device=True))
+            from ldm_b200 import ops as lops
+            variants["e2e_uint8_output_images_per_sec"] = timed(lambda: lops.images_to_uint8(diffusion.sample(
+                model, classes_host, shape, dev, cfg_scale=cfg, x_T=x_T_host, seed=99, sample_offset=offset,
+                return_device=True), "save_image").cpu())
+
         # ---- roofline leg: every launch of one 2B-row UNet pass timed with CUDA events on this stream
         prof = None
         if rank == 0:
@@ -377,7 +402,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_T_host.numel() * 4 + classes_host.numel() * 8,
                 "d2h_bytes_per_step": x_T_host.numel() * 4, "steps": e2e_steps},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_rec,
-        "unet_tflops": unet_tflops, "train": train,
+        "unet_tflops": unet_tflops, "variants": variants, "train": train,
     }
     emit(line)
 
@@ -415,6 +440,7 @@ def main():
     ap.add_argument("--cpu-timesteps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
+    ap.add_argument("--no-variants", action="store_true", help="skip the T=400 / cfg 0 / uint8-output variant timings")
     ap.add_argument("--train-batch", type=int, default=64)
     ap.add_argument("--train-eager", action="store_true", help="do not capture the training forward/backward as CUDA graphs")
     args = ap.parse_args()

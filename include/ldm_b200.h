@@ -291,6 +291,25 @@ int ldm_copy_channels(const void* src, int ld_src, void* dst, int ld_dst, int ch
 int ldm_linear_attention_qkv(const void* xn, int ldx, int cin, const void* wqkv_packed, void* out, int batch, int n_tokens,
                              int dtype, void* stream);
 
+/* ---- after the hot path: optimizer step, validation loss, image output ----------------- */
+
+/* torch.optim.Adam(params, lr) with its defaults, as src/Trainer.py:68-71 constructs it (no weight decay, no amsgrad),
+ * over FLAT fp32 device buffers of n elements (16-byte aligned): one launch for the whole model instead of one foreach
+ * group per tensor list.  step counts from 1.  grad is multiplied by grad_scale first (1/world_size after an
+ * all-reduce(sum); 1/loss_scale under AMP, src/DiffusionModelTrainer.py:55-63).  Elements whose gradient is zero and
+ * whose moments are zero are left unchanged, which is what skipping a grad-less parameter does in torch. */
+int ldm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, int step, double grad_scale, void* stream);
+
+/* fp32 NCHW images -> uint8 NHWC bytes on the device (one quarter of the D2H traffic of the fp32 tensor).
+ * convention 0 = torchvision.utils.save_image as called by save_images (src/utils.py:121-130): x*255+0.5, clamp, truncate;
+ * convention 1 = get_reverse_image_transform (src/transforms.py:22-35): ((x+1)/2)*255 then numpy astype(uint8)
+ *                (truncate toward zero, low byte kept: out-of-range values wrap exactly as numpy's cast does). */
+int ldm_images_to_uint8(const float* x_nchw, uint8_t* out_nhwc, int batch, int channels, int hw, int convention, void* stream);
+
+/* F.mse_loss(a, b) (mean reduction; src/Trainer.py:59, src/DiffusionModelTrainer.py:52,105) -> one device float */
+int ldm_mse(const float* a, const float* b, float* out_scalar, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,6 +108,9 @@ SIGNATURES = {
     "ldm_add": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int, vp]),
     "ldm_copy_channels": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp]),
     "ldm_linear_attention_qkv": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_adam_step": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, vp]),
+    "ldm_images_to_uint8": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_mse": (C.c_int, [vp, vp, vp, C.c_int64, vp]),
     "ldm_nchw_to_nhwc": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_nhwc_to_nchw": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
 }

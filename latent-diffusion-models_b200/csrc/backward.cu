@@ -622,22 +622,44 @@ __global__ void final_conv_dx_kernel(const float* __restrict__ dout, const float
     st4<T>(dx + i * cin + c0, v);
   }
 }
-// dw[o][c] += sum_pix dout[b][o][p] x[pix][c];  db[o] += sum dout.   grid (msplit), 256 threads
+// dw[o][c] += sum_pix dout[b][o][p] x[pix][c];  db[o] += sum dout.   grid (msplit), 256 threads = pixel lanes x channel
+// lanes (cpad = channels rounded up to a power of two): x rows are read coalesced, dout is a warp-uniform broadcast.
 template <typename T>
 __global__ void __launch_bounds__(256)
 final_conv_dw_kernel(const float* __restrict__ dout, const T* __restrict__ x, int ldx, float* __restrict__ dw,
-                     float* __restrict__ db, int cin, int cout, int HW, int64_t total, int m_per_split) {
-  const int64_t m0 = (int64_t)blockIdx.x * m_per_split, m1 = min(total, m0 + (int64_t)m_per_split);
-  for (int idx = threadIdx.x; idx < cout * cin; idx += blockDim.x) {
-    const int o = idx / cin, c = idx % cin;
-    float acc = 0.f;
-    for (int64_t m = m0; m < m1; ++m) acc = fmaf(dout[((m / HW) * cout + o) * HW + (m % HW)], ldf(x + m * ldx + c), acc);
-    atomicAdd(dw + idx, acc);
-  }
-  for (int o = threadIdx.x; o < cout; o += blockDim.x) {
-    float acc = 0.f;
-    for (int64_t m = m0; m < m1; ++m) acc += dout[((m / HW) * cout + o) * HW + (m % HW)];
-    atomicAdd(db + o, acc);
+                     float* __restrict__ db, int cin, int cout, int HW, int total, int m_per_split, int cpad) {
+  __shared__ float red[256];
+  const int m0 = blockIdx.x * m_per_split, m1 = min(total, m0 + m_per_split);
+  const int cl = threadIdx.x % cpad, pl = threadIdx.x / cpad, lanes = 256 / cpad;
+  for (int c = cl; c < ((cin + cpad - 1) / cpad) * cpad; c += cpad) {
+    const bool live = c < cin;
+    for (int o0 = 0; o0 < cout; o0 += 4) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int m = m0 + pl; m < m1; m += lanes) {
+        const float xv = live ? ldf(x + (int64_t)m * ldx + c) : 0.f;
+        const int b = m / HW, p = m - b * HW;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (o0 + j < cout) {
+            const float d = __ldg(dout + ((int64_t)b * cout + o0 + j) * HW + p);
+            acc[j] = fmaf(d, xv, acc[j]);
+            ds[j] += d;
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {   // 4 weight-gradient columns, then the 4 bias sums (channel lane 0 only)
+        red[threadIdx.x] = j < 4 ? acc[j & 3] : ds[j & 3];
+        __syncthreads();
+        if (pl == 0 && o0 + (j & 3) < cout) {
+          float t = 0.f;
+          for (int l = 0; l < lanes; ++l) t += red[l * cpad + cl];
+          if (j < 4) { if (live) atomicAdd(dw + (o0 + j) * cin + c, t); }
+          else if (c == 0) atomicAdd(db + o0 + (j & 3), t);
+        }
+        __syncthreads();
+      }
+    }
   }
 }
 
@@ -850,7 +872,7 @@ int k_initial_conv_wgrad(const float* x, const void* dy, float* dw, float* dbias
   const int M = batch * H * W;
   if (M == 0) return 0;
   LDM_REQUIRE(cin >= 1 && cin <= 4, "initial_conv_wgrad: in_channels %d not in [1,4]", cin);
-  const int mps = split_for(M, 64, 2 * 148);
+  const int mps = split_for(M, 64, 8 * 148);
   const int grid = (M + mps - 1) / mps;
 #define IW_GO(C) DISPATCH_T(dtype, initial_wgrad_kernel<T, C><<<grid, 256, 0, st>>>(x, (const T*)dy, dw, dbias, batch, cout, H, W, mps))
   switch (cin) {
@@ -871,8 +893,12 @@ int k_final_conv_backward(const float* dout, const void* x, int ldx, const float
   if (total == 0) return 0;
   DISPATCH_T(dtype, final_conv_dx_kernel<T><<<(int)ceil_div64(total, 128), 128, 0, st>>>(dout, w, (T*)dx, cin, cout, hw, total));
   LDM_LAUNCHED("final_conv_dx");
-  const int mps = split_for(total, 128, 2 * 148);
-  DISPATCH_T(dtype, final_conv_dw_kernel<T><<<(int)((total + mps - 1) / mps), 256, 0, st>>>(dout, (const T*)x, ldx, dw, db, cin, cout, hw, total, mps));
+  LDM_REQUIRE(total < (int64_t)1 << 31, "final_conv_backward: batch too large");
+  const int mps = split_for(total, 64, 8 * 148);
+  int cpad = 1;
+  while (cpad < cin && cpad < 256) cpad *= 2;
+  DISPATCH_T(dtype, final_conv_dw_kernel<T><<<(int)((total + mps - 1) / mps), 256, 0, st>>>(dout, (const T*)x, ldx, dw, db, cin, cout, hw,
+                                                                                       (int)total, mps, cpad));
   LDM_LAUNCHED("final_conv_dw");
   return 0;
 }

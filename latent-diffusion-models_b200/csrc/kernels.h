@@ -162,3 +162,9 @@ int k_conv_wgrad_tc_flat(const void* xF, int cin, const void* dyF, int cout, flo
                          cudaStream_t st);
 int k_conv_wgrad_tc(const void* xT, int cin, const void* dyT, const void* dyT_l, const void* dyT_r, int cout, float* dw,
                     int batch, int H, int W, int ksize, cudaStream_t st);
+
+// ---- trainer_ops.cu: Adam step over flat fp32 buffers, uint8 image output, MSE
+int k_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
+                int step, double grad_scale, cudaStream_t st);
+int k_images_to_u8(const float* x, uint8_t* out, int batch, int C, int hw, int convention, cudaStream_t st);
+int k_mse(const float* a, const float* b, float* out, int64_t n, cudaStream_t st);

@@ -190,4 +190,20 @@ int ldm_copy_channels(const void* src, int ld_src, void* dst, int ld_dst, int ch
   return k_copy_channels(src, ld_src, dst, ld_dst, channels, rows, dtype, (cudaStream_t)stream);
 }
 
+
+// ---- optimizer step, validation loss and output stage
+int ldm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, int step, double grad_scale, void* stream) {
+  LDM_REQUIRE(param && grad && exp_avg && exp_avg_sq, "ldm_adam_step: null argument");
+  return k_adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, (cudaStream_t)stream);
+}
+int ldm_images_to_uint8(const float* x_nchw, uint8_t* out_nhwc, int batch, int channels, int hw, int convention, void* stream) {
+  LDM_REQUIRE(x_nchw && out_nhwc, "ldm_images_to_uint8: null argument");
+  return k_images_to_u8(x_nchw, out_nhwc, batch, channels, hw, convention, (cudaStream_t)stream);
+}
+int ldm_mse(const float* a, const float* b, float* out_scalar, int64_t n, void* stream) {
+  LDM_REQUIRE(a && b && out_scalar, "ldm_mse: null argument");
+  return k_mse(a, b, out_scalar, n, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -143,3 +143,23 @@ def max_pool2x2(x: torch.Tensor) -> torch.Tensor:
     _lib.check(_lib.load().ldm_max_pool2x2(x.data_ptr(), x.stride(2), out.data_ptr(), C, B, H, W, C, _dt(x),
                                            _lib.stream_ptr()))
     return out
+
+
+_U8_CONVENTIONS = {"save_image": 0, "reverse_transform": 1}
+
+
+def images_to_uint8(x_nchw: torch.Tensor, convention: str = "save_image") -> torch.Tensor:
+    """fp32 [B,C,H,W] -> uint8 [B,H,W,C] on the device.  ``save_image``: what torchvision.utils.save_image writes for the
+    raw tensor (src/utils.py:121-130); ``reverse_transform``: the reference's PIL path (src/transforms.py:22-35)."""
+    _cuda(x_nchw)
+    if convention not in _U8_CONVENTIONS:
+        raise ValueError(f"convention must be one of {sorted(_U8_CONVENTIONS)}")
+    x = x_nchw.detach().to(torch.float32).contiguous()
+    B, Cc, H, W = x.shape
+    out = torch.empty(B, H, W, Cc, dtype=torch.uint8, device=x.device)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ldm_images_to_uint8(x.data_ptr(), out.data_ptr(), B, Cc, H * W, _U8_CONVENTIONS[convention],
+                                                   _lib.stream_ptr()))
+    return out

@@ -1,0 +1,211 @@
+"""What the reference does either side of the denoising hot path in its trainer:
+the optimizer step, the validation (CFG) loss and the image output stage, on the C ABI.
+
+* ``FlatAdam``        -- ``torch.optim.Adam(model.parameters(), lr)`` as ``Trainer._get_optimizer`` builds it
+                         (src/Trainer.py:68-71): parameters, gradients and both moments live in four flat fp32 buffers;
+                         one all-reduce over the gradient buffer (data parallel) and ONE kernel launch update the model.
+* ``train_step``      -- the body of ``DiffusionModelTrainer._train_epoch`` (src/DiffusionModelTrainer.py:36-67).
+* ``val_step``        -- the body of ``_val_epoch`` (:79-118): cond + uncond in one 2B-row UNet pass, lerp, MSE.
+* ``DiffusionModelTrainer`` -- the reference class's compute methods (forward / sample / _train_epoch / _val_epoch);
+                         logging, early stopping and checkpoint files stay with the caller (out of scope).
+
+CUDA only: there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .ops import images_to_uint8  # noqa: F401  (re-exported: the output stage belongs to this layer)
+
+
+class FlatAdam:
+    """Adam with torch's defaults (betas 0.9/0.999, eps 1e-8, no weight decay, no amsgrad) over flat buffers.
+
+    On construction every parameter's storage is moved into one flat fp32 buffer (``p.data`` becomes a view into it, so
+    the module, its ``state_dict()`` and the native weight re-pack keep working).  ``step()`` packs the ``.grad`` tensors
+    into the flat gradient buffer (zeros for parameters without one, e.g. the reference's four dead bottleneck ``mlp_t``
+    tensors, so every rank reduces the same length), all-reduces it when a process group is up, and launches
+    ``ldm_adam_step`` once.  The 1/world_size of the mean is folded into the kernel's ``grad_scale``.
+    """
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.params: List[torch.nn.Parameter] = [p for p in params]
+        if not self.params:
+            raise ValueError("FlatAdam: no parameters")
+        dev = self.params[0].device
+        for p in self.params:
+            if p.device != dev or not p.is_cuda or p.dtype != torch.float32:
+                raise _lib.LdmError("FlatAdam: parameters must be fp32 CUDA tensors on one device (no CPU path)")
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.device = dev
+        sizes = [p.numel() for p in self.params]
+        self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        n = int(self.offsets[-1])
+        self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.grad_views = []
+        with torch.no_grad():
+            for p, o, k in zip(self.params, self.offsets[:-1], sizes):
+                view = self.flat_param[int(o):int(o) + k].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                self.grad_views.append(self.flat_grad[int(o):int(o) + k].view_as(p))
+        self.step_count = 0
+        self._dead_zeroed = False
+
+    # torch.optim.Optimizer surface used by the reference (src/DiffusionModelTrainer.py:55-63)
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        for p in self.params:
+            if set_to_none or p.grad is None:
+                p.grad = None
+            else:
+                p.grad.zero_()
+
+    @torch.no_grad()
+    def step(self, grad_scale: float = 1.0) -> None:
+        src, dst, dead = [], [], []
+        for p, v in zip(self.params, self.grad_views):
+            if p.grad is None:
+                dead.append(v)
+            else:
+                src.append(p.grad)
+                dst.append(v)
+        if dead:
+            torch._foreach_zero_(dead)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        scale = float(grad_scale)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)      # NCCL over NVLink; the mean's 1/world is in the kernel
+            scale /= dist.get_world_size()
+        self.step_count += 1
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().ldm_adam_step(self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
+                                                 self.exp_avg_sq.data_ptr(), self.flat_param.numel(), self.lr, self.betas[0],
+                                                 self.betas[1], self.eps, self.step_count, scale, _lib.stream_ptr()))
+        torch.autograd.graph.increment_version(self.params)   # the kernel wrote through raw pointers: tell torch (and the
+        #                                                       UNet's weight re-pack, which keys on ._version)
+
+    def state_dict(self) -> dict:
+        return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "lr": self.lr, "betas": self.betas, "eps": self.eps}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.lr, self.betas, self.eps = float(sd["lr"]), tuple(sd["betas"]), float(sd["eps"])
+
+
+def mse_loss(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """F.mse_loss(a, b) for fp32 CUDA tensors without gradients -> 0-dim device tensor (ldm_mse)."""
+    a = a.detach().to(torch.float32).contiguous()
+    b = b.detach().to(torch.float32).contiguous()
+    if not a.is_cuda or a.shape != b.shape:
+        raise _lib.LdmError("mse_loss: two CUDA tensors of one shape expected (no CPU path)")
+    out = torch.empty((), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().ldm_mse(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _lib.stream_ptr()))
+    return out
+
+
+def train_step(model, diffusion, optimizer, data: torch.Tensor, targets: Optional[torch.Tensor], *, drop_labels: bool = False,
+               forward: Optional[Callable] = None, loss_fn: Callable = torch.nn.functional.mse_loss) -> torch.Tensor:
+    """One iteration of ``_train_epoch`` (src/DiffusionModelTrainer.py:36-67): noise, forward, MSE, backward, optimizer.
+    ``drop_labels`` is the reference's 10 % coin (:44), drawn by the caller so that all ranks agree.  ``forward`` may be a
+    CUDA-graphed callable from ``ldm_b200.train.make_graphed``.  Returns the (device) loss; the caller decides when to sync."""
+    noise, xt, t = diffusion(data)
+    y = None if drop_labels else targets
+    fwd = forward if forward is not None else model
+    eps_theta = fwd(xt, t, y) if y is not None else fwd(xt, t)
+    loss = loss_fn(noise, eps_theta)
+    optimizer.zero_grad(set_to_none=True)
+    loss.backward()
+    optimizer.step()
+    return loss.detach()
+
+
+@torch.no_grad()
+def val_step(model, diffusion, data: torch.Tensor, targets: Optional[torch.Tensor], cfg_scale: float) -> torch.Tensor:
+    """One iteration of ``_val_epoch`` (:94-107): eps(x_t, t, y), and when cfg_scale > 0 also eps(x_t, t, None) and
+    lerp(eps_u, eps_c, cfg_scale); the two predictions come from ONE UNet pass over 2B rows (first B conditional)."""
+    noise, xt, t = diffusion(data)
+    B = xt.shape[0]
+    if cfg_scale > 0 and targets is not None:
+        both = model._forward_nograd(torch.cat((xt, xt)), torch.cat((t, t)), targets, y_rows=B)
+        eps = torch.lerp(both[B:], both[:B], float(cfg_scale))
+    else:
+        eps = model._forward_nograd(xt, t, targets)
+        if cfg_scale > 0:   # reference: both passes unconditional, the lerp is the identity
+            eps = torch.lerp(eps, eps, float(cfg_scale))
+    return mse_loss(noise, eps)
+
+
+class DiffusionModelTrainer:
+    """Compute methods of ``src.DiffusionModelTrainer.DiffusionModelTrainer`` on the native path.
+
+    ``config`` needs ``lr``, ``epochs`` and ``data.image_channels`` / ``data.image_size`` (mapping or attribute access).
+    The reference's wandb logging, early stopping and checkpoint writing are the caller's business."""
+
+    def __init__(self, config, model, diffusion, train_loader=None, val_loader=None, classes=None, cfg_scale: float = 0.0,
+                 device=None, rng: Optional[np.random.Generator] = None):
+        get = (lambda k: config[k]) if hasattr(config, "__getitem__") else (lambda k: getattr(config, k))
+        self.config, self.model, self.diffusion = config, model, diffusion
+        self.train_loader, self.val_loader = train_loader, val_loader
+        self.classes, self.cfg_scale = classes, cfg_scale
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        self.epochs = int(get("epochs")) if self._has(config, "epochs") else 1
+        self.optimizer = FlatAdam(model.parameters(), lr=float(get("lr")))
+        self.loss_fn = torch.nn.functional.mse_loss
+        self._rng = rng if rng is not None else np.random.default_rng()
+        self._get = get
+
+    @staticmethod
+    def _has(config, key) -> bool:
+        try:
+            return key in config
+        except TypeError:
+            return hasattr(config, key)
+
+    def forward(self, x, t, targets=None):                      # src/DiffusionModelTrainer.py:151-160
+        return self.model(x, t) if targets is None else self.model(x, t, targets)
+
+    def _train_epoch(self, epoch: int) -> float:                 # :28-77
+        self.model.train()
+        total = torch.zeros((), dtype=torch.float64, device=self.device)
+        for data, targets in self.train_loader:
+            data, targets = data.to(self.device, non_blocking=True), targets.to(self.device, non_blocking=True)
+            loss = train_step(self.model, self.diffusion, self.optimizer, data, targets,
+                              drop_labels=bool(self._rng.random() < 0.1), loss_fn=self.loss_fn)
+            total += loss.double() * data.size(0)                # accumulated on the device: one sync per epoch, not per step
+        return float(total.item()) / len(self.train_loader)
+
+    def _val_epoch(self, epoch: int) -> float:                   # :79-118
+        self.model.eval()
+        total = torch.zeros((), dtype=torch.float64, device=self.device)
+        for data, targets in self.val_loader:
+            data, targets = data.to(self.device, non_blocking=True), targets.to(self.device, non_blocking=True)
+            total += val_step(self.model, self.diffusion, data, targets, self.cfg_scale).double() * data.size(0)
+        return float(total.item()) / len(self.val_loader)
+
+    def sample(self, classes, cfg_scale=0, as_uint8: bool = False):   # :162-180
+        data = self._get("data")
+        dget = (lambda k: data[k]) if hasattr(data, "__getitem__") else (lambda k: getattr(data, k))
+        shape = (len(classes), int(dget("image_channels")), int(dget("image_size")), int(dget("image_size")))
+        x = self.diffusion.sample(self.model, classes, shape=shape, device=self.device, cfg_scale=cfg_scale,
+                                  return_device=as_uint8)
+        if as_uint8:   # the reverse transform (src/transforms.py:22-35) on the device; HWC uint8 arrays, ready for PIL
+            return list(images_to_uint8(x, "reverse_transform").cpu().numpy())
+        return x
+
+    def to(self, device):                                        # :182-185
+        self.device = torch.device(device)
+        self.model.to(self.device)
+        self.diffusion.to(self.device)

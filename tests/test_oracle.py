@@ -145,3 +145,37 @@ def test_against_live_reference():
         assert rel_l2(U.unet_forward(sd, x, t, y), ref(x, t, y)) < 2e-6
     for m in [k for k in list(sys.modules) if k == "src" or k.startswith("src.")]:
         del sys.modules[m]
+
+
+# ---------------------------------------------------------------- steps either side of the hot path
+def test_adam_matches_torch_optim_golden():
+    from oracle import trainer_oracle as TO
+    g = golden("g7_adam.npz")
+    for j in range(3):
+        p = T(g[f"p0_{j}"]).clone()
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+        for s in range(int(g["steps"])):
+            TO.adam_step(p, T(g[f"grads_{j}"][s]), m, v, s + 1, float(g["lr"]))
+        assert rel_l2(p, T(g[f"p_final_{j}"])) < 1e-7
+        assert rel_l2(m, T(g[f"exp_avg_{j}"])) < 1e-6
+        assert rel_l2(v, T(g[f"exp_avg_sq_{j}"])) < 1e-6
+
+
+def test_output_stage_matches_reference_golden():
+    from oracle import trainer_oracle as TO
+    g = golden("g8_output.npz")
+    assert np.array_equal(TO.images_to_uint8(g["x"], "reverse_transform"), g["reverse_transform"])
+    assert np.array_equal(TO.images_to_uint8(g["x"], "save_image"), g["save_image"])
+    assert np.array_equal(TO.images_to_uint8(g["x_gray"], "reverse_transform")[..., 0], g["reverse_transform_gray"])
+
+
+def test_val_loss_matches_reference_golden():
+    from oracle import trainer_oracle as TO
+    g = golden("g9_val_loss.npz")
+    sd = oracle.init_state_dict(int(g["weight_seed"]), 3, 3, 64, (1, 2, 4, 8), True, 10)
+    sched = D.make_schedule(1000)
+    with torch.no_grad():
+        l3 = TO.val_loss(sd, sched, T(g["x0"]), T(g["noise"]), T(g["t"]), T(g["y"]), 3.0)
+        l0 = TO.val_loss(sd, sched, T(g["x0"]), T(g["noise"]), T(g["t"]), T(g["y"]), 0.0)
+    assert abs(float(l3) - float(g["loss_cfg3"])) < 1e-5 * float(g["loss_cfg3"])
+    assert abs(float(l0) - float(g["loss_cfg0"])) < 1e-5 * float(g["loss_cfg0"])
