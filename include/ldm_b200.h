@@ -310,6 +310,23 @@ int ldm_images_to_uint8(const float* x_nchw, uint8_t* out_nhwc, int batch, int c
 /* F.mse_loss(a, b) (mean reduction; src/Trainer.py:59, src/DiffusionModelTrainer.py:52,105) -> one device float */
 int ldm_mse(const float* a, const float* b, float* out_scalar, int64_t n, void* stream);
 
+/* ---- first-stage autoencoder (src/Autoencoder.py) ------------------------------------------
+ * Its 3x3 / 1x1 convolutions are ldm_conv2d; ldm_group_norm takes GroupNorm(32, C, eps=1e-6) + swish for every group
+ * width (:9-18).  The remaining pieces: */
+/* f.interpolate(x, scale_factor=2, mode="nearest") on NHWC (UpSample, :142-157) */
+int ldm_upsample_nearest2x(const void* x, int ldx, void* y, int ldy, int batch, int height, int width, int channels, int dtype,
+                           void* stream);
+/* y[n,i,j,:] = x[n,2i+1,2j+1,:]: applied to a full-resolution pad-1 3x3 conv it yields DownSample's
+ * pad (0,1,0,1) + stride-2 conv exactly (:160-180) */
+int ldm_downsample_pick(const void* x, int ldx, void* y, int ldy, int batch, int height, int width, int channels, int dtype,
+                        void* stream);
+/* AttnBlock core (:118-130): qkv [B][N][3C] (q | k | v) -> out [B][N][C] = softmax_j(C^-1/2 q_i.k_j) v_j, one head */
+int ldm_attention_single_head(const void* qkv, void* out, int batch, int n_tokens, int channels, int dtype, void* stream);
+/* GaussianDistribution (:21-43): moments NHWC (pixel stride ld; channels [0,Z) = mu, [Z,2Z) = log variance) -> fp32 NCHW
+ * mu, log_var, sigma = exp(log_var/2) and z = mu + sigma*eps; any output pointer may be NULL (z needs eps) */
+int ldm_gaussian_distribution(const void* moments, int ld, const float* eps, float* mu, float* log_var, float* sigma, float* z,
+                              int batch, int z_channels, int hw, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,6 +108,10 @@ SIGNATURES = {
     "ldm_add": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int, vp]),
     "ldm_copy_channels": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp]),
     "ldm_linear_attention_qkv": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_upsample_nearest2x": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_downsample_pick": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_attention_single_head": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_gaussian_distribution": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_adam_step": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, vp]),
     "ldm_images_to_uint8": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_mse": (C.c_int, [vp, vp, vp, C.c_int64, vp]),

@@ -453,6 +453,9 @@ int k_group_norm_mod(const void* x, int ldx, void* y, int ldy, const void* res, 
                      const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
                      float eps, int silu, int dtype, void* workspace, int x_mod, cudaStream_t st) {
   const int V = dtype == LDM_DT_BF16 ? 8 : 4;
+  if (groups >= 1 && channels % groups == 0 && (channels / groups) % V != 0 && res == nullptr && rowvec == nullptr && x_mod == 0)
+    // groups narrower than a vector chunk (the autoencoder's GroupNorm(32, C) at 64 / 128 channels, src/Autoencoder.py:9-11)
+    return k_group_norm_any(x, ldx, y, ldy, gamma, beta, batch, hw, channels, groups, eps, silu, dtype, st);
   LDM_REQUIRE(groups >= 1 && groups <= GN_MAX_GROUPS, "group_norm: groups=%d unsupported", groups);
   LDM_REQUIRE(channels % groups == 0 && (channels / groups) % V == 0,
               "group_norm: channels/groups (%d/%d) must be a multiple of %d", channels, groups, V);

@@ -168,3 +168,12 @@ int k_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double 
                 int step, double grad_scale, cudaStream_t st);
 int k_images_to_u8(const float* x, uint8_t* out, int batch, int C, int hw, int convention, cudaStream_t st);
 int k_mse(const float* a, const float* b, float* out, int64_t n, cudaStream_t st);
+
+// ---- autoencoder.cu: the first-stage autoencoder's extra pieces (src/Autoencoder.py)
+int k_group_norm_any(const void* x, int ldx, void* y, int ldy, const float* gamma, const float* beta, int batch, int hw,
+                     int channels, int groups, float eps, int silu, int dtype, cudaStream_t st);
+int k_upsample_nearest2x(const void* x, int ldx, void* y, int ldy, int batch, int H, int W, int C, int dtype, cudaStream_t st);
+int k_pick_odd(const void* x, int ldx, void* y, int ldy, int batch, int H, int W, int C, int dtype, cudaStream_t st);
+int k_attention_single_head(const void* qkv, void* out, int batch, int n_tokens, int channels, int dtype, cudaStream_t st);
+int k_gaussian(const void* moments, int ld, const float* eps, float* mu, float* log_var, float* sigma, float* z, int batch,
+               int zc, int hw, int dtype, cudaStream_t st);

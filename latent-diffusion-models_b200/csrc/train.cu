@@ -206,4 +206,26 @@ int ldm_mse(const float* a, const float* b, float* out_scalar, int64_t n, void* 
   return k_mse(a, b, out_scalar, n, (cudaStream_t)stream);
 }
 
+
+// ---- first-stage autoencoder (src/Autoencoder.py), the pieces beyond the UNet's conv / GroupNorm kernels
+int ldm_upsample_nearest2x(const void* x, int ldx, void* y, int ldy, int batch, int height, int width, int channels, int dtype,
+                           void* stream) {
+  LDM_REQUIRE(x && y, "ldm_upsample_nearest2x: null argument");
+  return k_upsample_nearest2x(x, ldx, y, ldy, batch, height, width, channels, dtype, (cudaStream_t)stream);
+}
+int ldm_downsample_pick(const void* x, int ldx, void* y, int ldy, int batch, int height, int width, int channels, int dtype,
+                        void* stream) {
+  LDM_REQUIRE(x && y, "ldm_downsample_pick: null argument");
+  return k_pick_odd(x, ldx, y, ldy, batch, height, width, channels, dtype, (cudaStream_t)stream);
+}
+int ldm_attention_single_head(const void* qkv, void* out, int batch, int n_tokens, int channels, int dtype, void* stream) {
+  LDM_REQUIRE(qkv && out, "ldm_attention_single_head: null argument");
+  return k_attention_single_head(qkv, out, batch, n_tokens, channels, dtype, (cudaStream_t)stream);
+}
+int ldm_gaussian_distribution(const void* moments, int ld, const float* eps, float* mu, float* log_var, float* sigma, float* z,
+                              int batch, int z_channels, int hw, int dtype, void* stream) {
+  LDM_REQUIRE(moments, "ldm_gaussian_distribution: null argument");
+  return k_gaussian(moments, ld, eps, mu, log_var, sigma, z, batch, z_channels, hw, dtype, (cudaStream_t)stream);
+}
+
 }  // extern "C"

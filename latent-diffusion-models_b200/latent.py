@@ -46,8 +46,11 @@ class LatentDiffusionModel(nn.Module):
         d.set_schedule(self.beta.data, self.alpha_bar.data)
         return d
 
-    def autoencoder_encode(self, image: torch.Tensor):
-        return self.latent_scaling_factor * self.autoencoder.encode(image).sample()
+    def autoencoder_encode(self, image: torch.Tensor, epsilon: torch.Tensor = None):
+        """Scaled latent of the image (:57-65).  ``epsilon`` (keyword, ours) fixes the reparameterisation noise for parity
+        tests; it is only passed on when given, so any autoencoder with the reference's ``encode(image)`` works."""
+        dist = self.autoencoder.encode(image) if epsilon is None else self.autoencoder.encode(image, epsilon)
+        return self.latent_scaling_factor * dist.sample()
 
     def autoencoder_decode(self, z: torch.Tensor):
         return self.autoencoder.decode(z / self.latent_scaling_factor)

@@ -7,6 +7,10 @@ g7_adam.npz      torch.optim.Adam(params, lr=5e-4) exactly as src/Trainer.py:68-
 g8_output.npz    the reference's reverse transform (src/transforms.py:22-35,58-66) and save_images (src/utils.py:121-130,
                  PNG bytes decoded again) on images that leave [-1, 1]
 g9_val_loss.npz  one `_val_epoch` batch (src/DiffusionModelTrainer.py:94-107) with the reference UNet / Diffusion, cfg 3 and 0
+g10_autoencoder_*.npz  src.Autoencoder.Autoencoder encode (mu, log_var, epsilon, sample), decode and forward, two configurations
+g11_ldm_latent.npz     LatentDiffusionModel (src/LatentDiffusionModel.py): schedule, scaled encode, eps-prediction on the latent
+                       shape, 3 reverse steps with the model's own schedule, decode (through self.autoencoder: the
+                       reference's autoencoder_decode raises AttributeError on `first_stage_model`, :72)
 """
 from __future__ import annotations
 
@@ -100,6 +104,73 @@ def main():
         loss_cfg0 = torch.nn.functional.mse_loss(noise, eps_c)
     save("g9_val_loss.npz", x0=x0, noise=noise, t=t, y=y, loss_cfg3=loss_cfg3, loss_cfg0=loss_cfg0, weight_seed=0)
     print("G9 ok", float(loss_cfg3), float(loss_cfg0))
+
+    # ---------------- G10: autoencoder ----------------
+    import hashlib
+    from src.Autoencoder import Autoencoder
+    from src.LatentDiffusionModel import LatentDiffusionModel
+
+    def sha(sd):
+        h = hashlib.sha256()
+        for k in sd:
+            h.update(k.encode())
+            h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+        return np.frombuffer(h.digest(), dtype=np.uint8)
+
+    for tag, cfgv, cin in (("ldm", (3, 4, 3, 64, [1, 2], 2), 3), ("deep", (1, 8, 1, 64, [1, 2, 4], 1), 1)):
+        torch.manual_seed(21)
+        ae = Autoencoder(*cfgv).eval()
+        g = torch.Generator().manual_seed(22)
+        img = torch.rand(2, cin, 32, 32, generator=g) * 2 - 1
+        with torch.no_grad():
+            torch.manual_seed(23)
+            dist = ae.encode(img)
+            zs = dist.sample()
+            rec = ae.decode(zs)
+            torch.manual_seed(23)
+            fwd_img, fwd_mu, fwd_lv = ae(img)
+        assert torch.equal(fwd_mu, dist.mu)
+        save(f"g10_autoencoder_{tag}.npz", img=img, mu=dist.mu, log_var=dist.log_var, epsilon=dist.epsilon, z=zs, recon=rec,
+             forward_img=fwd_img, weight_seed=21, weight_sha256=sha(ae.state_dict()), config=np.array(
+                 [cfgv[0], cfgv[1], cfgv[2], cfgv[3], cfgv[5]] + list(cfgv[4])))
+        print("G10", tag, tuple(zs.shape), float(rec.std()))
+
+    # ---------------- G11: latent diffusion model ----------------
+    torch.manual_seed(31)
+    unet = UNet(4, 4, 64, [1, 2, 4, 8], True, 10).eval()
+    torch.manual_seed(21)
+    ae = Autoencoder(3, 4, 3, 64, [1, 2], 2).eval()
+    ldm = LatentDiffusionModel(unet, ae, 0.18215, 1000, 0.00085, 0.012).eval()
+    g = torch.Generator().manual_seed(32)
+    img = torch.rand(2, 3, 32, 32, generator=g) * 2 - 1
+    y = torch.tensor([3, 7])
+    with torch.no_grad():
+        torch.manual_seed(33)
+        z0 = ldm.autoencoder_encode(img)
+        t = torch.tensor([999, 500])
+        eps_pred = ldm(z0, t, y)
+        # three reverse steps with the LDM's own schedule (DDPM.p_sample arithmetic, src/DDPM.py:71-96) from z0 as x_T
+        diff = Diffusion(1000, "cpu")
+        diff.beta = ldm.beta.data.clone()
+        diff.alpha = 1.0 - diff.beta
+        diff.alpha_bar = ldm.alpha_bar.data.clone()
+        diff.sigma2 = diff.beta
+        x = z0.clone()
+        zn = torch.randn(3, *z0.shape, generator=g)
+        for i, step in enumerate((999, 998, 997)):
+            tt = torch.full((2,), step, dtype=torch.long)
+            e_c, e_u = ldm(x, tt, y), ldm(x, tt, None)
+            eps = torch.lerp(e_u, e_c, 3.0)
+            ab, al = diff.alpha_bar[step], diff.alpha[step]
+            mean = (x - (1 - al) / (1 - ab) ** 0.5 * eps) / al ** 0.5
+            x = mean + diff.sigma2[step] ** 0.5 * zn[i]
+        dec = ldm.autoencoder.decode(x / ldm.latent_scaling_factor)
+    torch.manual_seed(33)
+    with torch.no_grad():
+        eps_used = ae.encode(img).epsilon
+    save("g11_ldm_latent.npz", img=img, y=y, t=t, z0=z0, encode_epsilon=eps_used, eps_pred=eps_pred, step_noise=zn, x_after3=x,
+         decoded=dec, beta=ldm.beta.data, alpha_bar=ldm.alpha_bar.data, unet_seed=31, ae_seed=21)
+    print("G11", float(eps_pred.std()), float(dec.std()))
 
 
 if __name__ == "__main__":

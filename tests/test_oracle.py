@@ -179,3 +179,55 @@ def test_val_loss_matches_reference_golden():
         l0 = TO.val_loss(sd, sched, T(g["x0"]), T(g["noise"]), T(g["t"]), T(g["y"]), 0.0)
     assert abs(float(l3) - float(g["loss_cfg3"])) < 1e-5 * float(g["loss_cfg3"])
     assert abs(float(l0) - float(g["loss_cfg0"])) < 1e-5 * float(g["loss_cfg0"])
+
+
+# ---------------------------------------------------------------- first-stage autoencoder and the latent model
+def _ae_from_golden(g, **kw):
+    import ldm_b200
+    cfg = [int(v) for v in g["config"]]
+    torch.manual_seed(int(g["weight_seed"]))
+    ae = ldm_b200.Autoencoder(cfg[0], cfg[1], cfg[2], cfg[3], cfg[5:], cfg[4], **kw)
+    return ae
+
+
+@pytest.mark.parametrize("tag", ["ldm", "deep"])
+def test_autoencoder_oracle_matches_reference_golden(tag):
+    from oracle import autoencoder_oracle as A
+    g = golden(f"g10_autoencoder_{tag}.npz")
+    ae = _ae_from_golden(g)                       # parameter holders only: built on the CPU, never called
+    sd = {k: v.detach() for k, v in ae.state_dict().items()}
+    assert _sha(sd) == bytes(g["weight_sha256"]), "holder construction order no longer reproduces the reference's init"
+    img = T(g["img"])
+    with torch.no_grad():
+        mu, lv = A.encode_moments(sd, img)
+        z = A.gaussian_sample(mu, lv, T(g["epsilon"]))
+        rec = A.decode(sd, z)
+    assert rel_l2(mu, T(g["mu"])) < 2e-6 and rel_l2(lv, T(g["log_var"])) < 2e-6
+    assert rel_l2(z, T(g["z"])) < 2e-6
+    assert rel_l2(rec, T(g["recon"])) < 5e-6
+    assert rel_l2(rec, T(g["forward_img"])) < 5e-6
+
+
+def test_latent_diffusion_oracle_matches_reference_golden():
+    from oracle import autoencoder_oracle as A
+    import ldm_b200
+    g = golden("g11_ldm_latent.npz")
+    sched = D.make_ldm_schedule(1000, 0.00085, 0.012)
+    assert torch.equal(sched["beta"], T(g["beta"])) and torch.equal(sched["alpha_bar"], T(g["alpha_bar"]))
+    sched = dict(sched, alpha=1.0 - sched["beta"], sigma2=sched["beta"])   # what a Diffusion built on this schedule derives
+    torch.manual_seed(int(g["ae_seed"]))
+    ae_sd = {k: v.detach() for k, v in ldm_b200.Autoencoder(3, 4, 3, 64, [1, 2], 2).state_dict().items()}
+    unet_sd = oracle.init_state_dict(int(g["unet_seed"]), 4, 4, 64, (1, 2, 4, 8), True, 10)
+    y = T(g["y"])
+    with torch.no_grad():
+        mu, lv = A.encode_moments(ae_sd, T(g["img"]))
+        z0 = 0.18215 * A.gaussian_sample(mu, lv, T(g["encode_epsilon"]))
+        assert rel_l2(z0, T(g["z0"])) < 2e-6
+        assert rel_l2(U.unet_forward(unet_sd, z0, T(g["t"]), y), T(g["eps_pred"])) < 5e-6
+        x = z0
+        for i, step in enumerate((999, 998, 997)):
+            tt = torch.full((2,), step, dtype=torch.long)
+            eps = D.cfg_combine(U.unet_forward(unet_sd, x, tt, y), U.unet_forward(unet_sd, x, tt, None), 3.0)
+            x = D.p_sample(sched, x, tt, eps, T(g["step_noise"][i]))
+        assert rel_l2(x, T(g["x_after3"])) < 1e-5
+        assert rel_l2(A.decode(ae_sd, x / 0.18215), T(g["decoded"])) < 1e-5

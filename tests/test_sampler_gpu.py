@@ -65,6 +65,22 @@ def test_graph_equals_eager_and_sharding_invariance(dtype):
     assert d.last_launches > 10 * 50
 
 
+def test_large_batch_is_invariant_to_batch_size():
+    """BASELINE config 5 (generation sweep, batch 64-8192 per GPU): a sample's trajectory depends on its global index
+    only, so the last 8 images of a 2048-image batch equal the same 8 global samples generated on their own."""
+    import ldm_b200
+    m, _ = make_model("bf16")
+    d = ldm_b200.Diffusion(1000, dev())
+    cls = torch.tensor([3])
+    B = 2048
+    big = d.sample(m, cls, (B, 3, 32, 32), dev(), cfg_scale=3, seed=5, first_step=999, num_steps=3, return_device=True)
+    head = d.sample(m, cls, (8, 3, 32, 32), dev(), cfg_scale=3, seed=5, first_step=999, num_steps=3, return_device=True)
+    tail = d.sample(m, cls, (8, 3, 32, 32), dev(), cfg_scale=3, seed=5, sample_offset=B - 8, first_step=999, num_steps=3,
+                    return_device=True)
+    assert torch.isfinite(big).all()
+    assert torch.equal(big[:8], head) and torch.equal(big[-8:], tail)
+
+
 def _reference_noise(g, T_, shape):
     torch.manual_seed(int(g["noise_seed"]))
     x_T = torch.randn(shape)
