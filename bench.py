@@ -323,6 +323,23 @@ def run_ours(args):
                 model, classes_dev, shape, dev, cfg_scale=cfg, seed=5, sample_offset=offset, return_device=True))
             variants["T1000_cfg0_images_per_sec"] = timed(lambda: diffusion.sample(
                 model, classes_dev, shape, dev, cfg_scale=0, seed=6, sample_offset=offset, return_device=True))
+            # BASELINE config 4: Autoencoder(3,4,3,64,[1,2],2) encode -> 1000-step CFG sampling of the [B,4,16,16] latent
+            # with the LatentDiffusionModel's sqrt-linear schedule -> decode (scale 0.18215, 0.00085/0.012)
+            torch.manual_seed(43)
+            lat_unet = ldm_b200.UNet(4, 4, 64, (1, 2, 4, 8), True, 10, dtype=args.dtype).to(dev)
+            lat_unet.requires_grad_(False)
+            ae = ldm_b200.Autoencoder(3, 4, 3, 64, [1, 2], 2, dtype=args.dtype).to(dev)
+            ldm = ldm_b200.LatentDiffusionModel(lat_unet, ae, 0.18215, T, 0.00085, 0.012).to(dev)
+            dl = ldm.make_diffusion(dev)
+            imgs = torch.rand(shape, device=dev) * 2 - 1
+
+            def ldm_round():
+                z0 = ldm.autoencoder_encode(imgs)                       # encode leg (its latent seeds nothing: timing only)
+                z = dl.sample(ldm, classes_dev, tuple(z0.shape), dev, cfg_scale=cfg, seed=8, sample_offset=offset,
+                              return_device=True)
+                return ldm.autoencoder_decode(z)
+
+            variants["ldm_encode_sample_decode_images_per_sec"] = timed(ldm_round)
             from ldm_b200 import ops as lops
             variants["e2e_uint8_output_images_per_sec"] = timed(lambda: lops.images_to_uint8(diffusion.sample(
                 model, classes_host, shape, dev, cfg_scale=cfg, x_T=x_T_host, seed=99, sample_offset=offset,
