@@ -387,7 +387,8 @@ def run_ours(args):
         except Exception:
             traffic = None
     roofline = {
-        "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv: 3x3, 1x1, conv-transpose)" if conv_name == "conv_tc" else "conv_simt",
+        "kernel": "3x3 implicit-GEMM convolutions on tcgen05 (conv_halo_kernel + conv_tc_kernel; 80 % of the UNet's FLOPs; the "
+                  "1x1 / conv-transpose launches are HBM bound and listed as conv_tc_1x1)" if conv_name == "conv_tc" else "conv_simt",
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["bf16_tflops_sustained"], "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",

@@ -99,12 +99,13 @@ int ldm_unet_set_tap(ldm_unet* h, const char* name, float* out_nchw, int64_t out
  * `t` is ONE device int64: the batch-constant timestep, used exactly as the sampler uses it.
  * Synchronises `stream` before returning; not capturable. */
 enum ldm_kernel_family {
-  LDM_FAM_CONV_TC = 0,          /* tcgen05 implicit-GEMM convolutions (3x3, 1x1, conv-transpose)  */
+  LDM_FAM_CONV_TC = 0,          /* tcgen05 implicit-GEMM 3x3 convolutions (tensor bound)          */
   LDM_FAM_CONV_FFMA = 1,        /* fp32 / forced-FFMA implicit-GEMM convolutions                  */
   LDM_FAM_GROUP_NORM = 2,       /* GroupNorm (+SiLU) (+residual)                                  */
   LDM_FAM_LINEAR_ATTENTION = 3,
   LDM_FAM_ATTENTION = 4,
   LDM_FAM_OTHER = 5,            /* time-embedding MLPs, initial/final conv, max-pool              */
+  LDM_FAM_CONV_TC_1X1 = 6,      /* tcgen05 1x1 convolutions and conv-transpose: K <= 768, HBM bound */
   LDM_FAM_COUNT = 8
 };
 typedef struct ldm_profile_family {

@@ -65,7 +65,14 @@ static inline int dtype_size(int dtype) { return dtype == LDM_DT_BF16 ? 2 : 4; }
 #ifdef __CUDACC__
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// The explicit early trigger let successors' CTAs take SM slots that the remaining waves of a multi-wave predecessor
+// still needed (measured slower); without it the successor is released when every predecessor CTA has exited, which
+// still hides its launch latency and prologue behind the predecessor's drain.
+#ifdef LDM_PDL_EARLY_TRIGGER
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+__device__ __forceinline__ void pdl_trigger() {}
+#endif
 
 template <typename T>
 struct VecTraits;
