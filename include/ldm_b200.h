@@ -251,11 +251,14 @@ int ldm_column_sum(const void* a, int lda, float* out, int rows, int cols, int d
 int ldm_group_norm_rowvec(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
                           const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
                           float eps, int silu, int dtype, void* workspace, void* stream);
-/* backward of y = [silu](GroupNorm(x + rowvec)): dx (overwritten), dgamma/dbeta (accumulated), drowvec [batch][ld] (overwritten) or NULL */
+/* backward of y = [silu](GroupNorm(x + rowvec)): dx (overwritten), dgamma/dbeta (accumulated), drowvec [batch][ld] (overwritten) or NULL.
+ * workspace (ldm_group_norm_backward_workspace_bytes, or NULL) enables the multi-CTA streaming kernels for bf16; forward_workspace
+ * (or NULL) is the workspace the matching ldm_group_norm_rowvec call used: its statistics are reused instead of recomputed. */
+int64_t ldm_group_norm_backward_workspace_bytes(int batch, int hw, int channels, int groups);
 int ldm_group_norm_backward(const void* x, int ldx, const void* dy, int lddy, const float* gamma, const float* beta,
                             const float* rowvec, int ld_rowvec, void* dx, int lddx, float* dgamma, float* dbeta,
                             float* drowvec, int ld_drowvec, int batch, int hw, int channels, int groups, float eps, int silu,
-                            int dtype, void* stream);
+                            int dtype, const void* forward_workspace, void* workspace, void* stream);
 int ldm_max_pool2x2_backward(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int batch, int height,
                              int width, int channels, int dtype, void* stream);
 /* ConvTranspose2d(k2,s2) backward gather: out[n,h,w,q*C+c] = dy[n,2h+q/2,2w+q%2,c]; then dx / dW are a 1x1 dgrad / wgrad */

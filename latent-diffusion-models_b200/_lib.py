@@ -89,8 +89,9 @@ SIGNATURES = {
     "ldm_column_sum": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_group_norm_rowvec": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp]),
+    "ldm_group_norm_backward_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ldm_group_norm_backward": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int,
-                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, vp]),
+                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp, vp]),
     "ldm_max_pool2x2_backward": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_int, vp]),
     "ldm_pixel_unshuffle2x2": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),

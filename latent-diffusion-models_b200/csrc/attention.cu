@@ -459,7 +459,10 @@ namespace {
 //   K: the constant is uniform along the softmax (token) axis and cancels; V: it passes through the normalised
 //   ctx unchanged (sum_n softmax = 1); Q: added before the softmax over d.
 template <bool FOLD>
-__global__ void __launch_bounds__(128, 3) linattn_qkv_fused_kernel(const bf16* __restrict__ xn, int ldx,
+#ifndef LINATTN_FUSED_MIN_CTAS
+#define LINATTN_FUSED_MIN_CTAS 3   // 4 (128 registers, spills) measured 4 % slower: the kernel is issue-bound, not tail-bound
+#endif
+__global__ void __launch_bounds__(128, LINATTN_FUSED_MIN_CTAS) linattn_qkv_fused_kernel(const bf16* __restrict__ xn, int ldx,
                                                                const bf16* __restrict__ wqkv,
                                                                const float* __restrict__ uv,
                                                                const float2* __restrict__ gn_part, int gn_splits,

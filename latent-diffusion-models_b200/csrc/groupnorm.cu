@@ -330,6 +330,225 @@ gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int l
   for (; p < p1; p += ppi) emit(load_raw(xb + (int64_t)p * ldx), rb ? load_raw(rb + (int64_t)p * ldres) : z4, p);
 }
 
+// ------------------------------------------------------------------ (B) streaming backward, bf16
+// y = [silu](gamma * xh + beta), xh = (x + rowvec - mean) * rstd.  Three multi-CTA kernels instead of one CTA per sample:
+//   gn_stats_kernel          part  [n][split][g] = pivoted sums of x            (or the forward's, if the caller kept them)
+//   gn_bwd_sums_kernel       part2 [n][split][g] = {sum dyh, sum dyh*xh};  dgamma, dbeta accumulated (atomics)
+//   gn_bwd_apply_kernel      dx = rstd * (dyh - mean(dyh) - xh * mean(dyh*xh));  drowvec[n][c] = sum_p dx  (atomics)
+__device__ __forceinline__ float silu_grad(float z) {
+  const float sg = 1.0f / (1.0f + __expf(-z));
+  return sg * (1.0f + z * (1.0f - sg));
+}
+
+// mean / rstd of every group of sample n from the pivoted partial sums (same arithmetic as gn_apply_kernel)
+template <bool RV>
+__device__ __forceinline__ void gn_group_stats(const bf16* xs, const float* rowvec, int ld_rowvec, int n, const float2* part,
+                                               int splits, int HW, int cpg, int G, float eps, float* s_mean, float* s_rstd) {
+  constexpr int V = 8;
+  if (threadIdx.x < G) {
+    const int gg = threadIdx.x;
+    float a = 0.f, b = 0.f;
+    for (int sp = 0; sp < splits; ++sp) {
+      const float2 v = part[((int64_t)n * splits + sp) * G + gg];
+      a += v.x; b += v.y;
+    }
+    const int c_first = gg * cpg * V;
+    const float K = __bfloat162float(xs[c_first]) + (RV ? rowvec[(int64_t)n * ld_rowvec + c_first] : 0.f);
+    const float inv_n = 1.0f / ((float)HW * (float)(cpg * V));
+    const float m1 = a * inv_n;
+    const float var = fmaxf(b * inv_n - m1 * m1, 0.f);
+    s_mean[gg] = K + m1;
+    s_rstd[gg] = 1.0f / sqrtf(var + eps);
+  }
+}
+
+// grid (splits, batch)
+template <bool RV>
+__global__ void __launch_bounds__(GS_THREADS)
+gn_bwd_sums_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy, int lddy, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const float* __restrict__ rowvec, int ld_rowvec,
+                   const float2* __restrict__ part, float2* __restrict__ part2, float* __restrict__ chan_part,
+                   float* __restrict__ drowvec, int ld_drowvec, int HW, int C, int G, float eps, int silu, int pix_per_split) {
+  constexpr int V = 8;
+  __shared__ float red_a[GS_THREADS], red_b[GS_THREADS];
+  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  const int n = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
+  const int cpp = C / V, cpg = cpp / G;
+  const bf16* xs = x + (int64_t)n * HW * ldx;
+  gn_group_stats<RV>(xs, rowvec, ld_rowvec, n, part, splits, HW, cpg, G, eps, s_mean, s_rstd);
+  if (drowvec && split == 0)   // the apply kernel accumulates into it
+    for (int c = threadIdx.x; c < C; c += blockDim.x) drowvec[(int64_t)n * ld_drowvec + c] = 0.f;
+  __syncthreads();
+  const int ci = threadIdx.x % cpp, pl = threadIdx.x / cpp, ppi = blockDim.x / cpp;
+  const int g = ci / cpg;
+  const float mean = s_mean[g], rstd = s_rstd[g];
+  float ga[V], be[V], sh[V];   // xh = x * rstd + sh
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    ga[i] = gamma[ci * V + i];
+    be[i] = beta[ci * V + i];
+    sh[i] = ((RV ? rowvec[(int64_t)n * ld_rowvec + ci * V + i] : 0.f) - mean) * rstd;
+  }
+  float s1 = 0.f, s2 = 0.f, dg[V], db[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+  const int p0 = split * pix_per_split, p1 = min(p0 + pix_per_split, HW);
+  const bf16* xb = xs + ci * V;
+  const bf16* dyb = dy + (int64_t)n * HW * lddy + ci * V;
+  auto acc = [&](const uint4& rx, const uint4& rd) {
+    float w[V], d[V];
+    unpack(rx, w);
+    unpack(rd, d);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float xh = fmaf(w[i], rstd, sh[i]);
+      float dz = d[i];
+      if (silu) dz *= silu_grad(fmaf(xh, ga[i], be[i]));
+      dg[i] = fmaf(dz, xh, dg[i]);
+      db[i] += dz;
+      const float dyh = dz * ga[i];
+      s1 += dyh;
+      s2 = fmaf(dyh, xh, s2);
+    }
+  };
+  int p = p0 + pl;
+  for (; p + ppi < p1; p += 2 * ppi) {
+    const uint4 x0 = load_raw(xb + (int64_t)p * ldx), x1 = load_raw(xb + (int64_t)(p + ppi) * ldx);
+    const uint4 d0 = load_raw(dyb + (int64_t)p * lddy), d1 = load_raw(dyb + (int64_t)(p + ppi) * lddy);
+    acc(x0, d0); acc(x1, d1);
+  }
+  for (; p < p1; p += ppi) acc(load_raw(xb + (int64_t)p * ldx), load_raw(dyb + (int64_t)p * lddy));
+  // group sums of this CTA's slab
+  red_a[threadIdx.x] = s1;
+  red_b[threadIdx.x] = s2;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int members = ppi * cpg;
+  for (int gg = warp; gg < G; gg += nwarps) {
+    float a = 0.f, b = 0.f;
+    for (int idx = lane; idx < members; idx += 32) {
+      const int t = (idx / cpg) * cpp + gg * cpg + idx % cpg;
+      a += red_a[t]; b += red_b[t];
+    }
+    a = warp_sum(a); b = warp_sum(b);
+    if (lane == 0) part2[((int64_t)n * splits + split) * G + gg] = make_float2(a, b);
+  }
+  // per-channel parameter gradients: sum over the pixel lanes of this CTA and write the CTA's row of partials
+  // chan_part[(n*splits + split)][2C] = {dgamma | dbeta}; gn_bwd_param_kernel adds the rows up (thousands of CTAs doing
+  // atomics on the same 2C floats serialise in L2: measured 3x the kernel's streaming time)
+  float* row = chan_part + ((int64_t)n * splits + split) * 2 * C;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    __syncthreads();
+    red_a[threadIdx.x] = dg[i];
+    red_b[threadIdx.x] = db[i];
+    __syncthreads();
+    if (pl == 0) {
+      float a = 0.f, b = 0.f;
+      for (int k = 0; k < ppi; ++k) { a += red_a[k * cpp + ci]; b += red_b[k * cpp + ci]; }
+      row[ci * V + i] = a;
+      row[C + ci * V + i] = b;
+    }
+  }
+}
+
+// dgamma[c] += sum_rows chan_part[r][c], dbeta[c] += sum_rows chan_part[r][C + c].  grid (ceil(2C / 32)), 256 threads =
+// 8 row lanes x 32 columns; fixed summation order (bit-reproducible)
+__global__ void __launch_bounds__(256)
+gn_bwd_param_kernel(const float* __restrict__ chan_part, int rows, int C, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  float a = 0.f;
+  if (col < 2 * C)
+    for (int r = rl; r < rows; r += 8) a += chan_part[(int64_t)r * 2 * C + col];
+  red[rl][threadIdx.x & 31] = a;
+  __syncthreads();
+  if (rl == 0 && col < 2 * C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
+    if (col < C) dgamma[col] += t; else dbeta[col - C] += t;
+  }
+}
+
+// grid (ceil(HW / pix_per_block), batch)
+template <bool RV>
+__global__ void __launch_bounds__(GS_THREADS)
+gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy, int lddy, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ rowvec, int ld_rowvec,
+                    const float2* __restrict__ part, const float2* __restrict__ part2, int splits, bf16* __restrict__ dx,
+                    int lddx, float* __restrict__ drowvec, int ld_drowvec, int HW, int C, int G, float eps, int silu,
+                    int pix_per_block) {
+  constexpr int V = 8;
+  __shared__ float red[GS_THREADS];
+  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS], s_m1[GN_MAX_GROUPS], s_m2[GN_MAX_GROUPS];
+  const int n = blockIdx.y;
+  const int cpp = C / V, cpg = cpp / G;
+  const bf16* xs = x + (int64_t)n * HW * ldx;
+  gn_group_stats<RV>(xs, rowvec, ld_rowvec, n, part, splits, HW, cpg, G, eps, s_mean, s_rstd);
+  if (threadIdx.x < G) {
+    float a = 0.f, b = 0.f;
+    for (int sp = 0; sp < splits; ++sp) {
+      const float2 v = part2[((int64_t)n * splits + sp) * G + threadIdx.x];
+      a += v.x; b += v.y;
+    }
+    const float inv_n = 1.0f / ((float)HW * (float)(cpg * V));
+    s_m1[threadIdx.x] = a * inv_n;
+    s_m2[threadIdx.x] = b * inv_n;
+  }
+  __syncthreads();
+  const int ci = threadIdx.x % cpp, pl = threadIdx.x / cpp, ppi = blockDim.x / cpp;
+  const int g = ci / cpg;
+  const float mean = s_mean[g], rstd = s_rstd[g], m1 = s_m1[g], m2 = s_m2[g];
+  float ga[V], be[V], sh[V], dr[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    ga[i] = gamma[ci * V + i];
+    be[i] = beta[ci * V + i];
+    sh[i] = ((RV ? rowvec[(int64_t)n * ld_rowvec + ci * V + i] : 0.f) - mean) * rstd;
+    dr[i] = 0.f;
+  }
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, HW);
+  const bf16* xb = xs + ci * V;
+  const bf16* dyb = dy + (int64_t)n * HW * lddy + ci * V;
+  bf16* dxb = dx + (int64_t)n * HW * lddx + ci * V;
+  auto emit = [&](const uint4& rx, const uint4& rd, int p) {
+    float w[V], d[V];
+    unpack(rx, w);
+    unpack(rd, d);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float xh = fmaf(w[i], rstd, sh[i]);
+      float dz = d[i];
+      if (silu) dz *= silu_grad(fmaf(xh, ga[i], be[i]));
+      const float o = rstd * (dz * ga[i] - m1 - xh * m2);
+      dr[i] += o;
+      w[i] = o;
+    }
+    store_chunk(dxb + (int64_t)p * lddx, w);
+  };
+  int p = p0 + pl;
+  for (; p + ppi < p1; p += 2 * ppi) {
+    const uint4 x0 = load_raw(xb + (int64_t)p * ldx), x1 = load_raw(xb + (int64_t)(p + ppi) * ldx);
+    const uint4 d0 = load_raw(dyb + (int64_t)p * lddy), d1 = load_raw(dyb + (int64_t)(p + ppi) * lddy);
+    emit(x0, d0, p); emit(x1, d1, p + ppi);
+  }
+  for (; p < p1; p += ppi) emit(load_raw(xb + (int64_t)p * ldx), load_raw(dyb + (int64_t)p * lddy), p);
+  if (drowvec) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      __syncthreads();
+      red[threadIdx.x] = dr[i];
+      __syncthreads();
+      if (pl == 0) {
+        float a = 0.f;
+        for (int k = 0; k < ppi; ++k) a += red[k * cpp + ci];
+        atomicAdd(drowvec + (int64_t)n * ld_drowvec + ci * V + i, a);
+      }
+    }
+  }
+}
+
 int gcd_i2(int a, int b) { return b ? gcd_i2(b, a % b) : a; }
 
 // geometry shared by the stats producer and its consumers (gn_apply, the fused attention kernel)
@@ -428,6 +647,51 @@ int k_group_norm_stats(const void* x, int ldx, int batch, int hw, int channels, 
   LDM_CUDA(ldm_launch_pdl(gn_stats_kernel<false>, dim3(splits, batch), dim3(threads), 0, st, (const bf16*)x, ldx, (const float*)nullptr,
                           0, (float2*)workspace, hw, channels, groups, pps, 0));
   LDM_LAUNCHED("gn_stats");
+  return 0;
+}
+
+// Streaming GroupNorm backward (bf16).  workspace: k_group_norm_backward_ws_bytes.  fwd_part: the partial sums the forward's
+// workspace holds (k_group_norm_rv with the same arguments) or nullptr to recompute them.
+int64_t k_group_norm_backward_ws_bytes(int batch, int hw, int channels, int groups) {
+  int threads, ppi, splits, pps;
+  gn_stream_geometry(hw, channels > 0 ? channels : 8, threads, ppi, splits, pps);
+  return 2 * k_group_norm_ws_bytes(batch, groups) + (int64_t)batch * splits * 2 * channels * sizeof(float) + 256;
+}
+bool k_group_norm_backward_streams(int batch, int hw, int channels, int groups, int dtype) {
+  return k_group_norm_streams(hw, channels, dtype) && channels % groups == 0 && (channels / groups) % 8 == 0 && batch <= 65535 &&
+         getenv("LDM_GN_BWD_ONE_CTA") == nullptr;
+}
+int k_group_norm_backward_stream(const void* x, int ldx, const void* dy, int lddy, const float* gamma, const float* beta,
+                                 const float* rowvec, int ld_rowvec, void* dx, int lddx, float* dgamma, float* dbeta,
+                                 float* drowvec, int ld_drowvec, int batch, int hw, int channels, int groups, float eps, int silu,
+                                 const void* fwd_part, void* workspace, cudaStream_t st) {
+  LDM_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && workspace, "group_norm_backward: unaligned stride / no workspace");
+  if (batch == 0 || hw == 0) return 0;
+  int threads, ppi, splits, pps;
+  gn_stream_geometry(hw, channels, threads, ppi, splits, pps);
+  float2* part = (float2*)workspace;
+  float2* part2 = (float2*)((char*)workspace + k_group_norm_ws_bytes(batch, groups));
+  float* chan_part = (float*)((char*)workspace + 2 * k_group_norm_ws_bytes(batch, groups));
+  const bf16* xp = (const bf16*)x;
+  const bf16* dyp = (const bf16*)dy;
+  if (fwd_part) {
+    part = (float2*)fwd_part;
+  } else {
+    if (rowvec) gn_stats_kernel<true><<<dim3(splits, batch), threads, 0, st>>>(xp, ldx, rowvec, ld_rowvec, part, hw, channels, groups, pps, 0);
+    else gn_stats_kernel<false><<<dim3(splits, batch), threads, 0, st>>>(xp, ldx, rowvec, ld_rowvec, part, hw, channels, groups, pps, 0);
+    LDM_LAUNCHED("gn_stats");
+  }
+  if (rowvec) gn_bwd_sums_kernel<true><<<dim3(splits, batch), threads, 0, st>>>(xp, ldx, dyp, lddy, gamma, beta, rowvec, ld_rowvec, part, part2, chan_part, drowvec, ld_drowvec, hw, channels, groups, eps, silu, pps);
+  else gn_bwd_sums_kernel<false><<<dim3(splits, batch), threads, 0, st>>>(xp, ldx, dyp, lddy, gamma, beta, rowvec, ld_rowvec, part, part2, chan_part, drowvec, ld_drowvec, hw, channels, groups, eps, silu, pps);
+  LDM_LAUNCHED("gn_bwd_sums");
+  gn_bwd_param_kernel<<<(2 * channels + 31) / 32, 256, 0, st>>>(chan_part, batch * splits, channels, dgamma, dbeta);
+  LDM_LAUNCHED("gn_bwd_param");
+  int ppb = ppi * 8;
+  if (ppb > hw) ppb = hw;
+  const dim3 grid((hw + ppb - 1) / ppb, batch);
+  if (rowvec) gn_bwd_apply_kernel<true><<<grid, threads, 0, st>>>(xp, ldx, dyp, lddy, gamma, beta, rowvec, ld_rowvec, part, part2, splits, (bf16*)dx, lddx, drowvec, ld_drowvec, hw, channels, groups, eps, silu, ppb);
+  else gn_bwd_apply_kernel<false><<<grid, threads, 0, st>>>(xp, ldx, dyp, lddy, gamma, beta, rowvec, ld_rowvec, part, part2, splits, (bf16*)dx, lddx, drowvec, ld_drowvec, hw, channels, groups, eps, silu, ppb);
+  LDM_LAUNCHED("gn_bwd_apply");
   return 0;
 }
 

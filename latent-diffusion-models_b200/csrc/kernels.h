@@ -177,3 +177,11 @@ int k_pick_odd(const void* x, int ldx, void* y, int ldy, int batch, int H, int W
 int k_attention_single_head(const void* qkv, void* out, int batch, int n_tokens, int channels, int dtype, cudaStream_t st);
 int k_gaussian(const void* moments, int ld, const float* eps, float* mu, float* log_var, float* sigma, float* z, int batch,
                int zc, int hw, int dtype, cudaStream_t st);
+
+// ---- groupnorm.cu: streaming (multi-CTA) GroupNorm backward, bf16
+bool k_group_norm_backward_streams(int batch, int hw, int channels, int groups, int dtype);
+int64_t k_group_norm_backward_ws_bytes(int batch, int hw, int channels, int groups);
+int k_group_norm_backward_stream(const void* x, int ldx, const void* dy, int lddy, const float* gamma, const float* beta,
+                                 const float* rowvec, int ld_rowvec, void* dx, int lddx, float* dgamma, float* dbeta,
+                                 float* drowvec, int ld_drowvec, int batch, int hw, int channels, int groups, float eps, int silu,
+                                 const void* fwd_part, void* workspace, cudaStream_t st);

@@ -55,11 +55,18 @@ int ldm_group_norm_rowvec(const void* x, int ldx, void* y, int ldy, const void* 
   return k_group_norm_rv(x, ldx, y, ldy, res, ldres, gamma, beta, rowvec, ld_rowvec, batch, hw, channels, groups, eps, silu,
                          dtype, workspace, (cudaStream_t)stream);
 }
+int64_t ldm_group_norm_backward_workspace_bytes(int batch, int hw, int channels, int groups) {
+  return k_group_norm_backward_ws_bytes(batch, hw, channels, groups);
+}
 int ldm_group_norm_backward(const void* x, int ldx, const void* dy, int lddy, const float* gamma, const float* beta,
                             const float* rowvec, int ld_rowvec, void* dx, int lddx, float* dgamma, float* dbeta,
                             float* drowvec, int ld_drowvec, int batch, int hw, int channels, int groups, float eps, int silu,
-                            int dtype, void* stream) {
+                            int dtype, const void* forward_workspace, void* workspace, void* stream) {
   LDM_REQUIRE(x && dy && gamma && beta && dx && dgamma && dbeta, "ldm_group_norm_backward: null argument");
+  if (workspace && k_group_norm_backward_streams(batch, hw, channels, groups, dtype))
+    return k_group_norm_backward_stream(x, ldx, dy, lddy, gamma, beta, rowvec, ld_rowvec, dx, lddx, dgamma, dbeta, drowvec,
+                                        ld_drowvec, batch, hw, channels, groups, eps, silu, forward_workspace, workspace,
+                                        (cudaStream_t)stream);
   return k_group_norm_backward(x, ldx, dy, lddy, gamma, beta, rowvec, ld_rowvec, dx, lddx, dgamma, dbeta, drowvec, ld_drowvec,
                                batch, hw, channels, groups, eps, silu, dtype, (cudaStream_t)stream);
 }

@@ -83,24 +83,27 @@ class _GroupNorm(Function):
         _lib.check(lib.ldm_group_norm_rowvec(x.data_ptr(), x.stride(2), y.data_ptr(), y.stride(2), None, 0, gamma.data_ptr(),
                                              beta.data_ptr(), _lib.ptr(rv), rv.stride(0) if rv is not None else 0, B, H * W,
                                              Cc, groups, _EPS, int(silu), ops._dt(x), ws.data_ptr(), _st()))
-        ctx.save_for_backward(x, gamma, beta, rowvec if rowvec is not None else torch.empty(0))
+        ctx.save_for_backward(x, gamma, beta, rowvec if rowvec is not None else torch.empty(0), ws)   # ws: the statistics
         ctx.groups, ctx.silu, ctx.has_rv = groups, silu, rowvec is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, gamma, beta, rowvec = ctx.saved_tensors
+        x, gamma, beta, rowvec, fwd_ws = ctx.saved_tensors
         dy = _c(dy)
         B, H, W, Cc = x.shape
         dx = torch.empty_like(x)
-        dg = torch.zeros_like(gamma)
-        db = torch.zeros_like(beta)
+        dgb = torch.zeros(2 * Cc, dtype=torch.float32, device=x.device)   # one fill for dgamma and dbeta
+        dg, db = dgb[:Cc], dgb[Cc:]
         rv = rowvec if ctx.has_rv else None
         drv = torch.empty(B, Cc, dtype=torch.float32, device=x.device) if ctx.has_rv else None
-        _lib.check(_lb().ldm_group_norm_backward(x.data_ptr(), x.stride(2), dy.data_ptr(), dy.stride(2), gamma.data_ptr(),
-                                                 beta.data_ptr(), _lib.ptr(rv), rv.stride(0) if rv is not None else 0,
-                                                 dx.data_ptr(), dx.stride(2), dg.data_ptr(), db.data_ptr(), _lib.ptr(drv),
-                                                 Cc, B, H * W, Cc, ctx.groups, _EPS, int(ctx.silu), ops._dt(x), _st()))
+        lib = _lb()
+        ws = torch.empty(lib.ldm_group_norm_backward_workspace_bytes(B, H * W, Cc, ctx.groups), dtype=torch.uint8, device=x.device)
+        _lib.check(lib.ldm_group_norm_backward(x.data_ptr(), x.stride(2), dy.data_ptr(), dy.stride(2), gamma.data_ptr(),
+                                               beta.data_ptr(), _lib.ptr(rv), rv.stride(0) if rv is not None else 0,
+                                               dx.data_ptr(), dx.stride(2), dg.data_ptr(), db.data_ptr(), _lib.ptr(drv),
+                                               Cc, B, H * W, Cc, ctx.groups, _EPS, int(ctx.silu), ops._dt(x),
+                                               fwd_ws.data_ptr(), ws.data_ptr(), _st()))
         return dx, dg, db, None, None, drv
 
 
