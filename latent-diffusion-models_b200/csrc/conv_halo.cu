@@ -456,8 +456,16 @@ bool k_conv_halo_applicable(const ConvArgs& a) {
   if (a.dtype != LDM_DT_BF16 || a.ksize != 3 || a.up2) return false;
   if (a.cout != 64 && a.cout != 128) return false;
   if (a.cin % BLOCK_K != 0 || (a.x2 && a.cin2 % BLOCK_K != 0)) return false;
-  if (a.width != 32 || a.height < 4) return false;   // full-resolution layers (W/P = 94 % useful rows)
-  return true;
+  if (a.height < 4) return false;
+  if (a.width == 32) return true;                    // full-resolution layers (W/P = 94 % useful rows)
+  // 16x16: 75 % of the MMA rows are useful (3 tiles per 288-position plane); LDM_HALO_W16: 1 = all, 2 = resident filters only
+  static const int w16 = getenv("LDM_HALO_W16") ? atoi(getenv("LDM_HALO_W16")) : 0;
+  if (a.width == 16 && w16 == 1) return true;
+  if (a.width == 16 && w16 == 2) {
+    const int n_kb = 9 * (a.cin / BLOCK_K) + (a.x2 ? a.cin2 / BLOCK_K : 0);
+    return (int64_t)n_kb * a.cout * BLOCK_K * 2 <= 120 * 1024;
+  }
+  return false;
 }
 
 int k_conv_halo(const ConvArgs& a, cudaStream_t st) {

@@ -158,10 +158,10 @@ bool k_conv_wgrad_tc_applicable(int cin, int cout, int H, int W, int ksize, int 
 bool k_conv_wgrad_tc_flat_applicable(int cin, int cout, int batch, int H, int W, int ksize, int dtype);
 int k_nhwc_to_flat_taps_bf16(const void* x, int ld, void* y, float* colsum, int batch, int C, int H, int W, int taps,
                              cudaStream_t st);
-int k_conv_wgrad_tc_flat(const void* xF, int cin, const void* dyF, int cout, float* dw, int batch, int H, int W, int ksize,
-                         cudaStream_t st);
+int k_conv_wgrad_tc_flat(const void* xF, int cin, const void* dyF, int cout, float* dw, float* nat, int batch, int H, int W,
+                         int ksize, cudaStream_t st);
 int k_conv_wgrad_tc(const void* xT, int cin, const void* dyT, const void* dyT_l, const void* dyT_r, int cout, float* dw,
-                    int batch, int H, int W, int ksize, cudaStream_t st);
+                    float* nat, int batch, int H, int W, int ksize, cudaStream_t st);
 
 // ---- trainer_ops.cu: Adam step over flat fp32 buffers, uint8 image output, MSE
 int k_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,

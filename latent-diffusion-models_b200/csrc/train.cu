@@ -11,34 +11,42 @@ int ldm_conv2d_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, 
   LDM_REQUIRE(x && dy && dw_oihw, "ldm_conv2d_wgrad: null argument");
   return k_conv_wgrad(x, ldx, cin, dy, lddy, cout, dw_oihw, dbias, batch, height, width, ksize, dtype, (cudaStream_t)stream);
 }
+static int64_t wgrad_nat_bytes(int cin, int cout, int ksize) {   // fp32 [tap][cout][cin] accumulator of 3x3 filters
+  return ksize == 1 ? 0 : ((int64_t)ksize * ksize * cout * cin * 4 + 255) / 256 * 256;
+}
 int64_t ldm_conv2d_wgrad_scratch_bytes(int cin, int cout, int batch, int height, int width, int ksize, int dtype) {
   if (k_conv_wgrad_tc_flat_applicable(cin, cout, batch, height, width, ksize, dtype))
-    return ((int64_t)batch * height * width * (cin + (int64_t)ksize * ksize * cout) * 2 + 255) / 256 * 256 + 256;
+    return ((int64_t)batch * height * width * (cin + (int64_t)ksize * ksize * cout) * 2 + 255) / 256 * 256 + 512 +
+           wgrad_nat_bytes(cin, cout, ksize);
   if (!k_conv_wgrad_tc_applicable(cin, cout, height, width, ksize, dtype)) return 0;
-  return (int64_t)batch * height * width * (cin + (ksize == 3 ? 3 : 1) * (int64_t)cout) * 2 + 4 * 256;
+  return (int64_t)batch * height * width * (cin + (ksize == 3 ? 3 : 1) * (int64_t)cout) * 2 + 4 * 256 + wgrad_nat_bytes(cin, cout, ksize);
 }
 // Tensor-core weight gradient: scratch (ldm_conv2d_wgrad_scratch_bytes, 256-byte aligned) receives the channel-major
-// copies of x and dy.  Falls back to nothing: returns an error for shapes the tcgen05 kernel does not take.
+// copies of x and dy and, for 3x3 filters, the fp32 accumulator in GEMM-natural layout.
 int ldm_conv2d_wgrad_tc(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw_oihw, float* dbias,
                         int batch, int height, int width, int ksize, void* scratch, void* stream) {
   LDM_REQUIRE(x && dy && dw_oihw && scratch, "ldm_conv2d_wgrad_tc: null argument");
+  LDM_REQUIRE(((uintptr_t)scratch & 255) == 0, "ldm_conv2d_wgrad_tc: scratch must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int hw = height * width;
   auto up = [](int64_t v) { return (v + 255) / 256 * 256; };
+  float* nat = (float*)scratch;                      // first: keeps its alignment whatever follows
+  char* rest = (char*)scratch + wgrad_nat_bytes(cin, cout, ksize);
+  if (ksize == 1) nat = nullptr;
   if (k_conv_wgrad_tc_flat_applicable(cin, cout, batch, height, width, ksize, LDM_DT_BF16)) {
-    char* xF = (char*)scratch;
+    char* xF = rest;
     char* dyF = xF + up((int64_t)batch * hw * cin * 2);
     RC(k_nhwc_to_flat_taps_bf16(x, ldx, xF, nullptr, batch, cin, height, width, 1, st));
     RC(k_nhwc_to_flat_taps_bf16(dy, lddy, dyF, dbias, batch, cout, height, width, ksize * ksize, st));
-    return k_conv_wgrad_tc_flat(xF, cin, dyF, cout, dw_oihw, batch, height, width, ksize, st);
+    return k_conv_wgrad_tc_flat(xF, cin, dyF, cout, dw_oihw, nat, batch, height, width, ksize, st);
   }
-  char* xT = (char*)scratch;
+  char* xT = rest;
   char* dyT = xT + up((int64_t)batch * hw * cin * 2);
   char* dyL = ksize == 3 ? dyT + up((int64_t)batch * hw * cout * 2) : nullptr;
   char* dyR = ksize == 3 ? dyL + up((int64_t)batch * hw * cout * 2) : nullptr;
   RC(k_nhwc_to_chw_bf16(x, ldx, xT, nullptr, nullptr, nullptr, batch, cin, hw, width, st));
   RC(k_nhwc_to_chw_bf16(dy, lddy, dyT, dyL, dyR, dbias, batch, cout, hw, width, st));
-  return k_conv_wgrad_tc(xT, cin, dyT, dyL, dyR, cout, dw_oihw, batch, height, width, ksize, st);
+  return k_conv_wgrad_tc(xT, cin, dyT, dyL, dyR, cout, dw_oihw, nat, batch, height, width, ksize, st);
 }
 int ldm_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin, int ksize, void* w_packed, int dtype, void* stream) {
   LDM_REQUIRE(w_oihw && w_packed, "ldm_pack_conv_weight_dgrad: null argument");

@@ -28,7 +28,7 @@ struct WgParams {
   int kb_per_image;           // H*W / 64
   int W;
   int flat;                   // 1: operands are [C][B*HW] (x) and [tap][C][B*HW] (dy, shifted per tap) -- images below 8x8
-  float* dw;
+  float* dw;                  // accumulation target: OIHW when taps == 1, else the GEMM-natural [tap][cout][cin] scratch
 };
 
 template <int BN>
@@ -134,7 +134,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     __syncwarp();
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    float* drow = p.dw + ((int64_t)co * p.cin + ci0) * p.taps + tap;
+    // [tap][cout][cin] (== OIHW for a 1x1 filter): a thread's 32 columns are 128 contiguous bytes, added with 16-byte
+    // vector reductions -- a quarter of the L2 atomic operations of scalar adds, which bound the large filters
+    float* drow = p.dw + ((int64_t)tap * p.cout + co) * p.cin + ci0;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -142,7 +144,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
       tmem_ld_wait();
       if (valid) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(drow + (int64_t)(c0 + j) * p.taps, __uint_as_float(r[j]));
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + j), "f"(__uint_as_float(r[j])),
+                       "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                       : "memory");
       }
     }
   }
@@ -249,6 +254,18 @@ nhwc_to_flat_taps_kernel(const bf16* __restrict__ x, int ld, bf16* __restrict__ 
   }
 }
 
+// dw_oihw[co][ci][tap] += nat[tap][co][ci]: grid (cin / 32, cout), 288 threads; both sides coalesced through shared memory
+__global__ void __launch_bounds__(288)
+wgrad_finish_kernel(const float* __restrict__ nat, float* __restrict__ dw, int cout, int cin) {
+  __shared__ float t[9][33];
+  const int co = blockIdx.y, ci0 = blockIdx.x * 32;
+  const int tap = threadIdx.x >> 5, l = threadIdx.x & 31;
+  t[tap][l] = nat[((int64_t)tap * cout + co) * cin + ci0 + l];
+  __syncthreads();
+  const int o = threadIdx.x;                // 0..287 = (ci local, tap)
+  dw[((int64_t)co * cin + ci0) * 9 + o] += t[o % 9][o / 9];
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 g_encode_w = nullptr;
 int wg_init() {
   if (g_encode_w) return 0;
@@ -314,30 +331,35 @@ bool k_conv_wgrad_tc_applicable(int cin, int cout, int H, int W, int ksize, int 
 }
 
 static int wg_launch(const void* xT, int cin, const void* dyT, const void* dyT_l, const void* dyT_r, int cout, float* dw,
-                     int batch, int H, int W, int ksize, int flat, cudaStream_t st);
+                     float* nat, int batch, int H, int W, int ksize, int flat, cudaStream_t st);
 
 // xT [B][cin][HW]; dyT, dyT_l, dyT_r [B][cout][HW] (bf16, channel-major; _l / _r: shifted one pixel left / right with zero
 // fill, only read by 3x3 filters); dw OIHW fp32, ACCUMULATED
 int k_conv_wgrad_tc(const void* xT, int cin, const void* dyT, const void* dyT_l, const void* dyT_r, int cout, float* dw,
-                    int batch, int H, int W, int ksize, cudaStream_t st) {
+                    float* nat, int batch, int H, int W, int ksize, cudaStream_t st) {
   if (int rc = wg_init()) return rc;
   LDM_REQUIRE(k_conv_wgrad_tc_applicable(cin, cout, H, W, ksize, LDM_DT_BF16), "conv_wgrad_tc: unsupported shape");
   if (batch == 0) return 0;
-  return wg_launch(xT, cin, dyT, dyT_l, dyT_r, cout, dw, batch, H, W, ksize, 0, st);
+  return wg_launch(xT, cin, dyT, dyT_l, dyT_r, cout, dw, nat, batch, H, W, ksize, 0, st);
 }
 
 // xF [cin][B*HW]; dyF [taps][cout][B*HW], copy t shifted by filter offset t (k_nhwc_to_flat_taps_bf16); dw ACCUMULATED
-int k_conv_wgrad_tc_flat(const void* xF, int cin, const void* dyF, int cout, float* dw, int batch, int H, int W, int ksize,
-                         cudaStream_t st) {
+int k_conv_wgrad_tc_flat(const void* xF, int cin, const void* dyF, int cout, float* dw, float* nat, int batch, int H, int W,
+                         int ksize, cudaStream_t st) {
   if (int rc = wg_init()) return rc;
   LDM_REQUIRE(k_conv_wgrad_tc_flat_applicable(cin, cout, batch, H, W, ksize, LDM_DT_BF16), "conv_wgrad_tc_flat: unsupported shape");
-  return wg_launch(xF, cin, dyF, nullptr, nullptr, cout, dw, batch, H, W, ksize, 1, st);
+  return wg_launch(xF, cin, dyF, nullptr, nullptr, cout, dw, nat, batch, H, W, ksize, 1, st);
 }
 
 static int wg_launch(const void* xT, int cin, const void* dyT, const void* dyT_l, const void* dyT_r, int cout, float* dw,
-                     int batch, int H, int W, int ksize, int flat, cudaStream_t st) {
+                     float* nat, int batch, int H, int W, int ksize, int flat, cudaStream_t st) {
   WgParams p;
-  p.cout = cout; p.cin = cin; p.taps = ksize * ksize; p.dw = dw; p.W = W; p.flat = flat;
+  p.cout = cout; p.cin = cin; p.taps = ksize * ksize; p.W = W; p.flat = flat;
+  // 3x3: accumulate in the GEMM-natural layout (zeroed here), transpose-add into OIHW afterwards
+  LDM_REQUIRE(ksize == 1 || nat != nullptr, "conv_wgrad_tc: 3x3 filters need the natural-layout scratch");
+  LDM_REQUIRE(((uintptr_t)dw & 15) == 0 && ((uintptr_t)nat & 15) == 0, "conv_wgrad_tc: gradient buffers must be 16-byte aligned");
+  p.dw = ksize == 1 ? dw : nat;
+  if (ksize != 1) LDM_CUDA(cudaMemsetAsync(nat, 0, (size_t)9 * cout * cin * sizeof(float), st));
   const int hw = H * W;
   const int64_t M = (int64_t)batch * hw;
   p.kb_per_image = flat ? 1 : hw / 64;
@@ -347,7 +369,13 @@ static int wg_launch(const void* xT, int cin, const void* dyT, const void* dyT_l
   p.row_tiles = (p.taps * cout + 127) / 128;
   p.col_tiles = cin / bn;
   const int tiles = p.row_tiles * p.col_tiles;
-  int splits = (2 * 148 + tiles - 1) / tiles;
+  // one CTA per SM is resident (the operand ring takes most of the shared memory), so more than one wave of split-K CTAs
+  // only multiplies the fp32 atomics of the epilogue (128 x BN per CTA), which is what bounds the large filters
+  static const int wg_ctas = getenv("LDM_WGRAD_CTAS") ? atoi(getenv("LDM_WGRAD_CTAS")) : 100;
+  int splits = (wg_ctas + tiles - 1) / tiles;
+  // long contractions (the 32x32 layers at large batch: thousands of k-blocks, few tiles) are bound by the k-loop, not by
+  // the epilogue: give them two waves
+  if (p.kb_total / splits > 96) splits = (2 * 148 + tiles - 1) / tiles;
   if (splits > p.kb_total) splits = p.kb_total;
   if (splits < 1) splits = 1;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
@@ -370,5 +398,9 @@ static int wg_launch(const void* xT, int cin, const void* dyT, const void* dyT_l
     default: wgrad_tc_kernel<64><<<grid, 192, 6 * (16384 + 64 * 128) + 2048, st>>>(mdy, mdl, mdr, mx, p); break;
   }
   LDM_LAUNCHED("conv_wgrad_tc");
+  if (ksize != 1) {
+    wgrad_finish_kernel<<<dim3(cin / 32, cout), 288, 0, st>>>(nat, dw, cout, cin);
+    LDM_LAUNCHED("conv_wgrad_finish");
+  }
   return 0;
 }

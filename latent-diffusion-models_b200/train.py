@@ -423,10 +423,26 @@ def unet_autograd_forward(model, x_noisy: torch.Tensor, t: torch.Tensor, y: Opti
     return _FinalConv.apply(h, model.final_conv[1].weight.view(model.out_channels, model.channels), model.final_conv[1].bias)
 
 
+class _GraphedVariant(torch.nn.Module):
+    """What gets captured: the autograd forward of ``model`` for one call signature.  A wrapper module of its own, because
+    torch.cuda.make_graphed_callables patches ``forward`` of the module it is given -- capturing a second signature (with /
+    without labels) on the UNet itself would capture the first one's replay stub."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+
+    def forward(self, x_noisy, t, y=None):
+        return unet_autograd_forward(self.model, x_noisy, t, y)
+
+
 def make_graphed(model, x_noisy: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor]):
-    """Capture the UNet's training forward and backward as CUDA graphs (torch.cuda.make_graphed_callables): the ~500
+    """Capture the UNet's training forward and backward as CUDA graphs (torch.cuda.make_graphed_callables): the ~560
     kernel launches of a step are replayed instead of re-issued from Python, which is what bounds small batches.
     Returns a callable with the model's signature for inputs of exactly these shapes (labels given or not, as captured);
-    gradients land in the same fp32 ``.grad`` tensors.  The four dead bottleneck mlp_t parameters are unused inputs."""
+    gradients land in the same fp32 ``.grad`` tensors.  The four dead bottleneck mlp_t parameters are unused inputs.
+    ``model`` itself is left untouched, so several signatures can be captured side by side."""
     args = (x_noisy.detach().clone(), t.detach().clone()) + ((y.detach().clone(),) if y is not None else ())
-    return torch.cuda.make_graphed_callables(model, args, allow_unused_input=True)
+    variant = _GraphedVariant(model)
+    variant.train(model.training)
+    return torch.cuda.make_graphed_callables(variant, args, allow_unused_input=True)

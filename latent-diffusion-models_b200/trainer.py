@@ -155,7 +155,7 @@ class DiffusionModelTrainer:
     The reference's wandb logging, early stopping and checkpoint writing are the caller's business."""
 
     def __init__(self, config, model, diffusion, train_loader=None, val_loader=None, classes=None, cfg_scale: float = 0.0,
-                 device=None, rng: Optional[np.random.Generator] = None):
+                 device=None, rng: Optional[np.random.Generator] = None, use_cuda_graphs: bool = True):
         get = (lambda k: config[k]) if hasattr(config, "__getitem__") else (lambda k: getattr(config, k))
         self.config, self.model, self.diffusion = config, model, diffusion
         self.train_loader, self.val_loader = train_loader, val_loader
@@ -166,6 +166,10 @@ class DiffusionModelTrainer:
         self.loss_fn = torch.nn.functional.mse_loss
         self._rng = rng if rng is not None else np.random.default_rng()
         self._get = get
+        # forward + backward of the UNet captured as CUDA graphs, one pair per (batch shape, labels given?): a step is
+        # ~560 kernel launches, and at the reference's batch 64 issuing them from Python takes twice as long as running them
+        self.use_cuda_graphs = use_cuda_graphs
+        self._graphed: dict = {}
 
     @staticmethod
     def _has(config, key) -> bool:
@@ -177,13 +181,28 @@ class DiffusionModelTrainer:
     def forward(self, x, t, targets=None):                      # src/DiffusionModelTrainer.py:151-160
         return self.model(x, t) if targets is None else self.model(x, t, targets)
 
+    def _graphed_forward(self, data: torch.Tensor, targets: Optional[torch.Tensor]):
+        """The CUDA-graphed UNet callable for this batch shape (captured on first use), or None to run eagerly."""
+        if not self.use_cuda_graphs:
+            return None
+        key = (tuple(data.shape), targets is not None)
+        if key not in self._graphed:
+            from .train import make_graphed
+            try:
+                noise, xt, t = self.diffusion(data)
+                self._graphed[key] = make_graphed(self.model, xt, t, targets)
+            except Exception:   # noqa: BLE001 -- capture is an optimisation; the eager autograd path is always there
+                self._graphed[key] = None
+        return self._graphed[key]
+
     def _train_epoch(self, epoch: int) -> float:                 # :28-77
         self.model.train()
         total = torch.zeros((), dtype=torch.float64, device=self.device)
         for data, targets in self.train_loader:
             data, targets = data.to(self.device, non_blocking=True), targets.to(self.device, non_blocking=True)
-            loss = train_step(self.model, self.diffusion, self.optimizer, data, targets,
-                              drop_labels=bool(self._rng.random() < 0.1), loss_fn=self.loss_fn)
+            drop = bool(self._rng.random() < 0.1)
+            loss = train_step(self.model, self.diffusion, self.optimizer, data, targets, drop_labels=drop,
+                              forward=self._graphed_forward(data, None if drop else targets), loss_fn=self.loss_fn)
             total += loss.double() * data.size(0)                # accumulated on the device: one sync per epoch, not per step
         return float(total.item()) / len(self.train_loader)
 

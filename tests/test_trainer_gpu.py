@@ -127,7 +127,8 @@ def test_mse_matches_torch():
         assert abs(float(trainer.mse_loss(a, b)) - float(ref)) < 1e-5 * float(ref)
 
 
-def test_trainer_epochs_reduce_loss():
+@pytest.mark.parametrize("graphs", [True, False])
+def test_trainer_epochs_reduce_loss(graphs):
     import ldm_b200
     from ldm_b200 import trainer
     torch.manual_seed(0)
@@ -139,11 +140,13 @@ def test_trainer_epochs_reduce_loss():
     loader = [(x0, y)] * 12
     cfg = {"lr": 5e-4, "epochs": 1, "data": {"image_channels": 3, "image_size": 32}}
     tr = trainer.DiffusionModelTrainer(cfg, model, d, loader, loader[:2], classes=torch.arange(4), cfg_scale=3.0,
-                                       rng=np.random.default_rng(0))
+                                       rng=np.random.default_rng(0), use_cuda_graphs=graphs)
     v0 = tr._val_epoch(0)
     first = tr._train_epoch(0)
     second = tr._train_epoch(1)
     assert np.isfinite(first) and second < first
     assert np.isfinite(v0) and np.isfinite(tr._val_epoch(1))
+    if graphs:   # both label variants were captured (seeded rng drops labels at least once in 24 steps) and actually used
+        assert any(v is not None for v in tr._graphed.values())
     imgs = tr.sample(torch.arange(2), cfg_scale=3.0, as_uint8=True)
     assert len(imgs) == 2 and imgs[0].shape == (32, 32, 3) and imgs[0].dtype == np.uint8
