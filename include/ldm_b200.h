@@ -264,7 +264,11 @@ int ldm_max_pool2x2_backward(const void* x, int ldx, const void* dy, int lddy, v
 /* ConvTranspose2d(k2,s2) backward gather: out[n,h,w,q*C+c] = dy[n,2h+q/2,2w+q%2,c]; then dx / dW are a 1x1 dgrad / wgrad */
 int ldm_pixel_unshuffle2x2(const void* dy, int lddy, void* out, int batch, int height, int width, int channels, int dtype,
                            void* stream);
-int ldm_linear_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int n_tokens, int dtype, void* stream);
+/* backward of ldm_linear_attention: dqkv [B][N][384] from qkv and dout [B][N][128].  workspace
+ * (ldm_linear_attention_backward_workspace_bytes, 16-byte aligned, or NULL) enables the mma.sync kernels (bf16, N % 16 == 0) */
+int64_t ldm_linear_attention_backward_workspace_bytes(int batch);
+int ldm_linear_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int n_tokens, int dtype,
+                                  void* workspace, void* stream);
 int ldm_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int n_tokens, int dtype, void* stream);
 /* initial 3x3 conv on the fp32 NCHW input (src/UNet.py:331) and its weight gradient; w_scratch: 9*cin*cout floats */
 int ldm_initial_conv(const float* x_nchw, const float* w_oihw, const float* bias, void* y, int batch, int cin, int cout,

@@ -95,7 +95,8 @@ SIGNATURES = {
     "ldm_max_pool2x2_backward": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_int, vp]),
     "ldm_pixel_unshuffle2x2": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
-    "ldm_linear_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_linear_attention_backward_workspace_bytes": (C.c_int64, [C.c_int]),
+    "ldm_linear_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "ldm_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_initial_conv": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "ldm_initial_conv_wgrad": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),

@@ -437,6 +437,396 @@ __global__ void __launch_bounds__(128) linattn_mma_kernel(const bf16* __restrict
   cp_async_wait<0>();
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// LinearAttention backward on mma.sync (bf16 operands, fp32 accumulate), two kernels:
+//   linattn_bwd_ctx_kernel    grid (batch), one warp per head: a pass over (k, v) like the forward's phase 1 gives
+//                             ctx[d][e] = sum_t ks[t][d] v[t][e] (ks = softmax over tokens) with its row max and 1/Z; a pass
+//                             over (q, dout) gives dctx[d][e] = sum_t qs[t][d] dout[t][e] (qs = 32^-1/2 softmax_d(q)).
+//   linattn_bwd_apply_kernel  grid (batch, token chunks): per 16-token tile  dqs = dout ctx^T, dks = v dctx^T, dv = ks dctx,
+//                             then dq = qs (dqs - <qs,dqs>/s), dk = ks (dks - cs[d]) with cs[d] = sum_e dctx[d][e] ctx[d][e]
+//                             (= sum_t ks dks, so no third pass over the tokens is needed).
+// ws per (sample, head): ctx[32][32], dctx[32][32], kmax[32], kzinv[32]  (fp32)
+constexpr int LB_WS = 2 * 32 * 32 + 64;
+
+__global__ void __launch_bounds__(128) linattn_bwd_ctx_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                              float* __restrict__ ws, int N) {
+  __shared__ __align__(128) uint8_t smem[4][2][2][LM_BUF];
+  const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const bf16* base = qkv + (int64_t)b * N * 384 + h * LA_D;
+  const bf16* dob = dout + (int64_t)b * N * 128 + h * LA_D;
+  float* wsp = ws + ((int64_t)b * 4 + h) * LB_WS;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&smem[h][0][0][0]);
+  auto buf = [&](int stage, int which) { return sbase + (uint32_t)((stage * 2 + which) * LM_BUF); };
+  const int steps = N >> 4;
+  const int tiles = (steps + 1) >> 1;
+
+  // pass 0: (k, v) -> ctx;  pass 1: (q, dout) -> dctx
+  for (int pass = 0; pass < 2; ++pass) {
+    auto load = [&](int tile, int stage) {
+      const int tok0 = tile * LM_TILE;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = lane + 32 * i;
+        const int which = c >> 7, r = (c & 127) >> 2, ch = c & 3;
+        if (tok0 + r < N) {
+          const bf16* src = pass == 0 ? base + (int64_t)(tok0 + r) * 384 + 128 * (1 + which) + ch * 8
+                                      : (which == 0 ? base + (int64_t)(tok0 + r) * 384 + ch * 8
+                                                    : dob + (int64_t)(tok0 + r) * 128 + ch * 8);
+          cp_async16(buf(stage, which) + lm_off(r, ch), src);
+        }
+      }
+    };
+    float acc[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+    float m_run[2][2], z[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) { m_run[mt][hf] = -INFINITY; z[mt][hf] = 0.f; }
+
+    load(0, 0);
+    cp_async_commit();
+    if (tiles > 1) load(1, 1);
+    cp_async_commit();
+    for (int t = 0; t < tiles; ++t) {
+      cp_async_wait<1>();
+      __syncwarp();
+      const int stage = t & 1;
+      const int nst = min(2, steps - 2 * t);
+      uint32_t a[2][2][4];   // A fragments of the transposed left operand: rows = head channel d, cols = token
+#pragma unroll
+      for (int st = 0; st < 2; ++st)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          if (st < nst) {
+            const int r = st * 16 + ((lane >> 4) << 3) + (lane & 7);
+            const int ch = mt * 2 + ((lane >> 3) & 1);
+            ldsm_x4_t(a[st][mt], buf(stage, 0) + lm_off(r, ch));
+          } else {
+            a[st][mt][0] = a[st][mt][1] = a[st][mt][2] = a[st][mt][3] = 0u;
+          }
+        }
+      if (pass == 0) {
+        // online softmax over the tokens (rows d are fixed per thread), exactly the forward's phase 1
+        float sc[2][2], ml2[2][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int st = 0; st < 2; ++st)
+              if (st < nst) {
+                float2 x0 = unpack_bf2(a[st][mt][hf]), x1 = unpack_bf2(a[st][mt][hf + 2]);
+                mx = fmaxf(mx, fmaxf(fmaxf(x0.x, x0.y), fmaxf(x1.x, x1.y)));
+              }
+            mx = quad_max(mx);
+            const float nm = fmaxf(m_run[mt][hf], mx);
+            sc[mt][hf] = ex2f((m_run[mt][hf] - nm) * LOG2E);
+            m_run[mt][hf] = nm;
+            ml2[mt][hf] = nm * LOG2E;
+            z[mt][hf] *= sc[mt][hf];
+          }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            acc[mt][nt][0] *= sc[mt][0]; acc[mt][nt][1] *= sc[mt][0];
+            acc[mt][nt][2] *= sc[mt][1]; acc[mt][nt][3] *= sc[mt][1];
+          }
+#pragma unroll
+        for (int st = 0; st < 2; ++st)
+          if (st < nst) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int hf = i & 1;
+                float2 x = unpack_bf2(a[st][mt][i]);
+                const float p0 = ex2f(fmaf(x.x, LOG2E, -ml2[mt][hf])), p1 = ex2f(fmaf(x.y, LOG2E, -ml2[mt][hf]));
+                z[mt][hf] += p0 + p1;
+                a[st][mt][i] = pack_bf2(p0, p1);
+              }
+          }
+      } else {
+        // softmax over d for every token column: a token's 32 channels are rows g, g+8 of both m-tiles on the 8 lanes
+        // that share tq -> reduce over lane bits 2..4
+#pragma unroll
+        for (int st = 0; st < 2; ++st)
+          if (st < nst) {
+#pragma unroll
+            for (int cg = 0; cg < 2; ++cg) {   // registers (0,1): tokens 2tq, 2tq+1;  (2,3): tokens 2tq+8, 2tq+9
+              float2 x[2][2];
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) x[mt][hf] = unpack_bf2(a[st][mt][cg * 2 + hf]);
+              float m0 = fmaxf(fmaxf(x[0][0].x, x[0][1].x), fmaxf(x[1][0].x, x[1][1].x));
+              float m1 = fmaxf(fmaxf(x[0][0].y, x[0][1].y), fmaxf(x[1][0].y, x[1][1].y));
+#pragma unroll
+              for (int o = 4; o <= 16; o <<= 1) {
+                m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+                m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+              }
+              m0 *= LOG2E; m1 *= LOG2E;
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  x[mt][hf].x = ex2f(fmaf(x[mt][hf].x, LOG2E, -m0));
+                  x[mt][hf].y = ex2f(fmaf(x[mt][hf].y, LOG2E, -m1));
+                  s0 += x[mt][hf].x; s1 += x[mt][hf].y;
+                }
+#pragma unroll
+              for (int o = 4; o <= 16; o <<= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+              }
+              const float i0 = 0.17677669529663687f / s0, i1 = 0.17677669529663687f / s1;
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) a[st][mt][cg * 2 + hf] = pack_bf2(x[mt][hf].x * i0, x[mt][hf].y * i1);
+            }
+          }
+      }
+      // B fragments of the right operand (rows = token, cols = e) and the MMAs
+#pragma unroll
+      for (int st = 0; st < 2; ++st)
+        if (st < nst) {
+          uint32_t bv[2][4];
+#pragma unroll
+          for (int jp = 0; jp < 2; ++jp) {
+            const int r = st * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+            const int ch = jp * 2 + (lane >> 4);
+            ldsm_x4_t(bv[jp], buf(stage, 1) + lm_off(r, ch));
+          }
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) hmma_bf16(acc[mt][nt], a[st][mt], bv[nt >> 1][(nt & 1) * 2], bv[nt >> 1][(nt & 1) * 2 + 1]);
+        }
+      __syncwarp();
+      if (t + 2 < tiles) load(t + 2, stage);
+      cp_async_commit();
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+    // results: row d = mt*16 + hf*8 + g, columns e = nt*8 + 2tq, +1
+    float* dst = wsp + pass * 1024;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int d = mt * 16 + hf * 8 + g;
+        float f = 1.f;
+        if (pass == 0) {
+          const float zs = quad_sum(z[mt][hf]);
+          f = 1.0f / zs;
+          if (tq == 0) { wsp[2048 + d] = m_run[mt][hf]; wsp[2048 + 32 + d] = f; }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          *reinterpret_cast<float2*>(dst + d * 32 + nt * 8 + 2 * tq) = make_float2(acc[mt][nt][hf * 2] * f, acc[mt][nt][hf * 2 + 1] * f);
+      }
+  }
+}
+
+constexpr int LB_CHUNK = 128;   // tokens per CTA of the apply kernel
+
+__global__ void __launch_bounds__(128) linattn_bwd_apply_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                                const float* __restrict__ ws, bf16* __restrict__ dqkv, int N) {
+  // per warp: [stage][q|k|v|dout] tiles of 2 KB, then ctx and dctx as bf16 [d][e] tiles, then kmax | kzinv | cs
+  extern __shared__ __align__(128) uint8_t lb_dyn[];
+  constexpr int WARP_BYTES = 2 * 4 * LM_BUF + 2 * LM_BUF + 3 * 32 * 4;
+  const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const bf16* base = qkv + (int64_t)b * N * 384 + h * LA_D;
+  const bf16* dob = dout + (int64_t)b * N * 128 + h * LA_D;
+  bf16* dbase = dqkv + (int64_t)b * N * 384 + h * LA_D;
+  const float* wsp = ws + ((int64_t)b * 4 + h) * LB_WS;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(lb_dyn + (size_t)h * WARP_BYTES);
+  auto buf = [&](int stage, int which) { return sbase + (uint32_t)((stage * 4 + which) * LM_BUF); };
+  const uint32_t ctx_s = sbase + 8 * LM_BUF, dctx_s = ctx_s + LM_BUF;
+  float* fl = reinterpret_cast<float*>(lb_dyn + (size_t)h * WARP_BYTES + 10 * LM_BUF);   // kmax[32] kzinv[32] cs[32]
+  const float scale = 0.17677669529663687f;
+
+  const int tok_begin = blockIdx.y * LB_CHUNK, tok_end = min(N, tok_begin + LB_CHUNK);
+  const int steps = (tok_end - tok_begin) >> 4;
+  const int tiles = (steps + 1) >> 1;
+  auto load = [&](int tile, int stage) {
+    const int tok0 = tok_begin + tile * LM_TILE;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = lane + 32 * i;                 // 0..511: which = c / 128 (q, k, v, dout)
+      const int which = c >> 7, r = (c & 127) >> 2, ch = c & 3;
+      if (tok0 + r < tok_end) {
+        const bf16* src = which < 3 ? base + (int64_t)(tok0 + r) * 384 + 128 * which + ch * 8 : dob + (int64_t)(tok0 + r) * 128 + ch * 8;
+        cp_async16(buf(stage, which) + lm_off(r, ch), src);
+      }
+    }
+  };
+  load(0, 0);
+  cp_async_commit();
+  if (tiles > 1) load(1, 1);
+  cp_async_commit();
+
+  // ctx, dctx -> bf16 tiles; cs[d] = sum_e dctx[d][e] ctx[d][e] in fp32 (lane = d)
+  {
+    float csd = 0.f;
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+      float cv[8], dv8[8];
+#pragma unroll
+      for (int j = 0; j < 8; j += 4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(wsp + lane * 32 + c8 * 8 + j);
+        const float4 d4 = *reinterpret_cast<const float4*>(wsp + 1024 + lane * 32 + c8 * 8 + j);
+        cv[j] = c4.x; cv[j + 1] = c4.y; cv[j + 2] = c4.z; cv[j + 3] = c4.w;
+        dv8[j] = d4.x; dv8[j + 1] = d4.y; dv8[j + 2] = d4.z; dv8[j + 3] = d4.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) csd = fmaf(cv[j], dv8[j], csd);
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ctx_s + lm_off(lane, c8)), "r"(pack_bf2(cv[0], cv[1])),
+                   "r"(pack_bf2(cv[2], cv[3])), "r"(pack_bf2(cv[4], cv[5])), "r"(pack_bf2(cv[6], cv[7])) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dctx_s + lm_off(lane, c8)), "r"(pack_bf2(dv8[0], dv8[1])),
+                   "r"(pack_bf2(dv8[2], dv8[3])), "r"(pack_bf2(dv8[4], dv8[5])), "r"(pack_bf2(dv8[6], dv8[7])) : "memory");
+    }
+    fl[lane] = wsp[2048 + lane];
+    fl[32 + lane] = wsp[2048 + 32 + lane];
+    fl[64 + lane] = csd;
+  }
+  __syncwarp();
+  // B fragments.  dqs / dks contract over e with B[k = e][n = d] = M[d][e]: plain ldmatrix on the [d][e] tile (rows = n);
+  // dv contracts over d with B[k = d][n = e] = dctx[d][e]: transposing ldmatrix (rows = k), as the forward does for ctx.
+  uint32_t bctx[2][2][4], bdc[2][2][4], bdct[2][2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int jp = 0; jp < 2; ++jp) {
+      // matrices: (n rows jp*16 + 0-7, k chunk 2ks), (same rows, chunk 2ks+1), (n rows +8, chunk 2ks), (n rows +8, chunk 2ks+1)
+      const int rn = jp * 16 + ((lane >> 4) << 3) + (lane & 7);
+      const int chn = ks * 2 + ((lane >> 3) & 1);
+      ldsm_x4(bctx[ks][jp], ctx_s + lm_off(rn, chn));
+      ldsm_x4(bdc[ks][jp], dctx_s + lm_off(rn, chn));
+      const int rk = ks * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+      const int chk = jp * 2 + (lane >> 4);
+      ldsm_x4_t(bdct[ks][jp], dctx_s + lm_off(rk, chk));
+    }
+  // per-column constants in C layout (cols nt*8 + 2tq, +1) and in A layout (k index ks*16 + 2tq (+1), +8 (+9))
+  float2 kmC[4], kzC[4], csC[4], kmA[2][2], kzA[2][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int c = nt * 8 + 2 * tq;
+    kmC[nt] = make_float2(fl[c] * LOG2E, fl[c + 1] * LOG2E);
+    kzC[nt] = make_float2(fl[32 + c], fl[32 + c + 1]);
+    csC[nt] = make_float2(fl[64 + c], fl[64 + c + 1]);
+  }
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const int c = ks * 16 + hi * 8 + 2 * tq;
+      kmA[ks][hi] = make_float2(fl[c] * LOG2E, fl[c + 1] * LOG2E);
+      kzA[ks][hi] = make_float2(fl[32 + c], fl[32 + c + 1]);
+    }
+
+  for (int t = 0; t < tiles; ++t) {
+    cp_async_wait<1>();
+    __syncwarp();
+    const int stage = t & 1;
+    const int nst = min(2, steps - 2 * t);
+    for (int mi = 0; mi < nst; ++mi) {
+      // A fragments (rows = tokens, k = channel): dout, v, and ks = exp(k - kmax) / Z
+      uint32_t ado[2][4], av[2][4], ak[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int r = mi * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+        const int ch = ks * 2 + (lane >> 4);
+        ldsm_x4(ado[ks], buf(stage, 3) + lm_off(r, ch));
+        ldsm_x4(av[ks], buf(stage, 2) + lm_off(r, ch));
+        ldsm_x4(ak[ks], buf(stage, 1) + lm_off(r, ch));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {             // regs 0,1: k cols 2tq,+1 (rows g, g+8); regs 2,3: k cols +8
+          const int hi = i >> 1;
+          float2 x = unpack_bf2(ak[ks][i]);
+          x.x = ex2f(fmaf(x.x, LOG2E, -kmA[ks][hi].x)) * kzA[ks][hi].x;
+          x.y = ex2f(fmaf(x.y, LOG2E, -kmA[ks][hi].y)) * kzA[ks][hi].y;
+          ak[ks][i] = pack_bf2(x.x, x.y);
+        }
+      }
+      float dqs[4][4], dks[4][4], dvv[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { dqs[nt][i] = 0.f; dks[nt][i] = 0.f; dvv[nt][i] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          // plain-ldmatrix B: n-tile nt = rows (nt>>1)*16 + (nt&1)*8: registers (nt&1)*2 (k lo), (nt&1)*2+1 (k hi)
+          hmma_bf16(dqs[nt], ado[ks], bctx[ks][nt >> 1][(nt & 1) * 2], bctx[ks][nt >> 1][(nt & 1) * 2 + 1]);
+          hmma_bf16(dks[nt], av[ks], bdc[ks][nt >> 1][(nt & 1) * 2], bdc[ks][nt >> 1][(nt & 1) * 2 + 1]);
+          hmma_bf16(dvv[nt], ak[ks], bdct[ks][nt >> 1][(nt & 1) * 2], bdct[ks][nt >> 1][(nt & 1) * 2 + 1]);
+        }
+      }
+      // elementwise part in C layout: rows g (regs 0,1) and g+8 (regs 2,3), cols nt*8 + 2tq, +1
+      const int tok0 = tok_begin + t * LM_TILE + mi * 16;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int row = mi * 16 + hf * 8 + g;
+        float2 qv[4], kv[4];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          uint32_t uq, uk;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(uq) : "r"(buf(stage, 0) + lm_off(row, nt) + tq * 4));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(uk) : "r"(buf(stage, 1) + lm_off(row, nt) + tq * 4));
+          qv[nt] = unpack_bf2(uq);
+          kv[nt] = unpack_bf2(uk);
+          mx = fmaxf(mx, fmaxf(qv[nt].x, qv[nt].y));
+        }
+        mx = quad_max(mx) * LOG2E;
+        float s = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          qv[nt].x = ex2f(fmaf(qv[nt].x, LOG2E, -mx)); qv[nt].y = ex2f(fmaf(qv[nt].y, LOG2E, -mx));
+          s += qv[nt].x + qv[nt].y;
+        }
+        const float inv = scale / quad_sum(s);
+        float inner = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          qv[nt].x *= inv; qv[nt].y *= inv;                       // qs
+          inner = fmaf(qv[nt].x, dqs[nt][hf * 2], inner);
+          inner = fmaf(qv[nt].y, dqs[nt][hf * 2 + 1], inner);
+        }
+        inner = quad_sum(inner) * (1.0f / scale);
+        bf16* orow = dbase + (int64_t)(tok0 + hf * 8 + g) * 384 + 2 * tq;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const float dq0 = qv[nt].x * (dqs[nt][hf * 2] - inner), dq1 = qv[nt].y * (dqs[nt][hf * 2 + 1] - inner);
+          const float k0 = ex2f(fmaf(kv[nt].x, LOG2E, -kmC[nt].x)) * kzC[nt].x;
+          const float k1 = ex2f(fmaf(kv[nt].y, LOG2E, -kmC[nt].y)) * kzC[nt].y;
+          const float dk0 = k0 * (dks[nt][hf * 2] - csC[nt].x), dk1 = k1 * (dks[nt][hf * 2 + 1] - csC[nt].y);
+          *reinterpret_cast<uint32_t*>(orow + nt * 8) = pack_bf2(dq0, dq1);
+          *reinterpret_cast<uint32_t*>(orow + 128 + nt * 8) = pack_bf2(dk0, dk1);
+          *reinterpret_cast<uint32_t*>(orow + 256 + nt * 8) = pack_bf2(dvv[nt][hf * 2], dvv[nt][hf * 2 + 1]);
+        }
+      }
+    }
+    __syncwarp();
+    if (t + 2 < tiles) load(t + 2, stage);
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
@@ -886,5 +1276,29 @@ int k_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, 
     attn_kernel<float><<<grid, threads, smem, st>>>((const float*)qkv, (float*)out, n_tokens);
   }
   LDM_LAUNCHED("attention");
+  return 0;
+}
+
+
+// ---- LinearAttention backward on mma.sync (bf16, N % 16 == 0); workspace: k_linear_attention_backward_ws_bytes
+int64_t k_linear_attention_backward_ws_bytes(int batch) { return (int64_t)batch * 4 * LB_WS * sizeof(float) + 256; }
+bool k_linear_attention_backward_mma_applicable(int n_tokens, int dtype) {
+  return dtype == LDM_DT_BF16 && n_tokens % 16 == 0 && getenv("LDM_LINATTN_BWD_SIMT") == nullptr;
+}
+int k_linear_attention_backward_mma(const void* qkv, const void* dout, void* dqkv, int batch, int N, void* workspace,
+                                    cudaStream_t st) {
+  LDM_REQUIRE(workspace && ((uintptr_t)workspace & 15) == 0, "linear_attention_backward: workspace missing or unaligned");
+  if (batch == 0 || N == 0) return 0;
+  constexpr int smem = 4 * (2 * 4 * LM_BUF + 2 * LM_BUF + 3 * 32 * 4);
+  static bool attr_set = false;
+  if (!attr_set) {
+    LDM_CUDA(cudaFuncSetAttribute(linattn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  linattn_bwd_ctx_kernel<<<batch, 128, 0, st>>>((const bf16*)qkv, (const bf16*)dout, (float*)workspace, N);
+  LDM_LAUNCHED("linattn_bwd_ctx");
+  linattn_bwd_apply_kernel<<<dim3(batch, (N + LB_CHUNK - 1) / LB_CHUNK), 128, smem, st>>>((const bf16*)qkv, (const bf16*)dout,
+                                                                                      (const float*)workspace, (bf16*)dqkv, N);
+  LDM_LAUNCHED("linattn_bwd_apply");
   return 0;
 }

@@ -185,3 +185,9 @@ int k_group_norm_backward_stream(const void* x, int ldx, const void* dy, int ldd
                                  const float* rowvec, int ld_rowvec, void* dx, int lddx, float* dgamma, float* dbeta,
                                  float* drowvec, int ld_drowvec, int batch, int hw, int channels, int groups, float eps, int silu,
                                  const void* fwd_part, void* workspace, cudaStream_t st);
+
+// ---- attention.cu: LinearAttention backward on mma.sync
+int64_t k_linear_attention_backward_ws_bytes(int batch);
+bool k_linear_attention_backward_mma_applicable(int n_tokens, int dtype);
+int k_linear_attention_backward_mma(const void* qkv, const void* dout, void* dqkv, int batch, int N, void* workspace,
+                                    cudaStream_t st);

@@ -88,8 +88,12 @@ int ldm_pixel_unshuffle2x2(const void* dy, int lddy, void* out, int batch, int h
   LDM_REQUIRE(dy && out, "ldm_pixel_unshuffle2x2: null argument");
   return k_unshuffle2(dy, lddy, out, batch, height, width, channels, dtype, (cudaStream_t)stream);
 }
-int ldm_linear_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int n_tokens, int dtype, void* stream) {
+int64_t ldm_linear_attention_backward_workspace_bytes(int batch) { return k_linear_attention_backward_ws_bytes(batch); }
+int ldm_linear_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int n_tokens, int dtype,
+                                  void* workspace, void* stream) {
   LDM_REQUIRE(qkv && dout && dqkv, "ldm_linear_attention_backward: null argument");
+  if (workspace && k_linear_attention_backward_mma_applicable(n_tokens, dtype))
+    return k_linear_attention_backward_mma(qkv, dout, dqkv, batch, n_tokens, workspace, (cudaStream_t)stream);
   return k_linear_attention_backward(qkv, dout, dqkv, batch, n_tokens, dtype, (cudaStream_t)stream);
 }
 int ldm_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int n_tokens, int dtype, void* stream) {

@@ -167,8 +167,10 @@ class _LinAttn(Function):
         dout = _c(dout)
         B, H, W, _ = qkv.shape
         dqkv = torch.empty_like(qkv)
-        _lib.check(_lb().ldm_linear_attention_backward(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, H * W,
-                                                       ops._dt(qkv), _st()))
+        lib = _lb()
+        ws = torch.empty(lib.ldm_linear_attention_backward_workspace_bytes(B), dtype=torch.uint8, device=qkv.device)
+        _lib.check(lib.ldm_linear_attention_backward(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, H * W,
+                                                     ops._dt(qkv), ws.data_ptr(), _st()))
         return dqkv
 
 

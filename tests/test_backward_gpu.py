@@ -92,7 +92,7 @@ def test_group_norm_backward(dtype, C, R, G, silu, rv):
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-@pytest.mark.parametrize("N,linear", [(1024, True), (16, True), (4, False), (64, False)])
+@pytest.mark.parametrize("N,linear", [(1024, True), (16, True), (64, True), (144, True), (256, True), (4, False), (64, False)])
 def test_attention_backward(dtype, N, linear):
     from ldm_b200 import train
     from oracle import unet_oracle as U
