@@ -244,6 +244,9 @@ int ldm_conv2d_wgrad_tc(const void* x, int ldx, int cin, const void* dy, int ldd
                         int batch, int height, int width, int ksize, void* scratch, void* stream);
 /* filter for the data gradient: dx = ldm_conv2d(dy, w_dgrad) with the roles of Cin and Cout exchanged.
  * w_packed [Cin][kh'][kw'][Cout] = w[co][ci][k-1-kh'][k-1-kw'] */
+/* ldm_pack_conv_weight and ldm_pack_conv_weight_dgrad of one filter in a single launch (the training forward needs both) */
+int ldm_pack_conv_weight_pair(const float* w_oihw, int cout, int cin, int ksize, void* w_packed, void* w_packed_dgrad, int dtype,
+                              void* stream);
 int ldm_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin, int ksize, void* w_packed, int dtype, void* stream);
 /* out[c] (accumulated) = sum_r a[r][c] */
 int ldm_column_sum(const void* a, int lda, float* out, int rows, int cols, int dtype, void* stream);

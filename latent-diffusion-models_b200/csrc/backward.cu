@@ -135,6 +135,29 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, int cout, int cin
   out[i] = from_float<T>(w[((int64_t)co * cin + ci) * taps + src_tap]);
 }
 
+// both packed forms in one launch: the first half of the grid writes the forward filter [cout][tap*cin + ci], the second
+// half the dgrad filter above (one thread per output element; a shared-memory tiled variant measured slower: the filters
+// are small and thousands of independent CTAs hide the strided reads better than 256 looping ones)
+template <typename T>
+__global__ void pack_pair_kernel(const float* __restrict__ w, int cout, int cin, int ksize, T* __restrict__ fwd, T* __restrict__ dgrad,
+                                 int half_blocks) {
+  const int taps = ksize * ksize;
+  const int64_t total = (int64_t)cin * taps * cout;
+  const bool second = (int)blockIdx.x >= half_blocks;
+  const int64_t i = (int64_t)(blockIdx.x - (second ? half_blocks : 0)) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  if (!second) {
+    const int k = (int)(i % (taps * cin)), o = (int)(i / (taps * cin));
+    const int tap = k / cin, c = k % cin;
+    fwd[i] = from_float<T>(w[((int64_t)o * cin + c) * taps + tap]);
+  } else {
+    const int co = (int)(i % cout);
+    const int tp = (int)((i / cout) % taps);
+    const int ci = (int)(i / ((int64_t)cout * taps));
+    dgrad[i] = from_float<T>(w[((int64_t)co * cin + ci) * taps + (taps - 1 - tp)]);
+  }
+}
+
 // ------------------------------------------------------------------ GroupNorm (+SiLU) backward, one CTA per sample
 template <typename T>
 __global__ void __launch_bounds__(1024)
@@ -794,6 +817,15 @@ int k_pack_dgrad_weight(const float* w_oihw, int cout, int cin, int ksize, void*
   if (total == 0) return 0;
   DISPATCH_T(dtype, pack_dgrad_kernel<T><<<(int)ceil_div64(total, 256), 256, 0, st>>>(w_oihw, cout, cin, ksize, (T*)out));
   LDM_LAUNCHED("pack_dgrad_weight");
+  return 0;
+}
+
+int k_pack_conv_weight_pair(const float* w_oihw, int cout, int cin, int ksize, void* fwd, void* dgrad, int dtype, cudaStream_t st) {
+  const int64_t total = (int64_t)cin * ksize * ksize * cout;
+  if (total == 0) return 0;
+  const int half = (int)ceil_div64(total, 256);
+  DISPATCH_T(dtype, pack_pair_kernel<T><<<2 * half, 256, 0, st>>>(w_oihw, cout, cin, ksize, (T*)fwd, (T*)dgrad, half));
+  LDM_LAUNCHED("pack_conv_weight_pair");
   return 0;
 }
 

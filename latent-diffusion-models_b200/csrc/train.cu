@@ -48,6 +48,11 @@ int ldm_conv2d_wgrad_tc(const void* x, int ldx, int cin, const void* dy, int ldd
   RC(k_nhwc_to_chw_bf16(dy, lddy, dyT, dyL, dyR, dbias, batch, cout, hw, width, st));
   return k_conv_wgrad_tc(xT, cin, dyT, dyL, dyR, cout, dw_oihw, nat, batch, height, width, ksize, st);
 }
+int ldm_pack_conv_weight_pair(const float* w_oihw, int cout, int cin, int ksize, void* w_packed, void* w_packed_dgrad, int dtype,
+                              void* stream) {
+  LDM_REQUIRE(w_oihw && w_packed && w_packed_dgrad, "ldm_pack_conv_weight_pair: null argument");
+  return k_pack_conv_weight_pair(w_oihw, cout, cin, ksize, w_packed, w_packed_dgrad, dtype, (cudaStream_t)stream);
+}
 int ldm_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin, int ksize, void* w_packed, int dtype, void* stream) {
   LDM_REQUIRE(w_oihw && w_packed, "ldm_pack_conv_weight_dgrad: null argument");
   return k_pack_dgrad_weight(w_oihw, cout, cin, ksize, w_packed, dtype, (cudaStream_t)stream);
