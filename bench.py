@@ -204,14 +204,14 @@ def train_leg(args, dev, rank, world, stream):
         return ltrainer.train_step(model, diffusion, opt, data, targets, forward=fwd)
 
     with torch.cuda.stream(stream):
-        for _ in range(3):
+        for _ in range(5):
             step()
         torch.cuda.synchronize(dev)
         if world > 1:
             tdist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        n = 5
+        n = 20
         for _ in range(n):
             loss = step()
         lv = float(loss.detach())  # the reference's loss.item() (:67), once at the end of the timed region
