@@ -192,3 +192,4 @@ bool k_linear_attention_backward_mma_applicable(int n_tokens, int dtype);
 int k_linear_attention_backward_mma(const void* qkv, const void* dout, void* dqkv, int batch, int N, void* workspace,
                                     cudaStream_t st);
 int k_pack_conv_weight_pair(const float* w_oihw, int cout, int cin, int ksize, void* fwd, void* dgrad, int dtype, cudaStream_t st);
+int k_pack_dense2x2_weight(const float* w_oihw, int cout, int cin, void* out, int dtype, cudaStream_t st);

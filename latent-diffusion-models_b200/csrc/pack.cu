@@ -106,3 +106,26 @@ int k_add2_f32(const float* a, const float* b, float* dst, int n, cudaStream_t s
   LDM_LAUNCHED("add2_f32");
   return 0;
 }
+
+// Dense form of a pad-1 3x3 filter on 2x2 images: out[(po*cout + co)][(pi*cin + ci)] = w[co][ci][ky][kx] with
+// (ky, kx) = (pi_y - po_y + 1, pi_x - po_x + 1) -- always a valid tap, because two pixels of a 2x2 image are at most one
+// step apart.  Row-major [4*cout][4*cin] = the packed layout of a 1x1 conv with 4*cin inputs.
+template <typename T>
+__global__ void pack_dense2x2_kernel(const float* __restrict__ w, int cout, int cin, T* __restrict__ out) {
+  const int64_t total = (int64_t)16 * cout * cin;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k = (int)(i % (4 * cin)), r = (int)(i / (4 * cin));
+  const int pi = k / cin, ci = k % cin, po = r / cout, co = r % cout;
+  const int ky = (pi >> 1) - (po >> 1) + 1, kx = (pi & 1) - (po & 1) + 1;
+  out[i] = from_float<T>(w[((int64_t)co * cin + ci) * 9 + ky * 3 + kx]);
+}
+int k_pack_dense2x2_weight(const float* w_oihw, int cout, int cin, void* out, int dtype, cudaStream_t st) {
+  const int64_t total = (int64_t)16 * cout * cin;
+  if (total == 0) return 0;
+  const int grid = (int)ceil_div64(total, 256);
+  if (dtype == LDM_DT_BF16) pack_dense2x2_kernel<bf16><<<grid, 256, 0, st>>>(w_oihw, cout, cin, (bf16*)out);
+  else pack_dense2x2_kernel<float><<<grid, 256, 0, st>>>(w_oihw, cout, cin, (float*)out);
+  LDM_LAUNCHED("pack_dense2x2_weight");
+  return 0;
+}

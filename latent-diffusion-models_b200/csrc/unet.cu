@@ -29,6 +29,11 @@ struct ResW {
       p_c2w = -1, p_c2b = -1, p_scw = -1, p_scb = -1;
   void* w1 = nullptr; float* b1 = nullptr;
   void* w2 = nullptr; float* b2 = nullptr;  // conv2 (+K-concatenated shortcut), bias = conv2.bias (+ shortcut.bias)
+  // 2x2 images (the bottleneck): every output pixel sees all four input pixels, so the pad-1 3x3 conv is the dense GEMM
+  // [B, 4*Cin] x [4*Cin, 4*Cout] -- 4/9 of the implicit GEMM's k-blocks (the rest multiply zero padding)
+  bool dense2 = false;
+  void* w1d = nullptr; float* b1d = nullptr;
+  void* w2d = nullptr; float* b2d = nullptr;
   float *g1 = nullptr, *be1 = nullptr, *g2 = nullptr, *be2 = nullptr;
   int tproj_off = -1;  // column offset into the concatenated time projection (-1: no live time embedding)
 };
@@ -146,6 +151,10 @@ void layout_res(Bump& b, ResW& r, int es) {
   b.take(r.b2, r.cout * 4);
   b.take(r.g1, r.cin * 4); b.take(r.be1, r.cin * 4);
   b.take(r.g2, r.cout * 4); b.take(r.be2, r.cout * 4);
+  if (r.dense2) {
+    b.take(r.w1d, (int64_t)16 * r.cout * r.cin * es); b.take(r.b1d, 4 * r.cout * 4);
+    b.take(r.w2d, (int64_t)16 * r.cout * r.cout * es); b.take(r.b2d, 4 * r.cout * 4);
+  }
 }
 void layout_attn(Bump& b, AttnW& a, int es) {
   b.take(a.wqkv, (int64_t)3 * HIDDEN * a.dim * es);
@@ -271,6 +280,12 @@ extern "C" int ldm_unet_create(const ldm_unet_desc* desc, ldm_unet** out) {
   add_res(h, h->bott1, "bottleneck.res1", CB, CB, te);
   add_attn(h, h->bott_attn, "bottleneck.attn", CB, false);
   add_res(h, h->bott2, "bottleneck.res2", CB, CB, te);
+  {
+    const int rb = h->d.image_size >> h->d.n_levels;   // bottleneck resolution
+    const bool dense = rb == 2 && h->d.dtype == LDM_DT_BF16 && h->d.conv_impl == 0 && getenv("LDM_NO_DENSE2X2") == nullptr;
+    h->bott1.dense2 = dense && !h->bott1.has_sc;
+    h->bott2.dense2 = dense && !h->bott2.has_sc;
+  }
   h->dec_res.resize(h->L); h->dec_attn.resize(h->L); h->ups.resize(h->L);
   for (int j = 0; j < h->L; ++j) {
     const int cin = h->dims[h->L - j], cout = h->dims[h->L - j - 1];  // rd[j], rd[j+1]
@@ -338,6 +353,14 @@ int pack_res(ldm_unet* h, ResW& r, const float* const* P, cudaStream_t st) {
   RC(k_add2_f32(P[r.p_c2b], r.has_sc ? P[r.p_scb] : nullptr, r.b2, r.cout, st));
   RC(k_copy_f32(P[r.p_n1w], r.g1, r.cin, st)); RC(k_copy_f32(P[r.p_n1b], r.be1, r.cin, st));
   RC(k_copy_f32(P[r.p_n2w], r.g2, r.cout, st)); RC(k_copy_f32(P[r.p_n2b], r.be2, r.cout, st));
+  if (r.dense2) {
+    RC(k_pack_dense2x2_weight(P[r.p_c1w], r.cout, r.cin, r.w1d, dt, st));
+    RC(k_pack_dense2x2_weight(P[r.p_c2w], r.cout, r.cout, r.w2d, dt, st));
+    for (int q = 0; q < 4; ++q) {
+      RC(k_copy_f32(P[r.p_c1b], r.b1d + q * r.cout, r.cout, st));
+      RC(k_copy_f32(P[r.p_c2b], r.b2d + q * r.cout, r.cout, st));
+    }
+  }
   if (r.tproj_off >= 0) {
     RC(k_transpose_f32(P[r.p_mlp_w], r.cout, h->D, h->tproj_wt, h->tproj_total, r.tproj_off, st));
     RC(k_copy_f32(P[r.p_mlp_w], h->tproj_w + (int64_t)r.tproj_off * h->D, (int64_t)r.cout * h->D, st));
@@ -502,6 +525,13 @@ struct Fwd {
       int rc = conv(s(0), r.cout, r.cout, nullptr, 0, 0, r.w2, r.b2, nullptr, 0, x, ldx, out, ldo, r.cout, R, 3);
       res_mod = 0;
       return rc;
+    }
+    if (r.dense2 && R == 2 && !(use_t && r.tproj_off >= 0) && ldx == r.cin && ldo == r.cout && impl == 0 && dt == LDM_DT_BF16) {
+      // [B][4][C] NHWC == [B][4C]: both convs as 1x1 GEMMs over "images" of one pixel with 4C channels
+      RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
+      RC(conv(s(0), 4 * r.cin, 4 * r.cin, nullptr, 0, 0, r.w1d, r.b1d, nullptr, 0, nullptr, 0, s(1), 4 * r.cout, 4 * r.cout, 1, 1));
+      RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1));
+      return conv(s(0), 4 * r.cout, 4 * r.cout, nullptr, 0, 0, r.w2d, r.b2d, nullptr, 0, x, 4 * ldx, out, 4 * ldo, 4 * r.cout, 1, 1);
     }
     RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
     // the time-embedding projection (h = h + mlp_t(t), :88-93) is a per-sample channel vector: it is added where
