@@ -141,40 +141,4 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 }
 
 
-// ---- coalesced epilogue stores -------------------------------------------------------------------------------
-// The accumulator comes out of TMEM one output ROW per lane.  Storing it that way makes every warp store touch 32
-// different 128-byte lines with 16 bytes each (partial-sector writes, 8 instructions per line).  Instead the warp
-// stages a 32-row x 64-column bf16 slab in shared memory (XOR-swizzled 16-byte chunks, conflict-free both ways) and
-// writes it back with lane = (row, chunk): every store instruction then covers 4 rows x 128 contiguous bytes.
-constexpr int EPI_STAGE_BYTES = 32 * 128 + 32 * 8;  // slab + per-row global byte offsets, per epilogue warp
-
-__device__ __forceinline__ void epi_set_row(uint32_t stg, int lane, long long byte_off_or_neg) {
-  asm volatile("st.shared.b64 [%0], %1;" ::"r"(stg + 4096 + lane * 8), "l"(byte_off_or_neg) : "memory");
-}
-// v[j] = bf16 columns [8j, 8j+8) of this lane's row; col_byte_off = byte offset of the slab's first column in a row
-__device__ __forceinline__ void epi_store_slab(uint32_t stg, int lane, const uint4 (&v)[8], char* ybase, int col_byte_off) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + lane * 128 + ((j ^ (lane & 7)) << 4)), "r"(v[j].x),
-                 "r"(v[j].y), "r"(v[j].z), "r"(v[j].w) : "memory");
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + (lane >> 3), ch = lane & 7;
-    uint4 t;
-    long long off;
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(stg + r * 128 + ((ch ^ (r & 7)) << 4)));
-    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(off) : "r"(stg + 4096 + r * 8));
-    if (off >= 0) *reinterpret_cast<uint4*>(ybase + off + col_byte_off + ch * 16) = t;
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
-  uint4 t;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-  return t;
-}
-
 }  // namespace tc
