@@ -323,6 +323,9 @@ def run_ours(args):
                 model, classes_dev, shape, dev, cfg_scale=cfg, seed=5, sample_offset=offset, return_device=True))
             variants["T1000_cfg0_images_per_sec"] = timed(lambda: diffusion.sample(
                 model, classes_dev, shape, dev, cfg_scale=0, seed=6, sample_offset=offset, return_device=True))
+            # generate_images.py (:18-41): one image per call, batch 1 -- latency, not throughput
+            one = timed(lambda: diffusion.sample(model, classes_dev, (1, 3, 32, 32), dev, cfg_scale=cfg, seed=7, return_device=True))
+            variants["generate_images_batch1_seconds_per_image"] = B * world / one
             # BASELINE config 4: Autoencoder(3,4,3,64,[1,2],2) encode -> 1000-step CFG sampling of the [B,4,16,16] latent
             # with the LatentDiffusionModel's sqrt-linear schedule -> decode (scale 0.18215, 0.00085/0.012)
             torch.manual_seed(43)

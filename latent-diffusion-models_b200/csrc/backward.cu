@@ -121,6 +121,37 @@ __global__ void colsum_kernel(const T* __restrict__ a, int lda, float* __restric
   }
 }
 
+// bf16 variant for channel counts that are multiples of 8: 16-byte loads, a thread owns one 8-channel chunk and walks the
+// rows of its CTA's slab; shared-memory reduction over the row lanes, then one atomic per channel and CTA
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const bf16* __restrict__ a, int lda, float* __restrict__ out, int M, int C, int rows_per_block) {
+  __shared__ float red[256][9];
+  const int cpp = C / 8, ppi = 256 / cpp;
+  const int ci = threadIdx.x % cpp, pl = threadIdx.x / cpp;
+  const int m0 = blockIdx.x * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (pl < ppi) {
+    const bf16* base = a + ci * 8;
+    for (int m = m0 + pl; m < m1; m += ppi) {
+      const uint4 r = *reinterpret_cast<const uint4*>(base + (int64_t)m * lda);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h2[i]);
+        acc[2 * i] += f.x; acc[2 * i + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {   // one thread per channel sums the row lanes
+    float t = 0.f;
+    for (int k = 0; k < ppi; ++k) t += red[k * cpp + (c >> 3)][c & 7];
+    atomicAdd(out + c, t);
+  }
+}
+
 // dgrad filter: out[ci][tap'][co] = w[co][ci][2-kh][2-kw] (3x3) / w[co][ci] (1x1), in the conv kernels' packed layout
 template <typename T>
 __global__ void pack_dgrad_kernel(const float* __restrict__ w, int cout, int cin, int ksize, T* __restrict__ out) {
@@ -807,6 +838,12 @@ int k_conv_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, int 
 int k_colsum(const void* a, int lda, float* out, int M, int C, int dtype, cudaStream_t st) {
   if (M == 0 || C == 0) return 0;
   const int rpb = split_for(M, 64, 4 * 148);
+  if (dtype == LDM_DT_BF16 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0 && lda % 8 == 0 && ((uintptr_t)a & 15) == 0) {
+    const int rpb2 = split_for(M, 256, 2 * 148);
+    colsum_bf16_kernel<<<(M + rpb2 - 1) / rpb2, 256, 0, st>>>((const bf16*)a, lda, out, M, C, rpb2);
+    LDM_LAUNCHED("colsum");
+    return 0;
+  }
   DISPATCH_T(dtype, colsum_kernel<T><<<(M + rpb - 1) / rpb, 256, 0, st>>>((const T*)a, lda, out, M, C, rpb));
   LDM_LAUNCHED("colsum");
   return 0;

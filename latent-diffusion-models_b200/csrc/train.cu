@@ -15,6 +15,7 @@ static int64_t wgrad_nat_bytes(int cin, int cout, int ksize) {   // fp32 [tap][c
   return ksize == 1 ? 0 : ((int64_t)ksize * ksize * cout * cin * 4 + 255) / 256 * 256;
 }
 int64_t ldm_conv2d_wgrad_scratch_bytes(int cin, int cout, int batch, int height, int width, int ksize, int dtype) {
+  if (k_conv_wgrad_mn_applicable(cin, cout, height, width, ksize, dtype)) return wgrad_nat_bytes(cin, cout, ksize) + 256;
   if (k_conv_wgrad_tc_flat_applicable(cin, cout, batch, height, width, ksize, dtype))
     return ((int64_t)batch * height * width * (cin + (int64_t)ksize * ksize * cout) * 2 + 255) / 256 * 256 + 512 +
            wgrad_nat_bytes(cin, cout, ksize);
@@ -33,6 +34,11 @@ int ldm_conv2d_wgrad_tc(const void* x, int ldx, int cin, const void* dy, int ldd
   float* nat = (float*)scratch;                      // first: keeps its alignment whatever follows
   char* rest = (char*)scratch + wgrad_nat_bytes(cin, cout, ksize);
   if (ksize == 1) nat = nullptr;
+  if (k_conv_wgrad_mn_applicable(cin, cout, height, width, ksize, LDM_DT_BF16)) {
+    // MN-major operands straight from the NHWC tensors; the bias gradient is a column sum of dy
+    if (dbias) RC(k_colsum(dy, lddy, dbias, batch * hw, cout, LDM_DT_BF16, st));
+    return k_conv_wgrad_mn(x, ldx, cin, dy, lddy, cout, dw_oihw, nat, batch, height, width, ksize, st);
+  }
   if (k_conv_wgrad_tc_flat_applicable(cin, cout, batch, height, width, ksize, LDM_DT_BF16)) {
     char* xF = rest;
     char* dyF = xF + up((int64_t)batch * hw * cin * 2);

@@ -157,6 +157,146 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, BN);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same GEMM with MN-MAJOR operands, read straight from the NHWC tensors -- no transposed copies at all.
+// UMMA's MN-major SWIZZLE_128B canonical layout is [k rows][64 elements = 128 bytes] per 64-wide block of M (or N), which
+// is exactly what a TMA box {64 channels, pixels...} of an NHWC tensor puts into shared memory: k = pixel, M/N = channel.
+//   A (dy, shifted by the tap): box {64 co, W, HB, NB} at (co0, -dx, h0 - dy, n0): out-of-range rows / columns are the
+//     conv's zero padding (TMA zero fill); the shift is in PIXEL coordinates, so no alignment constraint applies
+//   B (x): boxes {64 ci, W, HB, NB} at (ci0 + 64 j, 0, h0, n0)
+// One k-block = 64 pixels = HB rows of NB images (W * HB * NB = 64); per UMMA (K = 16) the descriptors advance 16 rows =
+// 2048 bytes; LBO = 8192 (next 64-channel block), SBO = 1024 (next 8 pixel rows).
+struct WgMnParams {
+  int cout, cin, taps;
+  int row_tiles, col_tiles;
+  int kb_total, kb_per_split;
+  int kb_per_image;           // > 0: H*W / 64 k-blocks per image;  0: one k-block spans NB whole images
+  int HB, NB;
+  float* dw;                  // [tap][cout][cin] accumulator (== OIHW for 1x1)
+};
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(8192u >> 4) << 16;             // leading byte offset: next 64-element block along M / N
+  d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset: next group of 8 k rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+wgrad_mn_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgMnParams p) {
+  constexpr int STAGES = BN == 256 ? 4 : 6;
+  constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t full_bar = bars, empty_bar = bars + 64, done_bar = bars + 128, tmem_slot = bars + 136;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_dy);
+    prefetch_tmap(&tmap_x);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int rt = blockIdx.x / p.col_tiles, ct = blockIdx.x % p.col_tiles;
+  const int kb0 = blockIdx.y * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+  const int ci0 = ct * BN;
+  int tap_h[2], co_h[2];
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    const int R = 128 * rt + 64 * hf;
+    tap_h[hf] = R / p.cout;
+    co_h[hf] = R - tap_h[hf] * p.cout;
+  }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int dyy[2], dxx[2], coa[2];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const bool live = tap_h[hf] < p.taps;
+        dyy[hf] = (live && p.taps == 9) ? tap_h[hf] / 3 - 1 : 0;
+        dxx[hf] = (live && p.taps == 9) ? tap_h[hf] % 3 - 1 : 0;
+        coa[hf] = live ? co_h[hf] : 0;
+      }
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        int n0, h0;
+        if (p.kb_per_image > 0) { n0 = kb / p.kb_per_image; h0 = (kb - n0 * p.kb_per_image) * p.HB; }
+        else { n0 = kb * p.NB; h0 = 0; }
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+        mbar_expect_tx(full_bar + 8 * stage, STAGE_BYTES);
+        const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+        // A[q] = dy[q - (dyy, dxx)]
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) tma_load_4d(sa + hf * 8192, &tmap_dy, full_bar + 8 * stage, coa[hf], -dxx[hf], h0 - dyy[hf], n0);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) tma_load_4d(sb + j * 8192, &tmap_x, full_bar + 8 * stage, ci0 + 64 * j, 0, h0, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN) | (1u << 15) | (1u << 16);   // A and B MN-major
+      const uint64_t adesc0 = make_sw128_mn_desc(smem_base), bdesc0 = make_sw128_mn_desc(smem_base + A_BYTES);
+      int stage = 0; uint32_t phase = 0;
+      uint32_t accum = 0u;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar + 8 * stage, phase);
+        tc_fence_after();
+        const uint64_t adesc = adesc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
+        const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
+        umma_bf16(tmem_base, adesc, bdesc, idesc, accum);
+#pragma unroll
+        for (int k = 1; k < BLOCK_K / UMMA_K; ++k) umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, 1u);   // +16 rows
+        accum = 1u;
+        umma_commit(empty_bar + 8 * stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int hf = row >> 6;
+    const int tap = tap_h[hf], co = co_h[hf] + (row & 63);
+    const bool valid = tap < p.taps && kb1 > kb0;
+    if (lane == 0) mbar_wait(done_bar, 0);
+    __syncwarp();
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float* drow = p.dw + ((int64_t)tap * p.cout + co) * p.cin + ci0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c0, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + j), "f"(__uint_as_float(r[j])),
+                       "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                       : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
 // NHWC (pixel stride ld) -> channel-major bf16 [B][C][HW]; optionally two more copies shifted by one pixel along W with
 // zero fill (y_r[h][w] = x[h][w-1], y_l[h][w] = x[h][w+1]) and the column sums (bias gradient)
 __global__ void __launch_bounds__(256)
@@ -276,7 +416,22 @@ int wg_init() {
   LDM_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (16384 + 64 * 128) + 2048));
   LDM_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (16384 + 128 * 128) + 2048));
   LDM_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (16384 + 256 * 128) + 2048));
+  LDM_CUDA(cudaFuncSetAttribute(wgrad_mn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (16384 + 64 * 128) + 2048));
+  LDM_CUDA(cudaFuncSetAttribute(wgrad_mn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (16384 + 128 * 128) + 2048));
+  LDM_CUDA(cudaFuncSetAttribute(wgrad_mn_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (16384 + 256 * 128) + 2048));
   g_encode_w = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return 0;
+}
+// NHWC tensor as dims (C, W, H, B); box = {64 channels, W, HB rows, NB images}: one k-block of 64 pixels, MN-major
+int make_nhwc_map(CUtensorMap* map, const void* t, int ld, int C, int B, int H, int W, int HB, int NB) {
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {64u, (cuuint32_t)W, (cuuint32_t)HB, (cuuint32_t)NB};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_w(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(t), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LDM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(wgrad NHWC operand) failed with CUresult %d", (int)r);
   return 0;
 }
 // channel-major tensor [B][C][HW] as dims (HW, C, N); box = {64 pixels, `rows` channels, 1 image}: K-major 128-byte rows
@@ -398,6 +553,64 @@ static int wg_launch(const void* xT, int cin, const void* dyT, const void* dyT_l
     default: wgrad_tc_kernel<64><<<grid, 192, 6 * (16384 + 64 * 128) + 2048, st>>>(mdy, mdl, mdr, mx, p); break;
   }
   LDM_LAUNCHED("conv_wgrad_tc");
+  if (ksize != 1) {
+    wgrad_finish_kernel<<<dim3(cin / 32, cout), 288, 0, st>>>(nat, dw, cout, cin);
+    LDM_LAUNCHED("conv_wgrad_finish");
+  }
+  return 0;
+}
+
+
+// ---- MN-major variant: operands are the NHWC tensors themselves
+bool k_conv_wgrad_mn_applicable(int cin, int cout, int H, int W, int ksize, int dtype) {
+  if (dtype != LDM_DT_BF16 || (ksize != 1 && ksize != 3)) return false;
+  if (cin % 64 != 0 || cout % 64 != 0) return false;
+  if (W < 1 || W > 64 || 64 % W != 0) return false;
+  const int HB = 64 / W < H ? 64 / W : H;
+  if (H % HB != 0 || 64 % (W * HB) != 0) return false;
+  return getenv("LDM_WGRAD_KMAJOR") == nullptr && getenv("LDM_WGRAD_FFMA") == nullptr;
+}
+// x NHWC [B][H][W] (pixel stride ldx), dy NHWC (pixel stride lddy); dw OIHW fp32 ACCUMULATED; nat: [9][cout][cin] fp32 scratch
+// for 3x3 filters (zeroed here)
+int k_conv_wgrad_mn(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, float* nat, int batch,
+                    int H, int W, int ksize, cudaStream_t st) {
+  if (int rc = wg_init()) return rc;
+  LDM_REQUIRE(k_conv_wgrad_mn_applicable(cin, cout, H, W, ksize, LDM_DT_BF16), "conv_wgrad_mn: unsupported shape");
+  LDM_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0,
+              "conv_wgrad_mn: operands must be 16-byte aligned with pixel strides that are multiples of 8");
+  LDM_REQUIRE(ksize == 1 || nat != nullptr, "conv_wgrad_mn: 3x3 filters need the natural-layout scratch");
+  LDM_REQUIRE(((uintptr_t)dw & 15) == 0 && ((uintptr_t)nat & 15) == 0, "conv_wgrad_mn: gradient buffers must be 16-byte aligned");
+  if (batch == 0) return 0;
+  WgMnParams p;
+  p.cout = cout; p.cin = cin; p.taps = ksize * ksize;
+  p.HB = 64 / W < H ? 64 / W : H;
+  p.NB = 64 / (W * p.HB);
+  p.kb_per_image = p.NB == 1 ? (H * W) / 64 : 0;
+  p.kb_total = p.NB == 1 ? batch * p.kb_per_image : (batch + p.NB - 1) / p.NB;
+  p.dw = ksize == 1 ? dw : nat;
+  if (ksize != 1) LDM_CUDA(cudaMemsetAsync(nat, 0, (size_t)9 * cout * cin * sizeof(float), st));
+  int bn = 64;
+  for (int c : {256, 128}) if (cin % c == 0) { bn = c; break; }
+  p.row_tiles = (p.taps * cout + 127) / 128;
+  p.col_tiles = cin / bn;
+  const int tiles = p.row_tiles * p.col_tiles;
+  static const int wg_ctas = getenv("LDM_WGRAD_CTAS") ? atoi(getenv("LDM_WGRAD_CTAS")) : 100;
+  int splits = (wg_ctas + tiles - 1) / tiles;
+  if (p.kb_total / splits > 96) splits = (2 * 148 + tiles - 1) / tiles;
+  if (splits > p.kb_total) splits = p.kb_total;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  CUtensorMap mdy, mx;
+  if (int rc = make_nhwc_map(&mdy, dy, lddy, cout, batch, H, W, p.HB, p.NB)) return rc;
+  if (int rc = make_nhwc_map(&mx, x, ldx, cin, batch, H, W, p.HB, p.NB)) return rc;
+  const dim3 grid(tiles, splits);
+  switch (bn) {
+    case 256: wgrad_mn_kernel<256><<<grid, 192, 4 * (16384 + 256 * 128) + 2048, st>>>(mdy, mx, p); break;
+    case 128: wgrad_mn_kernel<128><<<grid, 192, 6 * (16384 + 128 * 128) + 2048, st>>>(mdy, mx, p); break;
+    default: wgrad_mn_kernel<64><<<grid, 192, 6 * (16384 + 64 * 128) + 2048, st>>>(mdy, mx, p); break;
+  }
+  LDM_LAUNCHED("conv_wgrad_mn");
   if (ksize != 1) {
     wgrad_finish_kernel<<<dim3(cin / 32, cout), 288, 0, st>>>(nat, dw, cout, cin);
     LDM_LAUNCHED("conv_wgrad_finish");

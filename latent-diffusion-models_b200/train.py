@@ -181,8 +181,14 @@ class _ConvT(Function):
         dx = ops.conv2d(dyq, wd, 1, impl=ctx.impl)
         # dW'[(q,co)][ci] = sum_m dyq[m][(q,co)] x[m][ci]  -> back to the IOHW parameter layout
         dwq = _zeros(4 * cout * cin, x.device).view(4 * cout, cin)
-        _lib.check(lib.ldm_conv2d_wgrad(x.data_ptr(), x.stride(2), cin, dyq.data_ptr(), 4 * cout, 4 * cout, dwq.data_ptr(),
-                                        None, B, H, W, 1, ops._dt(x), _st()))
+        nscr = lib.ldm_conv2d_wgrad_scratch_bytes(cin, 4 * cout, B, H, W, 1, ops._dt(x)) if ctx.impl == 0 else 0
+        if nscr > 0:
+            scr = torch.empty(nscr, dtype=torch.uint8, device=x.device)
+            _lib.check(lib.ldm_conv2d_wgrad_tc(x.data_ptr(), x.stride(2), cin, dyq.data_ptr(), 4 * cout, 4 * cout, dwq.data_ptr(),
+                                               None, B, H, W, 1, scr.data_ptr(), _st()))
+        else:
+            _lib.check(lib.ldm_conv2d_wgrad(x.data_ptr(), x.stride(2), cin, dyq.data_ptr(), 4 * cout, 4 * cout, dwq.data_ptr(),
+                                            None, B, H, W, 1, ops._dt(x), _st()))
         dw = dwq.view(2, 2, cout, cin).permute(3, 2, 0, 1).contiguous()                        # layout only
         db = _zeros(cout, x.device)
         _lib.check(lib.ldm_column_sum(dy.data_ptr(), dy.stride(2), db.data_ptr(), B * 4 * H * W, cout, ops._dt(x), _st()))
