@@ -237,8 +237,9 @@ int ldm_nhwc_to_nchw(const void* x, int ldx, float* y, int batch, int channels, 
 /* dW[co][ci][kh][kw] (OIHW, accumulated) = sum_{n,h,w} dy[n,h,w,co] x[n,h+kh-p,w+kw-p,ci]; dbias[co] (accumulated) or NULL */
 int ldm_conv2d_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw_oihw, float* dbias,
                      int batch, int height, int width, int ksize, int dtype, void* stream);
-/* the same on tcgen05 (bf16): the contraction runs over pixels, so channel-major copies of x and dy are made in `scratch`
- * (ldm_conv2d_wgrad_scratch_bytes; 0 = this shape is not supported, use ldm_conv2d_wgrad) */
+/* the same on tcgen05 (bf16): the contraction runs over pixels with MN-major operands read straight from the NHWC tensors;
+ * `scratch` (ldm_conv2d_wgrad_scratch_bytes, 256-byte aligned; 0 = this shape is not supported, use ldm_conv2d_wgrad) holds
+ * the fp32 accumulator of a 3x3 filter in GEMM-natural layout (and the operand copies of the K-major fallback kernel) */
 int64_t ldm_conv2d_wgrad_scratch_bytes(int cin, int cout, int batch, int height, int width, int ksize, int dtype);
 int ldm_conv2d_wgrad_tc(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw_oihw, float* dbias,
                         int batch, int height, int width, int ksize, void* scratch, void* stream);
