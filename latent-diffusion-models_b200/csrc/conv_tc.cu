@@ -70,27 +70,31 @@ struct TcParams {
   int debug;
 };
 
-template <int BLOCK_N>
+// MT: M-tiles (128 output pixels each) a CTA works on at once.  They share every weight k-block: the kernel is bound by
+// L2->SM traffic (profiles/README.md finding 8), and with MT = 2 the weight half of it is fetched once per 256 pixels.
+template <int BLOCK_N, int MT = 1>
 struct TcCfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered accumulator (power of two >= 32)
+  static constexpr int A_BYTES = MT * A_STAGE_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = MT == 1 ? (BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4)) : (BLOCK_N == 64 ? 5 : 4);
+  static constexpr int TMEM_COLS = 2 * MT * BLOCK_N;  // double-buffered accumulators (power of two >= 32)
   // mbarriers + TMEM slot (1 KB), 2 bias slices, 128 x 8 floats for the fused projection's cross-warp sum
   static constexpr int BAR_BYTES = 1024 + 2 * BLOCK_N * 4 + 4096;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MT = 1>
 __global__ void __launch_bounds__(320, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, MT>;
+  static_assert(Cfg::TMEM_COLS <= 512, "accumulators do not fit TMEM");
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B needs 1024-B alignment
   const uint32_t smem_a = smem_base;
-  const uint32_t smem_b = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t smem_b = smem_base + STAGES * Cfg::A_BYTES;
   const uint32_t bars = smem_base + STAGES * Cfg::STAGE_BYTES;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
   const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
@@ -124,7 +128,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   pdl_trigger();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = ((p.num_m_tiles + MT - 1) / MT) * p.num_n_tiles;   // work units: MT stacked M-tiles x one N-tile
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -136,14 +140,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
-        int n0, h0;
-        if (NB == 1) {
-          n0 = mt / tpi;
-          h0 = (mt - n0 * tpi) * HB;
-        } else {
-          n0 = mt * NB;
-          h0 = 0;
+        const int um = tile / num_n_tiles, nt = tile - um * num_n_tiles;
+        int n0[MT], h0[MT];   // tiles past the last one read past the batch: TMA zero fill, never stored
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          const int mt = um * MT + j;
+          if (NB == 1) {
+            n0[j] = mt / tpi;
+            h0[j] = (mt - n0[j] * tpi) * HB;
+          } else {
+            n0[j] = mt * NB;
+            h0[j] = 0;
+          }
         }
         int tap = 0, cb = 0;  // (tap, channel block) of the main source, advanced incrementally
         for (int kb = 0; kb < kb_total; ++kb) {
@@ -152,11 +160,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (kb < kb_main) {
             int dy = 0, dx = 0;
             if (three) { dy = tap / 3 - 1; dx = tap - (dy + 1) * 3 - 1; }
-            tma_load_4d(smem_a + stage * A_STAGE_BYTES, &tmap_a, full_bar + 8 * stage, cb * BLOCK_K, dx, h0 + dy, n0);
+#pragma unroll
+            for (int j = 0; j < MT; ++j)
+              tma_load_4d(smem_a + stage * Cfg::A_BYTES + j * A_STAGE_BYTES, &tmap_a, full_bar + 8 * stage, cb * BLOCK_K, dx,
+                          h0[j] + dy, n0[j]);
             if (++cb == cin_blocks) { cb = 0; ++tap; }
           } else {
-            tma_load_4d(smem_a + stage * A_STAGE_BYTES, &tmap_a2, full_bar + 8 * stage, (kb - kb_main) * BLOCK_K,
-                        0, h0, n0);
+#pragma unroll
+            for (int j = 0; j < MT; ++j)
+              tma_load_4d(smem_a + stage * Cfg::A_BYTES + j * A_STAGE_BYTES, &tmap_a2, full_bar + 8 * stage,
+                          (kb - kb_main) * BLOCK_K, 0, h0[j], n0[j]);
           }
           tma_load_2d(smem_b + stage * Cfg::B_STAGE_BYTES, &tmap_b, full_bar + 8 * stage, kb * BLOCK_K, nt * BLOCK_N);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -178,18 +191,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(tempty_bar + 8 * acc, ((iter >> 1) & 1) ^ 1);
         TC_STAMP(1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        const uint32_t tmem_d = tmem_base + acc * MT * BLOCK_N;
         uint32_t accum = 0u;
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);
           if (kb == 0) TC_STAMP(2);
           tc_fence_after();
-          const uint64_t adesc = adesc0 + (uint64_t)(stage * (A_STAGE_BYTES >> 4));
           const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (Cfg::B_STAGE_BYTES >> 4));
-          // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (addr>>4) field
-          umma_bf16(tmem_d, adesc, bdesc, idesc, accum);
 #pragma unroll
-          for (int k = 1; k < BLOCK_K / UMMA_K; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+          for (int j = 0; j < MT; ++j) {
+            const uint64_t adesc = adesc0 + (uint64_t)(stage * (Cfg::A_BYTES >> 4) + j * (A_STAGE_BYTES >> 4));
+            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (addr>>4) field
+            umma_bf16(tmem_d + j * BLOCK_N, adesc, bdesc, idesc, accum);
+#pragma unroll
+            for (int k = 1; k < BLOCK_K / UMMA_K; ++k) umma_bf16(tmem_d + j * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+          }
           accum = 1u;
           umma_commit(empty_bar + 8 * stage);  // frees the smem stage when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -219,8 +235,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     float* const fin_out = p.fin_out;
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
-      const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
+      const int um = tile / num_n_tiles, nt = tile - um * num_n_tiles;
       const int acc = iter & 1;
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {
+      const int mt = um * MT + sub;
+      if (mt >= p.num_m_tiles) break;   // uniform over the CTA
       const int m = mt * TILE_M + row;
       const bool valid = m < M && !(p.debug & 2);
       const int img = valid ? m / hw : 0;
@@ -249,11 +269,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (warp == 2 && lane == 0) TC_STAMP(4);
-      if (lane == 0) mbar_wait(tfull_bar + 8 * acc, (iter >> 1) & 1);
-      __syncwarp();
+      if (sub == 0) {
+        if (lane == 0) mbar_wait(tfull_bar + 8 * acc, (iter >> 1) & 1);
+        __syncwarp();
+      }
       if (warp == 2 && lane == 0) TC_STAMP(5);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + cw;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * MT + sub) * BLOCK_N + cw;
       float fo[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c0 = 0; c0 < COLS; c0 += 32) {
@@ -334,6 +356,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (u < fin_cout) fin_out[((int64_t)img * fin_cout + u) * hw + pix] = fo[u] + fx[u] + __ldg(p.fin_b + u);
         }
       }
+      }   // sub-tiles
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed(tempty_bar + 8 * acc);
@@ -365,6 +388,8 @@ int tc_init() {
   LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM_BYTES));
   LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));
   LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES));
+  LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, 2>::SMEM_BYTES));
+  LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, 2>::SMEM_BYTES));
   g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   return 0;
 }
@@ -392,13 +417,13 @@ int make_weight_map(CUtensorMap* map, const void* w, int cout, int ktot, int blo
   return 0;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MT>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const TcParams& p,
               cudaStream_t st) {
-  using Cfg = TcCfg<BLOCK_N>;
-  int tiles = p.num_m_tiles * p.num_n_tiles;
+  using Cfg = TcCfg<BLOCK_N, MT>;
+  int tiles = ((p.num_m_tiles + MT - 1) / MT) * p.num_n_tiles;
   int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  LDM_CUDA(ldm_launch_pdl(conv_tc_kernel<BLOCK_N>, dim3(grid), dim3(320), (size_t)Cfg::SMEM_BYTES, st, ma, ma2, mb, p));
+  LDM_CUDA(ldm_launch_pdl(conv_tc_kernel<BLOCK_N, MT>, dim3(grid), dim3(320), (size_t)Cfg::SMEM_BYTES, st, ma, ma2, mb, p));
   LDM_LAUNCHED("conv_tc");
   return 0;
 }
@@ -473,9 +498,12 @@ int k_conv_tc(const ConvArgs& a, cudaStream_t st) {
     ma2 = ma;
   }
   if (int rc = make_weight_map(&mb, a.w, a.cout, ktot, block_n)) return rc;
+  // two M-tiles per CTA when that still leaves every SM at least two work units
+  static const int mt_env = getenv("LDM_TC_MT") ? atoi(getenv("LDM_TC_MT")) : 2;
+  const bool pair = mt_env == 2 && block_n <= 128 && !a.fin_out && (int64_t)(p.num_m_tiles / 2) * p.num_n_tiles >= 2 * g_num_sms;
   switch (block_n) {
-    case 256: return launch_tc<256>(ma, ma2, mb, p, st);
-    case 128: return launch_tc<128>(ma, ma2, mb, p, st);
-    default: return launch_tc<64>(ma, ma2, mb, p, st);
+    case 256: return launch_tc<256, 1>(ma, ma2, mb, p, st);
+    case 128: return pair ? launch_tc<128, 2>(ma, ma2, mb, p, st) : launch_tc<128, 1>(ma, ma2, mb, p, st);
+    default: return pair ? launch_tc<64, 2>(ma, ma2, mb, p, st) : launch_tc<64, 1>(ma, ma2, mb, p, st);
   }
 }
