@@ -209,19 +209,23 @@ def train_leg(args, dev, rank, world, stream):
         torch.cuda.synchronize(dev)
         if world > 1:
             tdist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
         n = 20
-        for _ in range(n):
-            loss = step()
-        lv = float(loss.detach())  # the reference's loss.item() (:67), once at the end of the timed region
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            tdist.barrier()
-    ms = ldist.max_over_ranks(e0.elapsed_time(e1), dev)
+        windows = []
+        for _ in range(3):   # three windows of n steps; the median window is reported
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(n):
+                loss = step()
+            lv = float(loss.detach())  # the reference's loss.item() (:67), once per window
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                tdist.barrier()
+            windows.append(ldist.max_over_ranks(e0.elapsed_time(e1), dev))
+    ms = sorted(windows)[1]
     return {"metric": "cifar10_ddpm_train_images_per_sec", "value": B * world * n / (ms / 1e3), "unit": "images/s",
-            "batch_per_gpu": B, "steps": n, "ms_per_step": ms / n, "loss": lv, "cuda_graphs": graphed,
+            "batch_per_gpu": B, "steps": n, "ms_per_step": ms / n, "ms_per_step_windows": [w / n for w in windows], "loss": lv,
+            "cuda_graphs": graphed,
             "optimizer": "ldm_adam_step over flat buffers (one launch)",
             "note": "q_sample + UNet fwd + MSE + bwd (tcgen05 fwd / dgrad / wgrad) + flat-gradient all-reduce + Adam; "
                     "4.536 GFLOP/image"}
