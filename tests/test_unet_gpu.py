@@ -106,6 +106,33 @@ def test_two_level_variant_and_batch_sizes():
             assert rel_l2(got, want) < BAR[dtype], (dtype, B)
 
 
+def test_64x64_images_forward_and_gradients():
+    """A size the reference config does not use: 64x64 (4x4 bottleneck, 4096-token LinearAttention at level 0)."""
+    import oracle
+    from oracle import unet_oracle as U
+    g = torch.Generator().manual_seed(64)
+    B = 2
+    x = torch.randn(B, 3, 64, 64, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    y = torch.randint(0, 10, (B,), generator=g)
+    noise = torch.randn(B, 3, 64, 64, generator=g)
+    for dtype in ("fp32", "bf16"):
+        m, sd = make_model(dtype, seed=6)
+        with torch.no_grad():
+            want = U.unet_forward(sd, x, t, y)
+            got = m(x.to(dev()), t.to(dev()), y.to(dev()))
+        assert rel_l2(got, want) < BAR[dtype], dtype
+    # gradients (bf16 path, the tensor-core weight-gradient kernels at W = 64 ... 4)
+    prm = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    torch.nn.functional.mse_loss(noise, U.unet_forward(prm, x, t, y)).backward()
+    m.zero_grad(set_to_none=True)
+    torch.nn.functional.mse_loss(noise.to(dev()), m(x.to(dev()), t.to(dev()), y.to(dev()))).backward()
+    for name in ("initial_conv.weight", "encoder.downs.0.0.block1.conv2d.weight", "encoder.downs.3.0.block2.conv2d.weight",
+                 "bottleneck.res1.block1.conv2d.weight", "decoder.ups.3.0.block1.conv2d.weight", "final_conv.1.weight"):
+        got = dict(m.named_parameters())[name].grad.cpu()
+        assert rel_l2(got, prm[name].grad) < 8e-2, name
+
+
 def test_rejects_bad_shapes():
     import ldm_b200
     from ldm_b200 import _lib
