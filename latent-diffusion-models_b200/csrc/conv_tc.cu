@@ -222,6 +222,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int half = (warp - 2) >> 2;         // column half of the tile
     constexpr int COLS = BLOCK_N / 2;         // columns per warp
     const int row = quarter * 32 + lane;
+    const bool keep_l2 = (p.debug & 8) == 0;      // L2 evict_last on the output (2688 -> 2678 us per timestep); debug bit 3 = off
+    const uint64_t l2pol = l2_evict_last_policy();
     const int et = threadIdx.x - 64;          // 0..255 among the epilogue threads
     // loop-invariant parameters in registers (no constant-bank traffic per tile)
     const int num_n_tiles = p.num_n_tiles, M = p.M, H = p.H, W = p.W, hw = p.H * p.W, up2 = p.up2;
@@ -319,7 +321,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               float t8[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) t8[u] = v[j + u];
-              store_chunk(yrow + c0 + j, t8);
+              if (keep_l2) store_chunk_keep(yrow + c0 + j, t8, l2pol); else store_chunk(yrow + c0 + j, t8);
             }
           }
           if (fin_out) {
