@@ -196,3 +196,4 @@ int k_pack_dense2x2_weight(const float* w_oihw, int cout, int cin, void* out, in
 bool k_conv_wgrad_mn_applicable(int cin, int cout, int H, int W, int ksize, int dtype);
 int k_conv_wgrad_mn(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, float* nat, int batch,
                     int H, int W, int ksize, cudaStream_t st);
+int k_pack_center_tap_weight(const float* w_oihw, int cout, int cin, void* out, int dtype, cudaStream_t st);

@@ -129,3 +129,19 @@ int k_pack_dense2x2_weight(const float* w_oihw, int cout, int cin, void* out, in
   LDM_LAUNCHED("pack_dense2x2_weight");
   return 0;
 }
+
+// centre tap of a 3x3 filter as a 1x1 filter: out[co][ci] = w[co][ci][1][1]
+template <typename T>
+__global__ void pack_center_tap_kernel(const float* __restrict__ w, int64_t total, T* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) out[i] = from_float<T>(w[i * 9 + 4]);
+}
+int k_pack_center_tap_weight(const float* w_oihw, int cout, int cin, void* out, int dtype, cudaStream_t st) {
+  const int64_t total = (int64_t)cout * cin;
+  if (total == 0) return 0;
+  const int grid = (int)ceil_div64(total, 256);
+  if (dtype == LDM_DT_BF16) pack_center_tap_kernel<bf16><<<grid, 256, 0, st>>>(w_oihw, total, (bf16*)out);
+  else pack_center_tap_kernel<float><<<grid, 256, 0, st>>>(w_oihw, total, (float*)out);
+  LDM_LAUNCHED("pack_center_tap_weight");
+  return 0;
+}

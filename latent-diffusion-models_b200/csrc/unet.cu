@@ -34,6 +34,9 @@ struct ResW {
   bool dense2 = false;
   void* w1d = nullptr; float* b1d = nullptr;
   void* w2d = nullptr; float* b2d = nullptr;
+  // 1x1 images (the bottleneck of a 16x16 latent): only the centre tap of a pad-1 3x3 filter ever meets data
+  bool dense1 = false;
+  void* w1c = nullptr; void* w2c = nullptr;
   float *g1 = nullptr, *be1 = nullptr, *g2 = nullptr, *be2 = nullptr;
   int tproj_off = -1;  // column offset into the concatenated time projection (-1: no live time embedding)
 };
@@ -154,6 +157,10 @@ void layout_res(Bump& b, ResW& r, int es) {
   if (r.dense2) {
     b.take(r.w1d, (int64_t)16 * r.cout * r.cin * es); b.take(r.b1d, 4 * r.cout * 4);
     b.take(r.w2d, (int64_t)16 * r.cout * r.cout * es); b.take(r.b2d, 4 * r.cout * 4);
+  }
+  if (r.dense1) {
+    b.take(r.w1c, (int64_t)r.cout * r.cin * es);
+    b.take(r.w2c, (int64_t)r.cout * r.cout * es);
   }
 }
 void layout_attn(Bump& b, AttnW& a, int es) {
@@ -285,6 +292,9 @@ extern "C" int ldm_unet_create(const ldm_unet_desc* desc, ldm_unet** out) {
     const bool dense = rb == 2 && h->d.dtype == LDM_DT_BF16 && h->d.conv_impl == 0 && getenv("LDM_NO_DENSE2X2") == nullptr;
     h->bott1.dense2 = dense && !h->bott1.has_sc;
     h->bott2.dense2 = dense && !h->bott2.has_sc;
+    const bool centre = rb == 1 && h->d.dtype == LDM_DT_BF16 && h->d.conv_impl == 0 && getenv("LDM_NO_DENSE2X2") == nullptr;
+    h->bott1.dense1 = centre && !h->bott1.has_sc;
+    h->bott2.dense1 = centre && !h->bott2.has_sc;
   }
   h->dec_res.resize(h->L); h->dec_attn.resize(h->L); h->ups.resize(h->L);
   for (int j = 0; j < h->L; ++j) {
@@ -360,6 +370,10 @@ int pack_res(ldm_unet* h, ResW& r, const float* const* P, cudaStream_t st) {
       RC(k_copy_f32(P[r.p_c1b], r.b1d + q * r.cout, r.cout, st));
       RC(k_copy_f32(P[r.p_c2b], r.b2d + q * r.cout, r.cout, st));
     }
+  }
+  if (r.dense1) {
+    RC(k_pack_center_tap_weight(P[r.p_c1w], r.cout, r.cin, r.w1c, dt, st));
+    RC(k_pack_center_tap_weight(P[r.p_c2w], r.cout, r.cout, r.w2c, dt, st));
   }
   if (r.tproj_off >= 0) {
     RC(k_transpose_f32(P[r.p_mlp_w], r.cout, h->D, h->tproj_wt, h->tproj_total, r.tproj_off, st));
@@ -532,6 +546,12 @@ struct Fwd {
       RC(conv(s(0), 4 * r.cin, 4 * r.cin, nullptr, 0, 0, r.w1d, r.b1d, nullptr, 0, nullptr, 0, s(1), 4 * r.cout, 4 * r.cout, 1, 1));
       RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1));
       return conv(s(0), 4 * r.cout, 4 * r.cout, nullptr, 0, 0, r.w2d, r.b2d, nullptr, 0, x, 4 * ldx, out, 4 * ldo, 4 * r.cout, 1, 1);
+    }
+    if (r.dense1 && R == 1 && !(use_t && r.tproj_off >= 0) && impl == 0 && dt == LDM_DT_BF16) {
+      RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
+      RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1c, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, 1, 1));
+      RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1));
+      return conv(s(0), r.cout, r.cout, nullptr, 0, 0, r.w2c, r.b2, nullptr, 0, x, ldx, out, ldo, r.cout, 1, 1);
     }
     RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
     // the time-embedding projection (h = h + mlp_t(t), :88-93) is a per-sample channel vector: it is added where
