@@ -277,8 +277,10 @@ int ldm_attention_backward(const void* qkv, const void* dout, void* dqkv, int ba
 /* initial 3x3 conv on the fp32 NCHW input (src/UNet.py:331) and its weight gradient; w_scratch: 9*cin*cout floats */
 int ldm_initial_conv(const float* x_nchw, const float* w_oihw, const float* bias, void* y, int batch, int cin, int cout,
                      int height, int width, int dtype, float* w_scratch, void* stream);
+/* scratch (ldm_initial_conv_wgrad_scratch_bytes, or NULL): per-CTA partial rows summed by a second kernel instead of atomics */
+int64_t ldm_initial_conv_wgrad_scratch_bytes(int batch, int cin, int cout, int height, int width);
 int ldm_initial_conv_wgrad(const float* x_nchw, const void* dy, float* dw_oihw, float* dbias, int batch, int cin, int cout,
-                           int height, int width, int dtype, void* stream);
+                           int height, int width, int dtype, void* scratch, void* stream);
 /* final 1x1 conv to fp32 NCHW (src/UNet.py:347) and its backward (dw/db accumulated, dx overwritten) */
 int ldm_final_conv(const void* x, int ldx, const float* w, const float* bias, float* y_nchw, int batch, int cin, int cout,
                    int hw, int dtype, void* stream);

@@ -100,7 +100,8 @@ SIGNATURES = {
     "ldm_linear_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "ldm_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_initial_conv": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
-    "ldm_initial_conv_wgrad": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_initial_conv_wgrad_scratch_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ldm_initial_conv_wgrad": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "ldm_final_conv": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_final_conv_backward": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_time_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),

@@ -616,7 +616,7 @@ attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, T* __rest
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256)
 initial_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, float* __restrict__ dbias,
-                     int B, int cout, int H, int W, int m_per_split) {
+                     float* __restrict__ part, int B, int cout, int H, int W, int m_per_split) {
   __shared__ float red[4][64];
   const int M = B * H * W;
   const int m0 = blockIdx.x * m_per_split, m1 = min(M, m0 + m_per_split);
@@ -646,11 +646,35 @@ initial_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, floa
       __syncthreads();
       if (pl == 0) {
         const float t = red[0][cl] + red[1][cl] + red[2][cl] + red[3][cl];
-        if (j < 9 * CIN) atomicAdd(dw + ((int64_t)(c0 + cl) * CIN + (j % CIN)) * 9 + (j / CIN), t);
+        const int64_t widx = ((int64_t)(c0 + cl) * CIN + (j % CIN)) * 9 + (j / CIN);
+        if (part) {   // this CTA's row of partials [dW (OIHW order) | db]; summed by rows_sum_f32_kernel: a thousand CTAs
+          //            doing atomics on the same 1.8 k floats serialise in L2
+          float* row = part + (int64_t)blockIdx.x * ((int64_t)cout * CIN * 9 + cout);
+          if (j < 9 * CIN) row[widx] = t; else row[(int64_t)cout * CIN * 9 + c0 + cl] = t;
+        } else if (j < 9 * CIN) atomicAdd(dw + widx, t);
         else if (dbias) atomicAdd(dbias + c0 + cl, t);
       }
       __syncthreads();
     }
+  }
+}
+
+// out0[c] += sum_r part[r][c] (c < n0), out1[c - n0] += ... (c >= n0).  grid (ceil(cols / 32)), 256 threads = 8 row lanes x
+// 32 columns, fixed summation order
+__global__ void __launch_bounds__(256)
+rows_sum_f32_kernel(const float* __restrict__ part, int rows, int cols, float* __restrict__ out0, int n0, float* __restrict__ out1) {
+  __shared__ float red[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  float a = 0.f;
+  if (col < cols)
+    for (int r = rl; r < rows; r += 8) a += part[(int64_t)r * cols + col];
+  red[rl][threadIdx.x & 31] = a;
+  __syncthreads();
+  if (rl == 0 && col < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
+    if (col < n0) out0[col] += t; else if (out1) out1[col - n0] += t;
   }
 }
 
@@ -935,15 +959,26 @@ int k_attention_backward(const void* qkv, const void* dout, void* dqkv, int batc
   return 0;
 }
 
+static int initial_wgrad_grid(int batch, int H, int W, int* mps_out) {
+  const int M = batch * H * W;
+  const int mps = split_for(M, 64, 8 * 148);
+  if (mps_out) *mps_out = mps;
+  return (M + mps - 1) / mps;
+}
+int64_t k_initial_conv_wgrad_scratch_bytes(int batch, int cin, int cout, int H, int W) {
+  if (batch * H * W == 0) return 0;
+  return (int64_t)initial_wgrad_grid(batch, H, W, nullptr) * ((int64_t)cout * cin * 9 + cout) * sizeof(float);
+}
 int k_initial_conv_wgrad(const float* x, const void* dy, float* dw, float* dbias, int batch, int cin, int cout, int H, int W,
-                         int dtype, cudaStream_t st) {
+                         int dtype, void* scratch, cudaStream_t st) {
   LDM_REQUIRE(cout % 64 == 0, "initial_conv_wgrad: channels must be a multiple of 64");
   const int M = batch * H * W;
   if (M == 0) return 0;
   LDM_REQUIRE(cin >= 1 && cin <= 4, "initial_conv_wgrad: in_channels %d not in [1,4]", cin);
-  const int mps = split_for(M, 64, 8 * 148);
-  const int grid = (M + mps - 1) / mps;
-#define IW_GO(C) DISPATCH_T(dtype, initial_wgrad_kernel<T, C><<<grid, 256, 0, st>>>(x, (const T*)dy, dw, dbias, batch, cout, H, W, mps))
+  int mps = 0;
+  const int grid = initial_wgrad_grid(batch, H, W, &mps);
+  float* part = (float*)scratch;
+#define IW_GO(C) DISPATCH_T(dtype, initial_wgrad_kernel<T, C><<<grid, 256, 0, st>>>(x, (const T*)dy, dw, dbias, part, batch, cout, H, W, mps))
   switch (cin) {
     case 1: IW_GO(1); break;
     case 2: IW_GO(2); break;
@@ -952,6 +987,11 @@ int k_initial_conv_wgrad(const float* x, const void* dy, float* dw, float* dbias
   }
 #undef IW_GO
   LDM_LAUNCHED("initial_conv_wgrad");
+  if (part) {
+    const int cols = cout * cin * 9 + cout;
+    rows_sum_f32_kernel<<<(cols + 31) / 32, 256, 0, st>>>(part, grid, cols, dw, cout * cin * 9, dbias);
+    LDM_LAUNCHED("rows_sum_f32");
+  }
   return 0;
 }
 

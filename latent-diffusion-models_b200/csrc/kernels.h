@@ -138,8 +138,9 @@ int k_maxpool2_backward(const void* x, int ldx, const void* dy, int lddy, void* 
 int k_unshuffle2(const void* dy, int lddy, void* out, int batch, int H, int W, int C, int dtype, cudaStream_t st);
 int k_linear_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int N, int dtype, cudaStream_t st);
 int k_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int N, int dtype, cudaStream_t st);
+int64_t k_initial_conv_wgrad_scratch_bytes(int batch, int cin, int cout, int H, int W);
 int k_initial_conv_wgrad(const float* x, const void* dy, float* dw, float* dbias, int batch, int cin, int cout, int H, int W,
-                         int dtype, cudaStream_t st);
+                         int dtype, void* scratch, cudaStream_t st);
 int k_final_conv_backward(const float* dout, const void* x, int ldx, const float* w, void* dx, float* dw, float* db, int batch,
                           int cin, int cout, int hw, int dtype, cudaStream_t st);
 int k_gemm_f32(const float* a, int64_t a_rs, int64_t a_cs, const float* b, int64_t b_rs, int64_t b_cs, float* c, int64_t c_rs,

@@ -117,10 +117,13 @@ int ldm_initial_conv(const float* x_nchw, const float* w_oihw, const float* bias
   RC(k_pack_initial_weight(w_oihw, cout, cin, w_scratch, (cudaStream_t)stream));
   return k_initial_conv(x_nchw, batch, w_scratch, bias, y, batch, cin, cout, height, width, dtype, (cudaStream_t)stream);
 }
+int64_t ldm_initial_conv_wgrad_scratch_bytes(int batch, int cin, int cout, int height, int width) {
+  return k_initial_conv_wgrad_scratch_bytes(batch, cin, cout, height, width);
+}
 int ldm_initial_conv_wgrad(const float* x_nchw, const void* dy, float* dw_oihw, float* dbias, int batch, int cin, int cout, int height,
-                           int width, int dtype, void* stream) {
+                           int width, int dtype, void* scratch, void* stream) {
   LDM_REQUIRE(x_nchw && dy && dw_oihw, "ldm_initial_conv_wgrad: null argument");
-  return k_initial_conv_wgrad(x_nchw, dy, dw_oihw, dbias, batch, cin, cout, height, width, dtype, (cudaStream_t)stream);
+  return k_initial_conv_wgrad(x_nchw, dy, dw_oihw, dbias, batch, cin, cout, height, width, dtype, scratch, (cudaStream_t)stream);
 }
 int ldm_final_conv(const void* x, int ldx, const float* w, const float* bias, float* y_nchw, int batch, int cin, int cout, int hw,
                    int dtype, void* stream) {

@@ -250,8 +250,10 @@ class _InitialConv(Function):
         cout = w.shape[0]
         dw = _zeros(w.numel(), w.device).view_as(w)
         db = _zeros(cout, x.device)
-        _lib.check(_lb().ldm_initial_conv_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), B, Cin, cout, H, W,
-                                                ops._dt(dy), _st()))
+        lib = _lb()
+        scr = torch.empty(lib.ldm_initial_conv_wgrad_scratch_bytes(B, Cin, cout, H, W), dtype=torch.uint8, device=x.device)
+        _lib.check(lib.ldm_initial_conv_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), B, Cin, cout, H, W,
+                                              ops._dt(dy), scr.data_ptr(), _st()))
         return None, dw, db, None     # the noised image x_t needs no gradient (src/DDPM.py:133-149)
 
 
