@@ -35,9 +35,11 @@ int ldm_conv2d_wgrad_tc(const void* x, int ldx, int cin, const void* dy, int ldd
   char* rest = (char*)scratch + wgrad_nat_bytes(cin, cout, ksize);
   if (ksize == 1) nat = nullptr;
   if (k_conv_wgrad_mn_applicable(cin, cout, height, width, ksize, LDM_DT_BF16)) {
-    // MN-major operands straight from the NHWC tensors; the bias gradient is a column sum of dy
-    if (dbias) RC(k_colsum(dy, lddy, dbias, batch * hw, cout, LDM_DT_BF16, st));
-    return k_conv_wgrad_mn(x, ldx, cin, dy, lddy, cout, dw_oihw, nat, batch, height, width, ksize, st);
+    // MN-major operands straight from the NHWC tensors; the bias gradient (column sums of dy) rides along as one more
+    // narrow MMA against a block of ones (LDM_WGRAD_COLSUM=1: the separate column-sum kernel instead)
+    static const bool sep = getenv("LDM_WGRAD_COLSUM") != nullptr;
+    if (dbias && sep) RC(k_colsum(dy, lddy, dbias, batch * hw, cout, LDM_DT_BF16, st));
+    return k_conv_wgrad_mn(x, ldx, cin, dy, lddy, cout, dw_oihw, sep ? nullptr : dbias, nat, batch, height, width, ksize, st);
   }
   if (k_conv_wgrad_tc_flat_applicable(cin, cout, batch, height, width, ksize, LDM_DT_BF16)) {
     char* xF = rest;

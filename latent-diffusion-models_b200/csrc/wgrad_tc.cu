@@ -173,6 +173,7 @@ struct WgMnParams {
   int kb_per_image;           // > 0: H*W / 64 k-blocks per image;  0: one k-block spans NB whole images
   int HB, NB;
   float* dw;                  // [tap][cout][cin] accumulator (== OIHW for 1x1)
+  float* dbias;               // bias gradient (accumulated) or null: column sums of dy = A^T * ones, an extra N = 16 MMA
 };
 __device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -193,6 +194,8 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
   const uint32_t full_bar = bars, empty_bar = bars + 64, done_bar = bars + 128, tmem_slot = bars + 136;
+  const uint32_t ones = bars + 1024;   // 16 k rows x 128 bytes of bf16 1.0: the B operand of the bias-gradient MMA
+  constexpr int TMEM_COLS = BN == 64 ? 128 : (BN == 128 ? 256 : 512);   // accumulator + 16 columns of row sums
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -203,7 +206,10 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  for (int i = threadIdx.x; i < 512; i += blockDim.x)
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ones + 4 * i), "r"(0x3F803F80u) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA's async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -219,6 +225,9 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     tap_h[hf] = R / p.cout;
     co_h[hf] = R - tap_h[hf] * p.cout;
   }
+  // the unshifted (centre) tap's rows of dy sum to the bias gradient; one column tile per row tile adds them
+  const int centre = p.taps == 9 ? 4 : 0;
+  const bool bias_tile = p.dbias != nullptr && ct == 0 && (tap_h[0] == centre || tap_h[1] == centre);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -249,7 +258,9 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN) | (1u << 15) | (1u << 16);   // A and B MN-major
+      constexpr uint32_t idesc1 = make_idesc(16) | (1u << 15) | (1u << 16);
       const uint64_t adesc0 = make_sw128_mn_desc(smem_base), bdesc0 = make_sw128_mn_desc(smem_base + A_BYTES);
+      const uint64_t odesc = make_sw128_mn_desc(ones);
       int stage = 0; uint32_t phase = 0;
       uint32_t accum = 0u;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -260,6 +271,10 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
         umma_bf16(tmem_base, adesc, bdesc, idesc, accum);
 #pragma unroll
         for (int k = 1; k < BLOCK_K / UMMA_K; ++k) umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, 1u);   // +16 rows
+        if (bias_tile) {
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_bf16(tmem_base + BN, adesc + 128 * k, odesc, idesc1, k == 0 ? accum : 1u);
+        }
         accum = 1u;
         umma_commit(empty_bar + 8 * stage);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -276,6 +291,12 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     __syncwarp();
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    if (bias_tile && valid && tap == centre) {
+      uint32_t r[32];
+      tmem_ld32(taddr + BN, r);      // 16 identical columns of row sums (the rest of the 32 is unused TMEM)
+      tmem_ld_wait();
+      atomicAdd(p.dbias + co, __uint_as_float(r[0]));
+    }
     float* drow = p.dw + ((int64_t)tap * p.cout + co) * p.cin + ci0;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -294,7 +315,7 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // NHWC (pixel stride ld) -> channel-major bf16 [B][C][HW]; optionally two more copies shifted by one pixel along W with
@@ -416,9 +437,9 @@ int wg_init() {
   LDM_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (16384 + 64 * 128) + 2048));
   LDM_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (16384 + 128 * 128) + 2048));
   LDM_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (16384 + 256 * 128) + 2048));
-  LDM_CUDA(cudaFuncSetAttribute(wgrad_mn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (16384 + 64 * 128) + 2048));
-  LDM_CUDA(cudaFuncSetAttribute(wgrad_mn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (16384 + 128 * 128) + 2048));
-  LDM_CUDA(cudaFuncSetAttribute(wgrad_mn_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (16384 + 256 * 128) + 2048));
+  LDM_CUDA(cudaFuncSetAttribute(wgrad_mn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (16384 + 64 * 128) + 4096 + 1024));
+  LDM_CUDA(cudaFuncSetAttribute(wgrad_mn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (16384 + 128 * 128) + 4096 + 1024));
+  LDM_CUDA(cudaFuncSetAttribute(wgrad_mn_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (16384 + 256 * 128) + 4096 + 1024));
   g_encode_w = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   return 0;
 }
@@ -572,8 +593,8 @@ bool k_conv_wgrad_mn_applicable(int cin, int cout, int H, int W, int ksize, int 
 }
 // x NHWC [B][H][W] (pixel stride ldx), dy NHWC (pixel stride lddy); dw OIHW fp32 ACCUMULATED; nat: [9][cout][cin] fp32 scratch
 // for 3x3 filters (zeroed here)
-int k_conv_wgrad_mn(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, float* nat, int batch,
-                    int H, int W, int ksize, cudaStream_t st) {
+int k_conv_wgrad_mn(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, float* dbias, float* nat,
+                    int batch, int H, int W, int ksize, cudaStream_t st) {
   if (int rc = wg_init()) return rc;
   LDM_REQUIRE(k_conv_wgrad_mn_applicable(cin, cout, H, W, ksize, LDM_DT_BF16), "conv_wgrad_mn: unsupported shape");
   LDM_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0,
@@ -588,6 +609,7 @@ int k_conv_wgrad_mn(const void* x, int ldx, int cin, const void* dy, int lddy, i
   p.kb_per_image = p.NB == 1 ? (H * W) / 64 : 0;
   p.kb_total = p.NB == 1 ? batch * p.kb_per_image : (batch + p.NB - 1) / p.NB;
   p.dw = ksize == 1 ? dw : nat;
+  p.dbias = dbias;
   if (ksize != 1) LDM_CUDA(cudaMemsetAsync(nat, 0, (size_t)9 * cout * cin * sizeof(float), st));
   int bn = 64;
   for (int c : {256, 128}) if (cin % c == 0) { bn = c; break; }
@@ -606,9 +628,9 @@ int k_conv_wgrad_mn(const void* x, int ldx, int cin, const void* dy, int lddy, i
   if (int rc = make_nhwc_map(&mx, x, ldx, cin, batch, H, W, p.HB, p.NB)) return rc;
   const dim3 grid(tiles, splits);
   switch (bn) {
-    case 256: wgrad_mn_kernel<256><<<grid, 192, 4 * (16384 + 256 * 128) + 2048, st>>>(mdy, mx, p); break;
-    case 128: wgrad_mn_kernel<128><<<grid, 192, 6 * (16384 + 128 * 128) + 2048, st>>>(mdy, mx, p); break;
-    default: wgrad_mn_kernel<64><<<grid, 192, 6 * (16384 + 64 * 128) + 2048, st>>>(mdy, mx, p); break;
+    case 256: wgrad_mn_kernel<256><<<grid, 192, 4 * (16384 + 256 * 128) + 4096 + 1024, st>>>(mdy, mx, p); break;
+    case 128: wgrad_mn_kernel<128><<<grid, 192, 6 * (16384 + 128 * 128) + 4096 + 1024, st>>>(mdy, mx, p); break;
+    default: wgrad_mn_kernel<64><<<grid, 192, 6 * (16384 + 64 * 128) + 4096 + 1024, st>>>(mdy, mx, p); break;
   }
   LDM_LAUNCHED("conv_wgrad_mn");
   if (ksize != 1) {
