@@ -58,7 +58,6 @@ class FlatAdam:
                 p.data = view
                 self.grad_views.append(self.flat_grad[int(o):int(o) + k].view_as(p))
         self.step_count = 0
-        self._dead_zeroed = False
 
     # torch.optim.Optimizer surface used by the reference (src/DiffusionModelTrainer.py:55-63)
     def zero_grad(self, set_to_none: bool = True) -> None:
@@ -141,10 +140,8 @@ def val_step(model, diffusion, data: torch.Tensor, targets: Optional[torch.Tenso
     if cfg_scale > 0 and targets is not None:
         both = model._forward_nograd(torch.cat((xt, xt)), torch.cat((t, t)), targets, y_rows=B)
         eps = torch.lerp(both[B:], both[:B], float(cfg_scale))
-    else:
+    else:   # cfg_scale == 0, or no labels (then the reference's two passes coincide and its lerp is the identity)
         eps = model._forward_nograd(xt, t, targets)
-        if cfg_scale > 0:   # reference: both passes unconditional, the lerp is the identity
-            eps = torch.lerp(eps, eps, float(cfg_scale))
     return mse_loss(noise, eps)
 
 
