@@ -277,7 +277,8 @@ int ldm_attention_backward(const void* qkv, const void* dout, void* dqkv, int ba
 /* initial 3x3 conv on the fp32 NCHW input (src/UNet.py:331) and its weight gradient; w_scratch: 9*cin*cout floats */
 int ldm_initial_conv(const float* x_nchw, const float* w_oihw, const float* bias, void* y, int batch, int cin, int cout,
                      int height, int width, int dtype, float* w_scratch, void* stream);
-/* scratch (ldm_initial_conv_wgrad_scratch_bytes, or NULL): per-CTA partial rows summed by a second kernel instead of atomics */
+/* scratch (ldm_initial_conv_wgrad_scratch_bytes, 256-byte aligned, or NULL): bf16 -> 3x3 patches of the image as a 64-channel
+ * tensor + the tcgen05 weight-gradient GEMM; fp32 -> per-CTA partial rows summed by a second kernel; NULL -> atomics */
 int64_t ldm_initial_conv_wgrad_scratch_bytes(int batch, int cin, int cout, int height, int width);
 int ldm_initial_conv_wgrad(const float* x_nchw, const void* dy, float* dw_oihw, float* dbias, int batch, int cin, int cout,
                            int height, int width, int dtype, void* scratch, void* stream);

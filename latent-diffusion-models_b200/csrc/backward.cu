@@ -959,6 +959,39 @@ int k_attention_backward(const void* qkv, const void* dout, void* dqkv, int batc
   return 0;
 }
 
+// ---- initial-conv weight gradient on the tensor cores: 3x3 patches of the fp32 NCHW image as a 64-channel bf16 NHWC
+// tensor (channel j = ci*9 + tap, the OIHW order; zero beyond 9*CIN), then the 1x1 weight-gradient GEMM
+template <int CIN>
+__global__ void __launch_bounds__(256)
+im2col3x3_small_kernel(const float* __restrict__ x, bf16* __restrict__ patches, int H, int W, int64_t total_chunks) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (pixel, 8-channel chunk)
+  if (i >= total_chunks) return;
+  const int chunk = (int)(i & 7);
+  const int64_t m = i >> 3;
+  const int w_ = (int)(m % W);
+  const int64_t r_ = m / W;
+  const int h_ = (int)(r_ % H);
+  const int64_t n_ = r_ / H;
+  float v[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int j = chunk * 8 + u;
+    float val = 0.f;
+    if (j < 9 * CIN) {
+      const int ci = j / 9, tap = j - ci * 9;
+      const int hh = h_ + tap / 3 - 1, ww = w_ + tap % 3 - 1;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(x + ((n_ * CIN + ci) * H + hh) * W + ww);
+    }
+    v[u] = val;
+  }
+  store_chunk(patches + m * 64 + chunk * 8, v);
+}
+__global__ void add_cols_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int rows, int cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  dst[i] += src[(i / cols) * ld_src + i % cols];
+}
+
 static int initial_wgrad_grid(int batch, int H, int W, int* mps_out) {
   const int M = batch * H * W;
   const int mps = split_for(M, 64, 8 * 148);
@@ -967,7 +1000,9 @@ static int initial_wgrad_grid(int batch, int H, int W, int* mps_out) {
 }
 int64_t k_initial_conv_wgrad_scratch_bytes(int batch, int cin, int cout, int H, int W) {
   if (batch * H * W == 0) return 0;
-  return (int64_t)initial_wgrad_grid(batch, H, W, nullptr) * ((int64_t)cout * cin * 9 + cout) * sizeof(float);
+  const int64_t rows = (int64_t)initial_wgrad_grid(batch, H, W, nullptr) * ((int64_t)cout * cin * 9 + cout) * sizeof(float);
+  const int64_t tc = (int64_t)batch * H * W * 64 * 2 + (int64_t)cout * 64 * 4 + 512;   // patches + [cout][64] accumulator
+  return rows > tc ? rows : tc;
 }
 int k_initial_conv_wgrad(const float* x, const void* dy, float* dw, float* dbias, int batch, int cin, int cout, int H, int W,
                          int dtype, void* scratch, cudaStream_t st) {
@@ -975,6 +1010,25 @@ int k_initial_conv_wgrad(const float* x, const void* dy, float* dw, float* dbias
   const int M = batch * H * W;
   if (M == 0) return 0;
   LDM_REQUIRE(cin >= 1 && cin <= 4, "initial_conv_wgrad: in_channels %d not in [1,4]", cin);
+  if (scratch && dtype == LDM_DT_BF16 && k_conv_wgrad_mn_applicable(64, cout, H, W, 1, dtype) && ((uintptr_t)scratch & 255) == 0 &&
+      getenv("LDM_INITIAL_WGRAD_SIMT") == nullptr) {
+    bf16* patches = (bf16*)scratch;
+    float* acc = (float*)((char*)scratch + ((int64_t)M * 64 * 2 + 255) / 256 * 256);
+    const int64_t chunks = (int64_t)M * 8;
+    const unsigned g = (unsigned)((chunks + 255) / 256);
+    switch (cin) {
+      case 1: im2col3x3_small_kernel<1><<<g, 256, 0, st>>>(x, patches, H, W, chunks); break;
+      case 2: im2col3x3_small_kernel<2><<<g, 256, 0, st>>>(x, patches, H, W, chunks); break;
+      case 3: im2col3x3_small_kernel<3><<<g, 256, 0, st>>>(x, patches, H, W, chunks); break;
+      default: im2col3x3_small_kernel<4><<<g, 256, 0, st>>>(x, patches, H, W, chunks); break;
+    }
+    LDM_LAUNCHED("im2col3x3_small");
+    LDM_CUDA(cudaMemsetAsync(acc, 0, (size_t)cout * 64 * sizeof(float), st));
+    if (int rc = k_conv_wgrad_mn(patches, 64, 64, dy, cout, cout, acc, dbias, nullptr, batch, H, W, 1, st)) return rc;
+    add_cols_kernel<<<(cout * 9 * cin + 255) / 256, 256, 0, st>>>(acc, 64, dw, cout, 9 * cin);
+    LDM_LAUNCHED("add_cols");
+    return 0;
+  }
   int mps = 0;
   const int grid = initial_wgrad_grid(batch, H, W, &mps);
   float* part = (float*)scratch;
