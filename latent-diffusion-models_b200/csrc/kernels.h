@@ -193,7 +193,8 @@ bool k_linear_attention_backward_mma_applicable(int n_tokens, int dtype);
 int k_linear_attention_backward_mma(const void* qkv, const void* dout, void* dqkv, int batch, int N, void* workspace,
                                     cudaStream_t st);
 int k_pack_conv_weight_pair(const float* w_oihw, int cout, int cin, int ksize, void* fwd, void* dgrad, int dtype, cudaStream_t st);
-int k_pack_dense2x2_weight(const float* w_oihw, int cout, int cin, void* out, int dtype, cudaStream_t st);
+int k_pack_dense2x2_weight(const float* w_oihw, int cout, int cin, const float* w2_oi11, int cin2, void* out, int dtype,
+                           cudaStream_t st);
 bool k_conv_wgrad_mn_applicable(int cin, int cout, int H, int W, int ksize, int dtype);
 int k_conv_wgrad_mn(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, float* dbias, float* nat,
                     int batch, int H, int W, int ksize, cudaStream_t st);

@@ -111,22 +111,43 @@ int k_add2_f32(const float* a, const float* b, float* dst, int n, cudaStream_t s
 // (ky, kx) = (pi_y - po_y + 1, pi_x - po_x + 1) -- always a valid tap, because two pixels of a 2x2 image are at most one
 // step apart.  Row-major [4*cout][4*cin] = the packed layout of a 1x1 conv with 4*cin inputs.
 template <typename T>
-__global__ void pack_dense2x2_kernel(const float* __restrict__ w, int cout, int cin, T* __restrict__ out) {
+__global__ void pack_dense2x2_kernel(const float* __restrict__ w, int cout, int cin, T* __restrict__ out, int ld_out) {
   const int64_t total = (int64_t)16 * cout * cin;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int k = (int)(i % (4 * cin)), r = (int)(i / (4 * cin));
   const int pi = k / cin, ci = k % cin, po = r / cout, co = r % cout;
   const int ky = (pi >> 1) - (po >> 1) + 1, kx = (pi & 1) - (po & 1) + 1;
-  out[i] = from_float<T>(w[((int64_t)co * cin + ci) * 9 + ky * 3 + kx]);
+  out[(int64_t)r * ld_out + k] = from_float<T>(w[((int64_t)co * cin + ci) * 9 + ky * 3 + kx]);
 }
-int k_pack_dense2x2_weight(const float* w_oihw, int cout, int cin, void* out, int dtype, cudaStream_t st) {
+// the 1x1 shortcut in the same dense form: out[(po*cout + co)][col_off + pi*cin + ci] = (pi == po) ? wsc[co][ci] : 0
+template <typename T>
+__global__ void pack_blockdiag4_kernel(const float* __restrict__ wsc, int cout, int cin, T* __restrict__ out, int ld_out,
+                                       int col_off) {
+  const int64_t total = (int64_t)16 * cout * cin;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k = (int)(i % (4 * cin)), r = (int)(i / (4 * cin));
+  const int pi = k / cin, ci = k % cin, po = r / cout, co = r % cout;
+  out[(int64_t)r * ld_out + col_off + k] = from_float<T>(pi == po ? wsc[(int64_t)co * cin + ci] : 0.f);
+}
+// w2_oi11 (optional): a K-concatenated 1x1 source of cin2 channels behind the 4*cin dense columns (row stride 4*cin + 4*cin2)
+int k_pack_dense2x2_weight(const float* w_oihw, int cout, int cin, const float* w2_oi11, int cin2, void* out, int dtype,
+                           cudaStream_t st) {
   const int64_t total = (int64_t)16 * cout * cin;
   if (total == 0) return 0;
+  if (!w2_oi11) cin2 = 0;
+  const int ld = 4 * cin + 4 * cin2;
   const int grid = (int)ceil_div64(total, 256);
-  if (dtype == LDM_DT_BF16) pack_dense2x2_kernel<bf16><<<grid, 256, 0, st>>>(w_oihw, cout, cin, (bf16*)out);
-  else pack_dense2x2_kernel<float><<<grid, 256, 0, st>>>(w_oihw, cout, cin, (float*)out);
+  if (dtype == LDM_DT_BF16) pack_dense2x2_kernel<bf16><<<grid, 256, 0, st>>>(w_oihw, cout, cin, (bf16*)out, ld);
+  else pack_dense2x2_kernel<float><<<grid, 256, 0, st>>>(w_oihw, cout, cin, (float*)out, ld);
   LDM_LAUNCHED("pack_dense2x2_weight");
+  if (cin2 > 0) {
+    const int grid2 = (int)ceil_div64((int64_t)16 * cout * cin2, 256);
+    if (dtype == LDM_DT_BF16) pack_blockdiag4_kernel<bf16><<<grid2, 256, 0, st>>>(w2_oi11, cout, cin2, (bf16*)out, ld, 4 * cin);
+    else pack_blockdiag4_kernel<float><<<grid2, 256, 0, st>>>(w2_oi11, cout, cin2, (float*)out, ld, 4 * cin);
+    LDM_LAUNCHED("pack_blockdiag4_weight");
+  }
   return 0;
 }
 

@@ -156,7 +156,7 @@ void layout_res(Bump& b, ResW& r, int es) {
   b.take(r.g2, r.cout * 4); b.take(r.be2, r.cout * 4);
   if (r.dense2) {
     b.take(r.w1d, (int64_t)16 * r.cout * r.cin * es); b.take(r.b1d, 4 * r.cout * 4);
-    b.take(r.w2d, (int64_t)16 * r.cout * r.cout * es); b.take(r.b2d, 4 * r.cout * 4);
+    b.take(r.w2d, (int64_t)4 * r.cout * (4 * r.cout + (r.has_sc ? 4 * r.cin : 0)) * es); b.take(r.b2d, 4 * r.cout * 4);
   }
   if (r.dense1) {
     b.take(r.w1c, (int64_t)r.cout * r.cin * es);
@@ -292,6 +292,10 @@ extern "C" int ldm_unet_create(const ldm_unet_desc* desc, ldm_unet** out) {
     const bool dense = rb == 2 && h->d.dtype == LDM_DT_BF16 && h->d.conv_impl == 0 && getenv("LDM_NO_DENSE2X2") == nullptr;
     h->bott1.dense2 = dense && !h->bott1.has_sc;
     h->bott2.dense2 = dense && !h->bott2.has_sc;
+    // encoder level i runs at image_size >> i, decoder level j at rb << (j + 1): the 16x16 latent model has both at 2x2
+    const bool any2 = h->d.dtype == LDM_DT_BF16 && h->d.conv_impl == 0 && getenv("LDM_NO_DENSE2X2") == nullptr;
+    for (int i = 0; i < (int)h->enc_res.size(); ++i) h->enc_res[i].dense2 = any2 && (h->d.image_size >> i) == 2;
+    for (int j = 0; j < (int)h->dec_res.size(); ++j) h->dec_res[j].dense2 = any2 && (rb << (j + 1)) == 2;
     const bool centre = rb == 1 && h->d.dtype == LDM_DT_BF16 && h->d.conv_impl == 0 && getenv("LDM_NO_DENSE2X2") == nullptr;
     h->bott1.dense1 = centre && !h->bott1.has_sc;
     h->bott2.dense1 = centre && !h->bott2.has_sc;
@@ -364,11 +368,11 @@ int pack_res(ldm_unet* h, ResW& r, const float* const* P, cudaStream_t st) {
   RC(k_copy_f32(P[r.p_n1w], r.g1, r.cin, st)); RC(k_copy_f32(P[r.p_n1b], r.be1, r.cin, st));
   RC(k_copy_f32(P[r.p_n2w], r.g2, r.cout, st)); RC(k_copy_f32(P[r.p_n2b], r.be2, r.cout, st));
   if (r.dense2) {
-    RC(k_pack_dense2x2_weight(P[r.p_c1w], r.cout, r.cin, r.w1d, dt, st));
-    RC(k_pack_dense2x2_weight(P[r.p_c2w], r.cout, r.cout, r.w2d, dt, st));
+    RC(k_pack_dense2x2_weight(P[r.p_c1w], r.cout, r.cin, nullptr, 0, r.w1d, dt, st));
+    RC(k_pack_dense2x2_weight(P[r.p_c2w], r.cout, r.cout, r.has_sc ? P[r.p_scw] : nullptr, r.has_sc ? r.cin : 0, r.w2d, dt, st));
     for (int q = 0; q < 4; ++q) {
       RC(k_copy_f32(P[r.p_c1b], r.b1d + q * r.cout, r.cout, st));
-      RC(k_copy_f32(P[r.p_c2b], r.b2d + q * r.cout, r.cout, st));
+      RC(k_copy_f32(r.b2, r.b2d + q * r.cout, r.cout, st));   // conv2.bias (+ shortcut.bias), computed above
     }
   }
   if (r.dense1) {
@@ -540,11 +544,19 @@ struct Fwd {
       res_mod = 0;
       return rc;
     }
-    if (r.dense2 && R == 2 && !(use_t && r.tproj_off >= 0) && ldx == r.cin && ldo == r.cout && impl == 0 && dt == LDM_DT_BF16) {
+    if (r.dense2 && R == 2 && ldx == r.cin && ldo == r.cout && impl == 0 && dt == LDM_DT_BF16) {
       // [B][4][C] NHWC == [B][4C]: both convs as 1x1 GEMMs over "images" of one pixel with 4C channels
       RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
       RC(conv(s(0), 4 * r.cin, 4 * r.cin, nullptr, 0, 0, r.w1d, r.b1d, nullptr, 0, nullptr, 0, s(1), 4 * r.cout, 4 * r.cout, 1, 1));
-      RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1));
+      const float* rvd = (use_t && r.tproj_off >= 0) ? tproj + r.tproj_off : nullptr;
+      if (rvd && join_event) {
+        LDM_CUDA(cudaStreamWaitEvent(st, join_event, 0));
+        join_event = nullptr;
+      }
+      RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1, rvd, h->tproj_total));
+      if (r.has_sc)   // the 1x1 shortcut as a block-diagonal K-concatenated source
+        return conv(s(0), 4 * r.cout, 4 * r.cout, x, 4 * ldx, 4 * r.cin, r.w2d, r.b2d, nullptr, 0, nullptr, 0, out, 4 * ldo,
+                    4 * r.cout, 1, 1);
       return conv(s(0), 4 * r.cout, 4 * r.cout, nullptr, 0, 0, r.w2d, r.b2d, nullptr, 0, x, 4 * ldx, out, 4 * ldo, 4 * r.cout, 1, 1);
     }
     if (r.dense1 && R == 1 && !(use_t && r.tproj_off >= 0) && impl == 0 && dt == LDM_DT_BF16) {
