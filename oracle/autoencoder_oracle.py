@@ -3,7 +3,7 @@ A functional restatement of src/Autoencoder.py over a plain state_dict; pinned b
 oracle/make_golden_next.py produced by running the unmodified reference modules."""
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Tuple
 
 import torch
 import torch.nn.functional as F

@@ -15,7 +15,6 @@ g11_ldm_latent.npz     LatentDiffusionModel (src/LatentDiffusionModel.py): sched
 from __future__ import annotations
 
 import argparse
-import io
 import os
 import sys
 import tempfile

@@ -7,7 +7,7 @@ torchvision.utils.save_image, src/DiffusionModelTrainer.py:94-107)."""
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional, Tuple
+from typing import Dict, Optional
 
 import numpy as np
 import torch
