@@ -449,28 +449,33 @@ __global__ void __launch_bounds__(128) linattn_mma_kernel(const bf16* __restrict
 // ws per (sample, head): ctx[32][32], dctx[32][32], kmax[32], kzinv[32]  (fp32)
 constexpr int LB_WS = 2 * 32 * 32 + 64;
 
+// grid (batch, S): split s takes tokens [s*chunk, (s+1)*chunk) and writes UNNORMALISED partial results (ctx accumulator with
+// its running row max and row sum, dctx); the apply kernel merges the S partials.  Small batches get S > 1 so that the pass
+// fills the machine.
 __global__ void __launch_bounds__(128) linattn_bwd_ctx_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
-                                                              float* __restrict__ ws, int N) {
+                                                              float* __restrict__ ws, int N, int chunk) {
   __shared__ __align__(128) uint8_t smem[4][2][2][LM_BUF];
   const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
   const bf16* base = qkv + (int64_t)b * N * 384 + h * LA_D;
   const bf16* dob = dout + (int64_t)b * N * 128 + h * LA_D;
-  float* wsp = ws + ((int64_t)b * 4 + h) * LB_WS;
+  const int S = gridDim.y, sp = blockIdx.y;
+  const int tok_b = sp * chunk, tok_e = min(N, tok_b + chunk);
+  float* wsp = ws + (((int64_t)b * 4 + h) * S + sp) * LB_WS;
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&smem[h][0][0][0]);
   auto buf = [&](int stage, int which) { return sbase + (uint32_t)((stage * 2 + which) * LM_BUF); };
-  const int steps = N >> 4;
+  const int steps = (tok_e - tok_b) >> 4;
   const int tiles = (steps + 1) >> 1;
 
   // pass 0: (k, v) -> ctx;  pass 1: (q, dout) -> dctx
   for (int pass = 0; pass < 2; ++pass) {
     auto load = [&](int tile, int stage) {
-      const int tok0 = tile * LM_TILE;
+      const int tok0 = tok_b + tile * LM_TILE;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int c = lane + 32 * i;
         const int which = c >> 7, r = (c & 127) >> 2, ch = c & 3;
-        if (tok0 + r < N) {
+        if (tok0 + r < tok_e) {
           const bf16* src = pass == 0 ? base + (int64_t)(tok0 + r) * 384 + 128 * (1 + which) + ch * 8
                                       : (which == 0 ? base + (int64_t)(tok0 + r) * 384 + ch * 8
                                                     : dob + (int64_t)(tok0 + r) * 128 + ch * 8);
@@ -627,11 +632,10 @@ __global__ void __launch_bounds__(128) linattn_bwd_ctx_kernel(const bf16* __rest
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int d = mt * 16 + hf * 8 + g;
-        float f = 1.f;
+        const float f = 1.f;   // unnormalised: the apply kernel divides by the merged row sum
         if (pass == 0) {
           const float zs = quad_sum(z[mt][hf]);
-          f = 1.0f / zs;
-          if (tq == 0) { wsp[2048 + d] = m_run[mt][hf]; wsp[2048 + 32 + d] = f; }
+          if (tq == 0) { wsp[2048 + d] = m_run[mt][hf]; wsp[2048 + 32 + d] = zs; }
         }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
@@ -643,7 +647,7 @@ __global__ void __launch_bounds__(128) linattn_bwd_ctx_kernel(const bf16* __rest
 constexpr int LB_CHUNK = 128;   // tokens per CTA of the apply kernel
 
 __global__ void __launch_bounds__(128) linattn_bwd_apply_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
-                                                                const float* __restrict__ ws, bf16* __restrict__ dqkv, int N) {
+                                                                const float* __restrict__ ws, bf16* __restrict__ dqkv, int N, int S) {
   // per warp: [stage][q|k|v|dout] tiles of 2 KB, then ctx and dctx as bf16 [d][e] tiles, then kmax | kzinv | cs
   extern __shared__ __align__(128) uint8_t lb_dyn[];
   constexpr int WARP_BYTES = 2 * 4 * LM_BUF + 2 * LM_BUF + 3 * 32 * 4;
@@ -652,7 +656,7 @@ __global__ void __launch_bounds__(128) linattn_bwd_apply_kernel(const bf16* __re
   const bf16* base = qkv + (int64_t)b * N * 384 + h * LA_D;
   const bf16* dob = dout + (int64_t)b * N * 128 + h * LA_D;
   bf16* dbase = dqkv + (int64_t)b * N * 384 + h * LA_D;
-  const float* wsp = ws + ((int64_t)b * 4 + h) * LB_WS;
+  const float* wsp = ws + ((int64_t)b * 4 + h) * S * LB_WS;   // S partial results of the ctx pass
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(lb_dyn + (size_t)h * WARP_BYTES);
   auto buf = [&](int stage, int which) { return sbase + (uint32_t)((stage * 4 + which) * LM_BUF); };
   const uint32_t ctx_s = sbase + 8 * LM_BUF, dctx_s = ctx_s + LM_BUF;
@@ -679,18 +683,33 @@ __global__ void __launch_bounds__(128) linattn_bwd_apply_kernel(const bf16* __re
   if (tiles > 1) load(1, 1);
   cp_async_commit();
 
-  // ctx, dctx -> bf16 tiles; cs[d] = sum_e dctx[d][e] ctx[d][e] in fp32 (lane = d)
+  // merge the S partials of row d = lane (softmax-over-tokens state: max m_s, sum z_s, accumulator acc_s):
+  //   ctx[d][e] = sum_s acc_s[d][e] exp(m_s - m) / sum_s z_s exp(m_s - m),  dctx = sum_s dctx_s
+  // then ctx, dctx -> bf16 tiles and cs[d] = sum_e dctx[d][e] ctx[d][e] in fp32
   {
+    float mrow = -INFINITY;
+    for (int sp = 0; sp < S; ++sp) mrow = fmaxf(mrow, wsp[(int64_t)sp * LB_WS + 2048 + lane]);
+    float zt = 0.f;
+    for (int sp = 0; sp < S; ++sp)
+      zt += wsp[(int64_t)sp * LB_WS + 2048 + 32 + lane] * ex2f((wsp[(int64_t)sp * LB_WS + 2048 + lane] - mrow) * LOG2E);
+    const float zinv = 1.0f / zt;
     float csd = 0.f;
 #pragma unroll
     for (int c8 = 0; c8 < 4; ++c8) {
       float cv[8], dv8[8];
 #pragma unroll
-      for (int j = 0; j < 8; j += 4) {
-        const float4 c4 = *reinterpret_cast<const float4*>(wsp + lane * 32 + c8 * 8 + j);
-        const float4 d4 = *reinterpret_cast<const float4*>(wsp + 1024 + lane * 32 + c8 * 8 + j);
-        cv[j] = c4.x; cv[j + 1] = c4.y; cv[j + 2] = c4.z; cv[j + 3] = c4.w;
-        dv8[j] = d4.x; dv8[j + 1] = d4.y; dv8[j + 2] = d4.z; dv8[j + 3] = d4.w;
+      for (int j = 0; j < 8; ++j) { cv[j] = 0.f; dv8[j] = 0.f; }
+      for (int sp = 0; sp < S; ++sp) {
+        const float* pw = wsp + (int64_t)sp * LB_WS;
+        const float wgt = ex2f((pw[2048 + lane] - mrow) * LOG2E) * zinv;
+#pragma unroll
+        for (int j = 0; j < 8; j += 4) {
+          const float4 c4 = *reinterpret_cast<const float4*>(pw + lane * 32 + c8 * 8 + j);
+          const float4 d4 = *reinterpret_cast<const float4*>(pw + 1024 + lane * 32 + c8 * 8 + j);
+          cv[j] = fmaf(c4.x, wgt, cv[j]); cv[j + 1] = fmaf(c4.y, wgt, cv[j + 1]);
+          cv[j + 2] = fmaf(c4.z, wgt, cv[j + 2]); cv[j + 3] = fmaf(c4.w, wgt, cv[j + 3]);
+          dv8[j] += d4.x; dv8[j + 1] += d4.y; dv8[j + 2] += d4.z; dv8[j + 3] += d4.w;
+        }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) csd = fmaf(cv[j], dv8[j], csd);
@@ -699,8 +718,8 @@ __global__ void __launch_bounds__(128) linattn_bwd_apply_kernel(const bf16* __re
       asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dctx_s + lm_off(lane, c8)), "r"(pack_bf2(dv8[0], dv8[1])),
                    "r"(pack_bf2(dv8[2], dv8[3])), "r"(pack_bf2(dv8[4], dv8[5])), "r"(pack_bf2(dv8[6], dv8[7])) : "memory");
     }
-    fl[lane] = wsp[2048 + lane];
-    fl[32 + lane] = wsp[2048 + 32 + lane];
+    fl[lane] = mrow;
+    fl[32 + lane] = zinv;
     fl[64 + lane] = csd;
   }
   __syncwarp();
@@ -1281,7 +1300,14 @@ int k_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, 
 
 
 // ---- LinearAttention backward on mma.sync (bf16, N % 16 == 0); workspace: k_linear_attention_backward_ws_bytes
-int64_t k_linear_attention_backward_ws_bytes(int batch) { return (int64_t)batch * 4 * LB_WS * sizeof(float) + 256; }
+// token splits of the ctx pass: enough CTAs for two per SM at small batch, never more than 8
+static int linattn_bwd_splits(int batch) {
+  int s = batch > 0 ? 296 / batch : 1;
+  return s < 1 ? 1 : (s > 8 ? 8 : s);
+}
+int64_t k_linear_attention_backward_ws_bytes(int batch) {
+  return (int64_t)batch * 4 * linattn_bwd_splits(batch) * LB_WS * sizeof(float) + 256;
+}
 bool k_linear_attention_backward_mma_applicable(int n_tokens, int dtype) {
   return dtype == LDM_DT_BF16 && n_tokens % 16 == 0 && getenv("LDM_LINATTN_BWD_SIMT") == nullptr;
 }
@@ -1295,10 +1321,14 @@ int k_linear_attention_backward_mma(const void* qkv, const void* dout, void* dqk
     LDM_CUDA(cudaFuncSetAttribute(linattn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  linattn_bwd_ctx_kernel<<<batch, 128, 0, st>>>((const bf16*)qkv, (const bf16*)dout, (float*)workspace, N);
+  int S = linattn_bwd_splits(batch);
+  if (S > N / 64) S = N / 64 > 0 ? N / 64 : 1;              // at least 64 tokens per split
+  const int chunk = ((N + S - 1) / S + 31) / 32 * 32;       // whole 32-token tiles
+  S = (N + chunk - 1) / chunk;
+  linattn_bwd_ctx_kernel<<<dim3(batch, S), 128, 0, st>>>((const bf16*)qkv, (const bf16*)dout, (float*)workspace, N, chunk);
   LDM_LAUNCHED("linattn_bwd_ctx");
   linattn_bwd_apply_kernel<<<dim3(batch, (N + LB_CHUNK - 1) / LB_CHUNK), 128, smem, st>>>((const bf16*)qkv, (const bf16*)dout,
-                                                                                      (const float*)workspace, (bf16*)dqkv, N);
+                                                                                      (const float*)workspace, (bf16*)dqkv, N, S);
   LDM_LAUNCHED("linattn_bwd_apply");
   return 0;
 }
