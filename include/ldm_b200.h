@@ -201,6 +201,22 @@ int ldm_conv2d(const void* x, int ldx, int cin, const void* x2, int ldx2, int ci
                const void* w_packed, const float* bias, const float* rowvec, int ld_rowvec,
                const void* res, int ldres, void* y, int ldy, int cout,
                int batch, int height, int width, int ksize, int dtype, int impl, void* stream);
+/* The same convolution with the GroupNorm that follows it fused into the epilogue (bf16, impl 0 only):
+ *   gn_mode 1: y = conv(x) (+res) is stored as usual and the epilogue also leaves GroupNorm(groups, Cout) partial sums of the
+ *              stored values, float2 {S, Q} at scratch[(n * groups + g) * nslots + slot]; *nslots_out slots per (image,
+ *              group) -- what PreNorm consumers read (src/UNet.py:106-110)
+ *   gn_mode 2: y = [silu](GroupNorm(conv(x) + gn_rowvec[n])) [+ gn_res] -- Block (src/UNet.py:52-58) with the ResNetBlock
+ *              time-embedding add (:88-93), or LinearAttention.to_out's GroupNorm(1, C) + the Residual add (:147,:20).
+ *              nvar = 2: image n is normalised twice (row vectors n and n + var_rows) and stored as images n and
+ *              n + var_rows (cond / uncond halves sharing one convolution).  scratch: zero-filled packet area of
+ *              ldm_conv2d_gn_scratch_bytes(batch); tag: non-zero, different for every call since the area was zeroed. */
+int64_t ldm_conv2d_gn_scratch_bytes(int batch);
+int ldm_conv2d_gn(const void* x, int ldx, int cin, const void* x2, int ldx2, int cin2, const void* w_packed,
+                  const float* bias, const void* res, int ldres, void* y, int ldy, int cout, int batch, int height,
+                  int width, int ksize, int gn_mode, int groups, float eps, int silu, const float* gamma,
+                  const float* beta, const float* gn_rowvec, int ld_gn_rowvec, const void* gn_res, int ld_gn_res,
+                  int nvar, int var_rows, void* scratch, int64_t scratch_bytes, unsigned tag, int* nslots_out,
+                  void* stream);
 /* OIHW fp32 -> packed [Cout][kh][kw][Cin] (+ optional OI11 second source appended along K) */
 int ldm_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize,
                          const float* w2_oi11, int cin2, void* w_packed, int dtype, void* stream);

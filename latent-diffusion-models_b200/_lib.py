@@ -72,6 +72,10 @@ SIGNATURES = {
     "ldm_group_norm_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "ldm_conv2d": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, vp,
                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_conv2d_gn_scratch_bytes": (C.c_int64, [C.c_int]),
+    "ldm_conv2d_gn": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int,
+                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int,
+                                C.c_int, C.c_int, vp, C.c_int64, C.c_uint, C.POINTER(C.c_int), vp]),
     "ldm_pack_conv_weight": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp]),
     "ldm_conv_transpose2x2": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_int, vp]),

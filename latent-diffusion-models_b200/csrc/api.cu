@@ -64,6 +64,28 @@ int ldm_group_norm(const void* x, int ldx, void* y, int ldy, const void* res, in
 }
 int64_t ldm_group_norm_workspace_bytes(int batch, int groups) { return k_group_norm_ws_bytes(batch, groups); }
 
+int64_t ldm_conv2d_gn_scratch_bytes(int batch) { return (int64_t)(batch > 0 ? batch : 1) * 256 * 16; }
+
+int ldm_conv2d_gn(const void* x, int ldx, int cin, const void* x2, int ldx2, int cin2, const void* w_packed,
+                  const float* bias, const void* res, int ldres, void* y, int ldy, int cout, int batch, int height,
+                  int width, int ksize, int gn_mode, int groups, float eps, int silu, const float* gamma,
+                  const float* beta, const float* gn_rowvec, int ld_gn_rowvec, const void* gn_res, int ld_gn_res,
+                  int nvar, int var_rows, void* scratch, int64_t scratch_bytes, unsigned tag, int* nslots_out,
+                  void* stream) {
+  LDM_REQUIRE(x && w_packed && y, "ldm_conv2d_gn: null argument");
+  LDM_REQUIRE(gn_mode == 1 || gn_mode == 2, "ldm_conv2d_gn: gn_mode must be 1 or 2");
+  ConvArgs a;
+  a.x = x; a.ldx = ldx; a.cin = cin; a.x2 = x2; a.ldx2 = ldx2; a.cin2 = x2 ? cin2 : 0; a.w = w_packed; a.bias = bias;
+  a.rowvec = nullptr; a.ld_rowvec = 0; a.res = res; a.ldres = ldres; a.y = y; a.ldy = ldy; a.cout = cout;
+  a.batch = batch; a.height = height; a.width = width; a.ksize = ksize; a.up2 = 0; a.dtype = LDM_DT_BF16;
+  a.gn.mode = gn_mode; a.gn.groups = groups; a.gn.eps = eps; a.gn.silu = silu; a.gn.gamma = gamma; a.gn.beta = beta;
+  a.gn.rowvec = gn_rowvec; a.gn.ld_rowvec = ld_gn_rowvec; a.gn.res = gn_res; a.gn.ldres = ld_gn_res;
+  a.gn.nvar = nvar > 0 ? nvar : 1; a.gn.var_rows = var_rows; a.gn.scratch = scratch; a.gn.scratch_bytes = scratch_bytes;
+  a.gn.tag = tag; a.gn.nslots_out = nslots_out;
+  if (int rc = k_conv_tc_prepare()) return rc;
+  return k_conv(a, 0, (cudaStream_t)stream);
+}
+
 int ldm_conv2d(const void* x, int ldx, int cin, const void* x2, int ldx2, int cin2, const void* w_packed,
                const float* bias, const float* rowvec, int ld_rowvec, const void* res, int ldres, void* y, int ldy,
                int cout, int batch, int height, int width, int ksize, int dtype, int impl, void* stream) {

@@ -908,17 +908,32 @@ __global__ void __launch_bounds__(128, LINATTN_FUSED_MIN_CTAS) linattn_qkv_fused
   // per-sample GroupNorm(1, C) statistics from the slab partials (fixed order), see gn_apply_kernel
   float gr = 1.f, gmu = 0.f;
   if (FOLD) {
-    float a = 0.f, bsum = 0.f;
-    for (int sp = 0; sp < gn_splits; ++sp) {
-      const float2 v = gn_part[(int64_t)b * gn_splits + sp];
-      a += v.x; bsum += v.y;
+    if (gn_splits < 0) {
+      // un-pivoted sums {S, Q} left by the producing convolution's epilogue (conv_epilogue.cuh, mode 1): -gn_splits slots
+      double a = 0.0, bsum = 0.0;
+      for (int sp = 0; sp < -gn_splits; ++sp) {
+        const float2 v = gn_part[(int64_t)b * (-gn_splits) + sp];
+        a += (double)v.x; bsum += (double)v.y;
+      }
+      const double cnt = (double)N * (double)C;
+      const double m1 = a / cnt;
+      double var = bsum / cnt - m1 * m1;
+      if (var < 0.0) var = 0.0;
+      gmu = (float)m1;
+      gr = (float)(1.0 / sqrt(var + (double)gn_eps));
+    } else {
+      float a = 0.f, bsum = 0.f;
+      for (int sp = 0; sp < gn_splits; ++sp) {
+        const float2 v = gn_part[(int64_t)b * gn_splits + sp];
+        a += v.x; bsum += v.y;
+      }
+      const float K = __bfloat162float(xb[0]);
+      const float inv_n = 1.0f / ((float)N * (float)C);
+      const float m1 = a * inv_n;
+      const float var = fmaxf(bsum * inv_n - m1 * m1, 0.f);
+      gmu = K + m1;
+      gr = 1.0f / sqrtf(var + gn_eps);
     }
-    const float K = __bfloat162float(xb[0]);
-    const float inv_n = 1.0f / ((float)N * (float)C);
-    const float m1 = a * inv_n;
-    const float var = fmaxf(bsum * inv_n - m1 * m1, 0.f);
-    gmu = K + m1;
-    gr = 1.0f / sqrtf(var + gn_eps);
   }
   const float kscale = gr * LOG2E;   // softmax over tokens of r*k: the scale folds into the exp2 argument
 
@@ -1172,7 +1187,7 @@ int k_linear_attention_qkv(const void* xn, int ldx, int cin, const void* wqkv, v
 }
 int k_linear_attention_qkv_prenorm(const void* x, int ldx, int cin, const void* wfold, const float* uv, const void* gn_part,
                                    int gn_splits, float eps, void* out, int batch, int n_tokens, int dtype, cudaStream_t st) {
-  LDM_REQUIRE(dtype == LDM_DT_BF16 && cin == 64 && n_tokens % 16 == 0 && ldx % 8 == 0 && uv && gn_part && gn_splits >= 1,
+  LDM_REQUIRE(dtype == LDM_DT_BF16 && cin == 64 && n_tokens % 16 == 0 && ldx % 8 == 0 && uv && gn_part && gn_splits != 0,
               "linear_attention_qkv_prenorm: needs bf16, 64 input channels, a multiple of 16 tokens and GroupNorm statistics");
   if (batch == 0 || n_tokens == 0) return 0;
   LDM_CUDA(ldm_launch_pdl(linattn_qkv_fused_kernel<true>, dim3(batch), dim3(128), 0, st, (const bf16*)x, ldx, (const bf16*)wfold, uv,
@@ -1316,10 +1331,12 @@ int k_linear_attention_backward_mma(const void* qkv, const void* dout, void* dqk
   LDM_REQUIRE(workspace && ((uintptr_t)workspace & 15) == 0, "linear_attention_backward: workspace missing or unaligned");
   if (batch == 0 || N == 0) return 0;
   constexpr int smem = 4 * (2 * 4 * LM_BUF + 2 * LM_BUF + 3 * 32 * 4);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};   // the dynamic shared-memory opt-in is per device
+  int dev = 0;
+  LDM_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
     LDM_CUDA(cudaFuncSetAttribute(linattn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   int S = linattn_bwd_splits(batch);
   if (S > N / 64) S = N / 64 > 0 ? N / 64 : 1;              // at least 64 tokens per split

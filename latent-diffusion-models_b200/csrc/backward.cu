@@ -933,11 +933,13 @@ int k_unshuffle2(const void* dy, int lddy, void* out, int batch, int H, int W, i
 
 int k_linear_attention_backward(const void* qkv, const void* dout, void* dqkv, int batch, int N, int dtype, cudaStream_t st) {
   if (batch == 0 || N == 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};   // the dynamic shared-memory opt-in is per device
+  int dev = 0;
+  LDM_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
     LDM_CUDA(cudaFuncSetAttribute(linattn_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbSmem)));
     LDM_CUDA(cudaFuncSetAttribute(linattn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbSmem)));
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   DISPATCH_T(dtype, linattn_bwd_kernel<T><<<batch * 4, 256, sizeof(LbSmem), st>>>((const T*)qkv, (const T*)dout, (T*)dqkv, N));
   LDM_LAUNCHED("linear_attention_backward");

@@ -25,6 +25,7 @@
 
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "conv_epilogue.cuh"
 
 // timeline probe (LDM_HALO_DEBUG bit 2): CTA 0 records globaltimer stamps of its first tiles
 __device__ unsigned long long g_halo_dbg[1024];
@@ -50,27 +51,22 @@ __device__ __forceinline__ unsigned long long gtime() {
   } while (0)
 
 struct HaloParams {
-  int B, H, W, P;          // batch, spatial size, padded pitch W+2
-  int RB;                  // slab rows
+  int P;                   // padded pitch W+2
   int tiles_per_image, num_tiles;
   int slabs_main;          // cin/64
   int slabs_total;         // + cin2/64 (centre tap only)
   int n_kb;                // 9*slabs_main + slabs2
   int a_stage_bytes;       // RB*P*128 rounded up to 1024
   int a_stages, b_stages;  // ring depths; b_stages >= n_kb means the filter is resident
-  int cout;                // == BLOCK_N (one N tile)
   int a_tx_bytes, w_start; // TMA box bytes, first W coordinate (-1)
-  int res_mod;             // > 0: residual image index = n % res_mod
   int debug;               // profiling knob (LDM_HALO_DEBUG bit 0: no epilogue memory traffic, bit 1: no MMAs)
   int base_offset_mode;    // experiment knob: 0 = descriptor base_offset 0, 1 = (start >> 7) & 7
-  const float* bias;
-  const float* rowvec; int ld_rowvec;
-  const bf16* res; int ldres;
-  bf16* y; int ldy;
-  const float* fin_w; const float* fin_b; float* fin_out; int fin_cout;
+  EpiP e;                  // everything the epilogue warps need (conv_epilogue.cuh)
 };
 
-template <int BLOCK_N>
+constexpr int HALO_NACC = 4;   // accumulator ring depth (the fused GroupNorm defers its second pass by one tile)
+
+template <int BLOCK_N, int GM = 0>
 __global__ void __launch_bounds__(320, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                  const __grid_constant__ CUtensorMap tmap_b, const HaloParams p) {
@@ -80,10 +76,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t smem_b = smem_base;
   const uint32_t smem_a = smem_b + p.b_stages * B_TILE_BYTES;
   const uint32_t bars = smem_a + p.a_stages * p.a_stage_bytes;
-  // barrier map: afull[8] aempty[8] bfull[32] bempty[32] tfull[2] tempty[2] | tmem slot
+  // barrier map: afull[8] aempty[8] bfull[32] bempty[32] tfull[4] tempty[4] | tmem slot
   const uint32_t afull = bars, aempty = bars + 64, bfull = bars + 128, bempty = bars + 384, tfull = bars + 640,
-                 tempty = bars + 656, tmem_slot = bars + 672;
-  float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 1024 - smem_u32(smem_raw)));  // [BLOCK_N]
+                 tempty = bars + 672, tmem_slot = bars + 704;
+  float* s_epi = reinterpret_cast<float*>(smem_raw + (bars + 1024 - smem_u32(smem_raw)));   // epilogue staging area
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -94,10 +90,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < 8; ++s) { mbar_init(afull + 8 * s, 1); mbar_init(aempty + 8 * s, 1); }
     for (int s = 0; s < 32; ++s) { mbar_init(bfull + 8 * s, 1); mbar_init(bempty + 8 * s, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull + 8 * i, 1); mbar_init(tempty + 8 * i, 8); }
+    for (int i = 0; i < HALO_NACC; ++i) { mbar_init(tfull + 8 * i, 1); mbar_init(tempty + 8 * i, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BLOCK_N);
+  if (warp == 1) tmem_alloc(tmem_slot, HALO_NACC * BLOCK_N);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -105,7 +101,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   pdl_trigger();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const bool resident = p.b_stages >= p.n_kb;
-  const int PL_rows = p.H + 2;
   const int slabs2 = p.slabs_total - p.slabs_main;
   (void)slabs2;
 
@@ -191,9 +186,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int r0 = lo >= 0 ? lo / P : -1;
         const int off0 = q0 - r0 * P;  // slab row of the tile's first output position (centre tap)
         tin += tstep; if (tin >= tiles_per_image) tin -= tiles_per_image;
-        const int acc = iter & 1;
+        const int acc = iter % HALO_NACC;
         DBG_STAMP(0);
-        mbar_wait(tempty + 8 * acc, ((iter >> 1) & 1) ^ 1);
+        mbar_wait(tempty + 8 * acc, ((iter / HALO_NACC) & 1) ^ 1);
         DBG_STAMP(1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
@@ -254,146 +249,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    // 8 epilogue warps: two per TMEM lane quarter, each taking half of the tile's columns (one warp per scheduler
-    // would leave every TMEM-load / convert / store chain exposed)
-    const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
-    constexpr int COLS = BLOCK_N / 2;
-    const int cw = half * COLS;
-    const int row = quarter * 32 + lane;
-    const bool keep_l2 = (p.debug & 8) == 0;      // L2 evict_last on the output (2688 -> 2678 us per timestep); debug bit 3 = off
-    const uint64_t l2pol = l2_evict_last_policy();
-    const int H = p.H, W = p.W, P = p.P, hw = p.H * p.W;
-    const int tiles_per_image = p.tiles_per_image, num_tiles = p.num_tiles;
-    const int ldy = p.ldy, ldres = p.ldres, ld_rowvec = p.ld_rowvec, fin_cout = p.fin_cout;
-    bf16* const y = p.y;
-    const bf16* const res = p.res;
-    const float* const rowvec = p.rowvec;
-    const float* const fin_w = p.fin_w;
-    float* const fin_out = p.fin_out;
-    const bool no_mem = p.debug & 1;
-    const int res_mod = p.res_mod;
-    float* s_fin = s_bias + 768;  // [128][8] cross-warp sums of the fused projection (offset 3 KB in the 7 KB region)
-    // the bias vector is read by every row of every tile: stage it in shared memory once (the CTA runs with the
-    // maximum shared-memory carve-out, so L1 is tiny and a __ldg per tile would pay L2 latency each time)
-    {
-      const int et = threadIdx.x - 64;
-      for (int c = et; c < BLOCK_N; c += 256) s_bias[c] = p.bias ? p.bias[c] : 0.f;
-      if (fin_out)  // fused output projection: [fin_cout][BLOCK_N] weights behind the bias vector
-        for (int c = et; c < fin_cout * BLOCK_N; c += 256) s_bias[BLOCK_N + c] = fin_w[c];
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
-    int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
-      const int n = tile / tiles_per_image;
-      const int q0 = P + (tile - n * tiles_per_image) * TILE_M;
-      const int acc = iter & 1;
-      const int q = q0 + row;
-      const int r = q / P, c = q - r * P;
-      const bool valid = r >= 1 && r <= H && c >= 1 && c <= W && !no_mem;  // a real pixel, not a halo column / tail row
-      const int pix = (r - 1) * W + (c - 1);
-      const int64_t m = (int64_t)n * hw + pix;
-      bf16* yrow = y ? y + m * ldy + cw : nullptr;
-      const float* rvrow = rowvec ? rowvec + (int64_t)n * ld_rowvec + cw : nullptr;
-      // residual row: requested BEFORE waiting for the accumulator, so its latency hides behind the MMAs
-      uint4 rr[COLS / 8];
-      if (res && valid) {
-        const int64_t mr = res_mod > 0 ? (int64_t)(n % res_mod) * hw + pix : m;
-        const uint4* rp = reinterpret_cast<const uint4*>(res + mr * ldres + cw);
-#pragma unroll
-        for (int j = 0; j < COLS / 8; ++j) rr[j] = __ldg(rp + j);
-      }
-      if (warp == 2 && lane == 0) DBG_STAMP(4);
-      if (lane == 0) mbar_wait(tfull + 8 * acc, (iter >> 1) & 1);
-      __syncwarp();
-      if (warp == 2 && lane == 0) DBG_STAMP(5);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + cw;
-      float fo[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c0 = 0; c0 < COLS; c0 += 32) {
-        uint32_t rg[32];
-        tmem_ld32(taddr + c0, rg);
-        tmem_ld_wait();
-        if (valid) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cw + c0 + j);
-            v[j] = __uint_as_float(rg[j]) + b4.x; v[j + 1] = __uint_as_float(rg[j + 1]) + b4.y;
-            v[j + 2] = __uint_as_float(rg[j + 2]) + b4.z; v[j + 3] = __uint_as_float(rg[j + 3]) + b4.w;
-          }
-          if (rvrow) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b4 = __ldg(reinterpret_cast<const float4*>(rvrow + c0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          }
-          if (res) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rr[(c0 + j) >> 3]);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float2 f = __bfloat1622float2(h2[u]);
-                v[j + 2 * u] += f.x; v[j + 2 * u + 1] += f.y;
-              }
-            }
-          }
-          if (yrow) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float t8[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) t8[u] = v[j + u];
-              if (keep_l2) store_chunk_keep(yrow + c0 + j, t8, l2pol); else store_chunk(yrow + c0 + j, t8);
-            }
-          }
-          if (fin_out) {
-            for (int o = 0; o < fin_cout; ++o) {
-              const float* wrow = s_bias + BLOCK_N + o * BLOCK_N + cw + c0;
-              float sacc = 0.f;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 w4 = *reinterpret_cast<const float4*>(wrow + j);
-                sacc = fmaf(v[j], w4.x, sacc); sacc = fmaf(v[j + 1], w4.y, sacc);
-                sacc = fmaf(v[j + 2], w4.z, sacc); sacc = fmaf(v[j + 3], w4.w, sacc);
-              }
-#pragma unroll
-              for (int u = 0; u < 8; ++u)
-                if (u == o) fo[u] += sacc;
-            }
-          }
-        }
-      }
-      if (fin_out) {
-        // the two column halves of a row live in two warps: combine through shared memory, half 0 writes
-        float* fx = s_fin + row * 8;
-        if (half == 1) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) fx[u] = fo[u];
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (half == 0 && valid) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (u < fin_cout) fin_out[((int64_t)n * fin_cout + u) * hw + pix] = fo[u] + fx[u] + __ldg(p.fin_b + u);
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // fx is rewritten by the next tile
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_relaxed(tempty + 8 * acc);
-      if (warp == 2 && lane == 0) DBG_STAMP(6);
-    }
+    // ===================== epilogue (warps 2..9): conv_epilogue.cuh =====================
+    conv_epilogue<BLOCK_N, 1, HALO_NACC, true, GM>(p.e, tmem_base, tfull, tempty, s_epi, p.num_tiles);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * BLOCK_N);
-  (void)PL_rows;
+  if (warp == 1) tmem_dealloc(tmem_base, HALO_NACC * BLOCK_N);
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 g_encode_h = nullptr;
@@ -402,21 +264,27 @@ int g_halo_enabled = -1;
 int g_base_offset_mode = 0;
 
 int halo_init() {
-  if (g_encode_h) return 0;
+  static bool inited[64] = {};   // function attributes are per device
+  int dev = 0;
+  LDM_CUDA(cudaGetDevice(&dev));
+  if (g_encode_h && inited[dev & 63]) return 0;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   LDM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   LDM_REQUIRE(qres == cudaDriverEntryPointSuccess && fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
-  int dev = 0;
-  LDM_CUDA(cudaGetDevice(&dev));
   LDM_CUDA(cudaDeviceGetAttribute(&g_num_sms_h, cudaDevAttrMultiProcessorCount, dev));
-  LDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  LDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  LDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  LDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  LDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  LDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  LDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  LDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const char* e = getenv("LDM_CONV_HALO");
   g_halo_enabled = e ? atoi(e) : 1;
   const char* bo = getenv("LDM_HALO_BASE_OFFSET");
   g_base_offset_mode = bo ? atoi(bo) : 0;
   g_encode_h = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  inited[dev & 63] = true;
   return 0;
 }
 
@@ -478,56 +346,92 @@ int k_conv_halo(const ConvArgs& a, cudaStream_t st) {
   LDM_REQUIRE(((uintptr_t)a.x & 15) == 0 && ((uintptr_t)a.w & 15) == 0 && ((uintptr_t)a.y & 15) == 0 &&
                   ((uintptr_t)a.fin_w & 15) == 0, "conv_halo: pointers must be 16-byte aligned");
   LDM_REQUIRE(a.y || a.fin_out, "conv_halo: no output requested");
-  LDM_REQUIRE(!a.fin_out || (a.fin_cout >= 1 && (a.fin_cout + 1) * a.cout * 4 <= 3072 && a.fin_cout <= 8),
-              "conv_halo: fused projection supports at most %d outputs", 3072 / (a.cout * 4) - 1);
+  LDM_REQUIRE(!a.fin_out || (a.fin_cout >= 1 && a.fin_cout * a.cout <= 768 && a.fin_cout <= 8),
+              "conv_halo: fused projection supports at most %d outputs", 768 / a.cout);
   if (a.batch == 0) return 0;
   HaloParams p;
-  p.B = a.batch; p.H = a.height; p.W = a.width; p.P = a.width + 2;
+  EpiP& e = p.e;
+  const int H = a.height, W = a.width;
+  p.P = W + 2;
   const int span = TILE_M + 2 * (p.P + 1);                 // positions a tile touches over all taps
-  p.RB = (span + p.P - 1) / p.P + 1;                       // rows covering any alignment of that span
-  if (p.RB > p.H + 2) p.RB = p.H + 2 > 0 ? p.RB : p.RB;    // (box may exceed the image: OOB rows are zero)
-  p.tiles_per_image = (a.height * p.P + TILE_M - 1) / TILE_M;
+  const int RB = (span + p.P - 1) / p.P + 1;               // rows covering any alignment of that span (OOB rows are zero)
+  p.tiles_per_image = (H * p.P + TILE_M - 1) / TILE_M;
   p.num_tiles = a.batch * p.tiles_per_image;
   p.slabs_main = a.cin / BLOCK_K;
   p.slabs_total = p.slabs_main + (a.x2 ? a.cin2 / BLOCK_K : 0);
   p.n_kb = 9 * p.slabs_main + (p.slabs_total - p.slabs_main);
-  p.a_stage_bytes = (p.RB * p.P * 128 + 1023) / 1024 * 1024;
-  p.cout = a.cout;
+  p.a_stage_bytes = (RB * p.P * 128 + 1023) / 1024 * 1024;
   p.base_offset_mode = g_base_offset_mode;
   { const char* d = getenv("LDM_HALO_DEBUG"); p.debug = d ? atoi(d) : 0; }
-  p.a_tx_bytes = p.RB * p.P * 128; p.w_start = -1;
+  p.a_tx_bytes = RB * p.P * 128; p.w_start = -1;
   {
     const char* ex = getenv("LDM_HALO_EXP");
     const int eb = ex ? atoi(ex) : 0;
-    const int bw = (eb & 1) ? p.W : p.P, bh = (eb & 2) ? 4 : p.RB;
+    const int bw = (eb & 1) ? W : p.P, bh = (eb & 2) ? 4 : RB;
     if (eb & 1) p.w_start = 0;
     p.a_tx_bytes = bw * bh * 128;
   }
-  p.bias = a.bias; p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec;
-  p.res = (const bf16*)a.res; p.ldres = a.ldres; p.res_mod = a.res_mod;
-  p.y = (bf16*)a.y; p.ldy = a.ldy;
-  p.fin_w = a.fin_w; p.fin_b = a.fin_b; p.fin_out = a.fin_out; p.fin_cout = a.fin_cout;
+  e.M = a.batch * H * W; e.H = H; e.W = W; e.hw = H * W; e.P = p.P; e.tiles_per_image = p.tiles_per_image;
+  e.num_m_tiles = p.num_tiles; e.num_n_tiles = 1; e.batch = a.batch;
+  e.up2 = 0; e.cout = a.cout; e.cout_real = a.cout;
+  e.bias = a.bias; e.rowvec = a.rowvec; e.ld_rowvec = a.ld_rowvec;
+  e.res = (const bf16*)a.res; e.ldres = a.ldres; e.res_mod = a.res_mod;
+  e.y = (bf16*)a.y; e.ldy = a.ldy;
+  e.fin_w = a.fin_w; e.fin_b = a.fin_b; e.fin_out = a.fin_out; e.fin_cout = a.fin_cout;
+  e.debug = p.debug | ((getenv("LDM_EPI_DEBUG") ? atoi(getenv("LDM_EPI_DEBUG")) : 0) << 16);
+  // ---- fused GroupNorm plan (conv_epilogue.cuh): a sample always spans tiles_per_image tiles -> packet exchange
+  const ConvGn& g = a.gn;
+  e.gn_mode = g.mode;
+  e.gn_G = 1; e.gn_cpg = a.cout; e.gn_silu = 0; e.gn_nvar = 1; e.gn_var_rows = 0; e.gn_nslots = 1; e.gn_cross = 0; e.gn_upt = 1;
+  e.gn_eps = g.eps; e.gn_tag = g.tag; e.gn_gamma = g.gamma; e.gn_beta = g.beta; e.gn_rowvec = g.rowvec; e.gn_ld_rowvec = g.ld_rowvec;
+  e.gn_res = (const bf16*)g.res; e.gn_ldres = g.ldres; e.gn_scratch = g.scratch;
+  if (g.mode) {
+    LDM_REQUIRE(g.mode == 1 || g.mode == 2, "conv_halo: GroupNorm epilogue mode %d unknown", g.mode);
+    LDM_REQUIRE(!a.fin_out && a.y, "conv_halo: the GroupNorm epilogue needs a plain NHWC output");
+    LDM_REQUIRE(g.groups >= 1 && a.cout % g.groups == 0 && (a.cout / g.groups) % 8 == 0, "conv_halo: GroupNorm groups %d vs Cout %d", g.groups, a.cout);
+    LDM_REQUIRE(g.nvar == 1 || (g.nvar == 2 && g.var_rows >= a.batch && g.rowvec), "conv_halo: GroupNorm variants need a row vector and var_rows >= batch");
+    LDM_REQUIRE(g.mode == 1 || (g.gamma && g.beta && !a.res && !a.rowvec), "conv_halo: GroupNorm mode 2 takes gamma/beta and no pre-norm residual / row vector");
+    LDM_REQUIRE(!g.res || g.ldres % 8 == 0, "conv_halo: GroupNorm residual stride must be a multiple of 8");
+    e.gn_G = g.groups; e.gn_cpg = a.cout / g.groups; e.gn_silu = g.silu; e.gn_nvar = g.nvar; e.gn_var_rows = g.var_rows;
+    LDM_REQUIRE(g.mode == 1 || a.cout <= EPI_FULL_VEC, "conv_halo: GroupNorm mode 2 supports at most %d channels", EPI_FULL_VEC);
+    e.gn_upt = p.tiles_per_image; e.gn_cross = (g.mode == 2 && p.tiles_per_image > 1) ? 1 : 0;
+    e.gn_nslots = p.tiles_per_image * (g.groups == 1 ? a.cout / 64 : 1);
+    if (g.mode == 1)   // warp-local partial sums: (32-position block of the padded plane) x (group, or 32-column chunk)
+      e.gn_nslots = p.tiles_per_image * 4 * (g.groups == 1 ? a.cout / 32 : (a.cout / g.groups > 32 ? a.cout / g.groups / 32 : 1));
+    LDM_REQUIRE(g.mode != 2 || g.groups * g.nvar * e.gn_nslots <= 256, "conv_halo: GroupNorm packet fan-in too large");
+    const int64_t need = (int64_t)a.batch * g.groups * g.nvar * e.gn_nslots * (g.mode == 1 ? 8 : 16);
+    LDM_REQUIRE(g.mode == 2 && !e.gn_cross ? true : (g.scratch && g.scratch_bytes >= need && ((uintptr_t)g.scratch & 15) == 0),
+                "conv_halo: GroupNorm scratch missing / too small (need %lld bytes)", (long long)need);
+    LDM_REQUIRE(g.mode != 2 || !e.gn_cross || g.tag != 0, "conv_halo: GroupNorm packets need a non-zero tag");
+    if (g.nslots_out) *g.nslots_out = e.gn_nslots;
+  }
   // shared-memory plan: filter resident if it leaves room for >= 2 slabs, else a streaming ring of 8 tiles
   const int b_tile = a.cout * BLOCK_K * 2;
-  // barriers (1 KB) + bias / projection vectors (3 KB) + projection cross-warp sums (4 KB) + alignment slack
-  const int budget = 227 * 1024 - 9216;
+  // barriers (1 KB) + the epilogue's staging area + alignment slack
+  const int fixed = 1024 + epi_smem_bytes(a.cout) + 1024;
+  const int budget = 227 * 1024 - fixed;
   if ((int64_t)p.n_kb * b_tile + 2 * p.a_stage_bytes <= budget && p.n_kb <= 32) p.b_stages = p.n_kb;
   else p.b_stages = 8;
   p.a_stages = (budget - p.b_stages * b_tile) / p.a_stage_bytes;
   if (p.a_stages > 8) p.a_stages = 8;
   LDM_REQUIRE(p.a_stages >= 2, "conv_halo: shared memory plan failed (cout %d, %d k-blocks)", a.cout, p.n_kb);
-  const int smem = p.b_stages * b_tile + p.a_stages * p.a_stage_bytes + 8192 + 1024;
+  const int smem = p.b_stages * b_tile + p.a_stages * p.a_stage_bytes + fixed;
   CUtensorMap ma, ma2, mb;
-  if (int rc = make_slab_map(&ma, a.x, a.ldx, a.cin, a.batch, a.height, a.width, p.P, p.RB)) return rc;
+  if (int rc = make_slab_map(&ma, a.x, a.ldx, a.cin, a.batch, a.height, a.width, p.P, RB)) return rc;
   if (a.x2) {
-    if (int rc = make_slab_map(&ma2, a.x2, a.ldx2, a.cin2, a.batch, a.height, a.width, p.P, p.RB)) return rc;
+    if (int rc = make_slab_map(&ma2, a.x2, a.ldx2, a.cin2, a.batch, a.height, a.width, p.P, RB)) return rc;
   } else {
     ma2 = ma;
   }
   if (int rc = make_filter_map(&mb, a.w, a.cout, p.n_kb * BLOCK_K, a.cout)) return rc;
   const int grid = p.num_tiles < g_num_sms_h ? p.num_tiles : g_num_sms_h;
-  if (a.cout == 64) LDM_CUDA(ldm_launch_pdl(conv_halo_kernel<64>, dim3(grid), dim3(320), (size_t)smem, st, ma, ma2, mb, p));
-  else LDM_CUDA(ldm_launch_pdl(conv_halo_kernel<128>, dim3(grid), dim3(320), (size_t)smem, st, ma, ma2, mb, p));
+#define HALO_GO(BN, GMV) LDM_CUDA(ldm_launch_pdl(conv_halo_kernel<BN, GMV>, dim3(grid), dim3(320), (size_t)smem, st, ma, ma2, mb, p))
+  if (a.cout == 64) {
+    if (e.gn_mode == 0) HALO_GO(64, 0); else if (e.gn_mode == 1) HALO_GO(64, 1); else HALO_GO(64, 2);
+  } else {
+    if (e.gn_mode == 0) HALO_GO(128, 0); else if (e.gn_mode == 1) HALO_GO(128, 1); else HALO_GO(128, 2);
+  }
+#undef HALO_GO
   LDM_LAUNCHED("conv_halo");
   return 0;
 }

@@ -172,5 +172,6 @@ int k_conv(const ConvArgs& a, int impl, cudaStream_t st) {
     if (k_conv_halo_applicable(a)) return k_conv_halo(a, st);
     return k_conv_tc(a, st);
   }
+  LDM_REQUIRE(a.gn.mode == 0, "conv: the fused GroupNorm epilogue exists only in the tcgen05 kernels (bf16, impl 0)");
   return k_conv_simt(a, st);
 }

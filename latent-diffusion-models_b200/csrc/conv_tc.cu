@@ -27,6 +27,7 @@
 
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "conv_epilogue.cuh"
 
 // timeline probe (LDM_TC_DEBUG=1): CTA 0 records globaltimer stamps of its first tiles
 __device__ unsigned long long g_tc_dbg[1024];
@@ -49,25 +50,15 @@ __device__ __forceinline__ unsigned long long gtime_tc() {
 constexpr int A_STAGE_BYTES = TILE_M * BLOCK_K * 2;
 
 struct TcParams {
-  int M;          // valid rows
-  int H, W;       // spatial size
+  int H;          // image height
   int HB, NB;     // M-tile box: NB images x HB rows x W columns = 128 pixels
   int num_m_tiles, num_n_tiles;
   int kb_main;    // k-blocks from the main source = taps * cin/64
   int kb_total;   // + cin2/64
   int cin_blocks; // cin/64
   int taps;       // 1 or 9
-  int cout;       // GEMM N
-  int cout_real;  // channels of the output tensor (cout/4 for up2)
-  int up2;
-  const float* bias;
-  const float* rowvec; int ld_rowvec;
-  const bf16* res; int ldres;
-  bf16* y; int ldy;   // may be null when only the fused projection output is wanted
-  // fused trailing 1x1 projection (the UNet's final_conv.1, src/UNet.py:347): out[b][o][pix] = fin_b[o] +
-  // sum_c fin_w[o][c] * row[c], computed from the fp32 accumulators; requires one N-tile (BLOCK_N == cout)
-  const float* fin_w; const float* fin_b; float* fin_out; int fin_cout;
   int debug;
+  EpiP e;         // everything the epilogue warps need (conv_epilogue.cuh)
 };
 
 // MT: M-tiles (128 output pixels each) a CTA works on at once.  They share every weight k-block: the kernel is bound by
@@ -78,13 +69,16 @@ struct TcCfg {
   static constexpr int A_BYTES = MT * A_STAGE_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = MT == 1 ? (BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4)) : (BLOCK_N == 64 ? 5 : 4);
-  static constexpr int TMEM_COLS = 2 * MT * BLOCK_N;  // double-buffered accumulators (power of two >= 32)
-  // mbarriers + TMEM slot (1 KB), 2 bias slices, 128 x 8 floats for the fused projection's cross-warp sum
-  static constexpr int BAR_BYTES = 1024 + 2 * BLOCK_N * 4 + 4096;
+  // accumulator ring: as deep as TMEM allows, at most 4 (the fused GroupNorm defers its second pass by one work unit)
+  static constexpr int NACC = 512 / (MT * BLOCK_N) >= 4 ? 4 : 2;
+  static constexpr int TMEM_COLS = NACC * MT * BLOCK_N;  // power of two >= 32
+  // mbarriers + TMEM slot (1 KB) + the epilogue's staging area
+  static constexpr int BAR_BYTES = 1024 + epi_smem_bytes(BLOCK_N);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory plan exceeds 227 KB");
 };
 
-template <int BLOCK_N, int MT = 1>
+template <int BLOCK_N, int MT = 1, int GM = 0>
 __global__ void __launch_bounds__(320, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
@@ -97,10 +91,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t smem_b = smem_base + STAGES * Cfg::A_BYTES;
   const uint32_t bars = smem_base + STAGES * Cfg::STAGE_BYTES;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
-  const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
-  const uint32_t tmem_slot = tempty_bar + 16;
-  float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 1024 - smem_u32(smem_raw)));  // [2][BLOCK_N]
-  float* s_fin = s_bias + 2 * BLOCK_N;                                                      // [128][8]
+  constexpr int NACC = Cfg::NACC;
+  const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 8 * NACC;
+  const uint32_t tmem_slot = tempty_bar + 8 * NACC;
+  float* s_epi = reinterpret_cast<float*>(smem_raw + (bars + 1024 - smem_u32(smem_raw)));   // epilogue staging area
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -114,7 +108,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NACC; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
       mbar_init(tempty_bar + 8 * i, 8);  // one arrival per epilogue warp
     }
@@ -186,9 +180,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       int iter = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
-        const int acc = iter & 1;
+        const int acc = iter % NACC;
         TC_STAMP(0);
-        mbar_wait(tempty_bar + 8 * acc, ((iter >> 1) & 1) ^ 1);
+        mbar_wait(tempty_bar + 8 * acc, ((iter / NACC) & 1) ^ 1);
         TC_STAMP(1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * MT * BLOCK_N;
@@ -215,155 +209,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    // 8 epilogue warps: two per TMEM lane quarter, each taking half of the tile's columns.  One warp per scheduler
-    // is latency-bound (every TMEM load / convert / store chain is exposed); two overlap each other's stalls.
-    const int quarter = warp & 3;             // TMEM lanes [32*quarter, +32) are the ones this warp may read
-    const int half = (warp - 2) >> 2;         // column half of the tile
-    constexpr int COLS = BLOCK_N / 2;         // columns per warp
-    const int row = quarter * 32 + lane;
-    const bool keep_l2 = (p.debug & 8) == 0;      // L2 evict_last on the output (2688 -> 2678 us per timestep); debug bit 3 = off
-    const uint64_t l2pol = l2_evict_last_policy();
-    const int et = threadIdx.x - 64;          // 0..255 among the epilogue threads
-    // loop-invariant parameters in registers (no constant-bank traffic per tile)
-    const int num_n_tiles = p.num_n_tiles, M = p.M, H = p.H, W = p.W, hw = p.H * p.W, up2 = p.up2;
-    const int cout_real = p.cout_real, cout = p.cout, ldy = p.ldy, ldres = p.ldres, ld_rowvec = p.ld_rowvec;
-    const int fin_cout = p.fin_cout;
-    bf16* const y = p.y;
-    const bf16* const res = p.res;
-    const float* const bias = p.bias;
-    const float* const rowvec = p.rowvec;
-    const float* const fin_w = p.fin_w;
-    float* const fin_out = p.fin_out;
-    int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
-      const int um = tile / num_n_tiles, nt = tile - um * num_n_tiles;
-      const int acc = iter & 1;
-#pragma unroll 1
-      for (int sub = 0; sub < MT; ++sub) {
-      const int mt = um * MT + sub;
-      if (mt >= p.num_m_tiles) break;   // uniform over the CTA
-      const int m = mt * TILE_M + row;
-      const bool valid = m < M && !(p.debug & 2);
-      const int img = valid ? m / hw : 0;
-      // output placement
-      const int ncol0 = nt * BLOCK_N;              // GEMM column of this tile
-      const int q = up2 ? ncol0 / cout_real : 0;
-      const int cc0 = up2 ? ncol0 - q * cout_real : ncol0;
-      int64_t orow = m;
-      if (up2) {
-        const int r_ = m / W, w_ = m - r_ * W, h_ = r_ % H;
-        orow = ((int64_t)img * 2 * H + 2 * h_ + (q >> 1)) * (2 * W) + 2 * w_ + (q & 1);
-      }
-      const int cw = half * COLS;                  // this warp's first column inside the tile
-      bf16* yrow = y + orow * ldy + cc0 + cw;
-      const bf16* rrow = res ? res + (int64_t)m * ldres + cc0 + cw : nullptr;
-      const float* rvrow = rowvec ? rowvec + (int64_t)img * ld_rowvec + cc0 + cw : nullptr;
-      // Everything the accumulator will be combined with is requested BEFORE the wait for the MMAs: the tile's bias
-      // slice goes to shared memory (L1 is tiny under the maximum shared-memory carve-out, a __ldg would pay L2
-      // latency per chunk), the first residual chunk to registers.
-      float* sb = s_bias + acc * BLOCK_N;
-      for (int c = et; c < BLOCK_N; c += 256) sb[c] = bias ? __ldg(bias + cc0 + c) : 0.f;
-      uint4 rr[4];
-      if (rrow && valid) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rr[j] = __ldg(reinterpret_cast<const uint4*>(rrow) + j);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (warp == 2 && lane == 0) TC_STAMP(4);
-      if (sub == 0) {
-        if (lane == 0) mbar_wait(tfull_bar + 8 * acc, (iter >> 1) & 1);
-        __syncwarp();
-      }
-      if (warp == 2 && lane == 0) TC_STAMP(5);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * MT + sub) * BLOCK_N + cw;
-      float fo[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-      for (int c0 = 0; c0 < COLS; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-        uint4 rn[4];  // next chunk's residual, in flight while this chunk is processed
-        if (rrow && valid && c0 + 32 < COLS) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rn[j] = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + 32) + j);
-        }
-        tmem_ld_wait();
-        if (valid) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sb + cw + c0 + j);
-            v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-            v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-          }
-          if (rvrow) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b4 = __ldg(reinterpret_cast<const float4*>(rvrow + c0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          }
-          if (rrow) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float2 f = __bfloat1622float2(h2[u]);
-                v[8 * j + 2 * u] += f.x; v[8 * j + 2 * u + 1] += f.y;
-              }
-            }
-          }
-          if (y) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float t8[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) t8[u] = v[j + u];
-              if (keep_l2) store_chunk_keep(yrow + c0 + j, t8, l2pol); else store_chunk(yrow + c0 + j, t8);
-            }
-          }
-          if (fin_out) {
-            for (int o = 0; o < fin_cout; ++o) {
-              const float* wrow = fin_w + o * cout + cw + c0;
-              float s = 0.f;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + j));
-                s = fmaf(v[j], w4.x, s); s = fmaf(v[j + 1], w4.y, s);
-                s = fmaf(v[j + 2], w4.z, s); s = fmaf(v[j + 3], w4.w, s);
-              }
-#pragma unroll
-              for (int u = 0; u < 8; ++u)
-                if (u == o) fo[u] += s;
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rr[j] = rn[j];
-      }
-      if (fin_out) {
-        // the two column halves of a row live in two warps: combine through shared memory, half 0 writes
-        float* fx = s_fin + row * 8;
-        if (half == 1) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) fx[u] = fo[u];
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (half == 0 && valid) {
-          const int pix = m - img * hw;
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (u < fin_cout) fin_out[((int64_t)img * fin_cout + u) * hw + pix] = fo[u] + fx[u] + __ldg(p.fin_b + u);
-        }
-      }
-      }   // sub-tiles
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_relaxed(tempty_bar + 8 * acc);
-      if (warp == 2 && lane == 0) TC_STAMP(6);
-    }
+    // ===================== epilogue (warps 2..9): conv_epilogue.cuh =====================
+    conv_epilogue<BLOCK_N, MT, NACC, false, GM>(p.e, tmem_base, tfull_bar, tempty_bar, s_epi, num_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -376,23 +223,26 @@ PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 int g_num_sms = 0;
 
 int tc_init() {
-  if (g_encode) return 0;
+  static bool inited[64] = {};   // function attributes (and the SM count) are per device
+  int dev = 0;
+  LDM_CUDA(cudaGetDevice(&dev));
+  if (g_encode && inited[dev & 63]) return 0;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   LDM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   LDM_REQUIRE(qres == cudaDriverEntryPointSuccess && fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
-  int dev = 0;
-  LDM_CUDA(cudaGetDevice(&dev));
   LDM_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   int cc_major = 0;
   LDM_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
   LDM_REQUIRE(cc_major == 10, "conv_tc: tcgen05 kernels need an sm_100-class GPU (found cc %d.x)", cc_major);
-  LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM_BYTES));
-  LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));
-  LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES));
-  LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, 2>::SMEM_BYTES));
-  LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, 2>::SMEM_BYTES));
+#define TC_ATTR(BN, MTV)                                                                                                         \
+  LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MTV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, MTV>::SMEM_BYTES)); \
+  LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MTV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, MTV>::SMEM_BYTES)); \
+  LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MTV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, MTV>::SMEM_BYTES))
+  TC_ATTR(64, 1); TC_ATTR(128, 1); TC_ATTR(256, 1); TC_ATTR(64, 2); TC_ATTR(128, 2);
+#undef TC_ATTR
   g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  inited[dev & 63] = true;
   return 0;
 }
 
@@ -425,7 +275,11 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& 
   using Cfg = TcCfg<BLOCK_N, MT>;
   int tiles = ((p.num_m_tiles + MT - 1) / MT) * p.num_n_tiles;
   int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  LDM_CUDA(ldm_launch_pdl(conv_tc_kernel<BLOCK_N, MT>, dim3(grid), dim3(320), (size_t)Cfg::SMEM_BYTES, st, ma, ma2, mb, p));
+  switch (p.e.gn_mode) {
+    case 0: LDM_CUDA(ldm_launch_pdl(conv_tc_kernel<BLOCK_N, MT, 0>, dim3(grid), dim3(320), (size_t)Cfg::SMEM_BYTES, st, ma, ma2, mb, p)); break;
+    case 1: LDM_CUDA(ldm_launch_pdl(conv_tc_kernel<BLOCK_N, MT, 1>, dim3(grid), dim3(320), (size_t)Cfg::SMEM_BYTES, st, ma, ma2, mb, p)); break;
+    default: LDM_CUDA(ldm_launch_pdl(conv_tc_kernel<BLOCK_N, MT, 2>, dim3(grid), dim3(320), (size_t)Cfg::SMEM_BYTES, st, ma, ma2, mb, p)); break;
+  }
   LDM_LAUNCHED("conv_tc");
   return 0;
 }
@@ -459,38 +313,99 @@ int k_conv_tc(const ConvArgs& a, cudaStream_t st) {
   const int NB = TILE_M / (W * HB);
   LDM_REQUIRE(NB == 1 || HB == H, "conv_tc: internal tiling error");
   TcParams p;
-  p.M = a.batch * H * W;
-  if (p.M == 0) return 0;
-  p.H = H; p.W = W; p.HB = HB; p.NB = NB;
-  p.num_m_tiles = (p.M + TILE_M - 1) / TILE_M;
+  EpiP& e = p.e;
+  e.M = a.batch * H * W;
+  if (e.M == 0) return 0;
+  p.H = H; p.HB = HB; p.NB = NB;
+  e.H = H; e.W = W; e.hw = H * W; e.P = 0; e.tiles_per_image = 0; e.batch = a.batch;
+  p.num_m_tiles = (e.M + TILE_M - 1) / TILE_M;
   p.taps = a.ksize * a.ksize;
   p.cin_blocks = a.cin / BLOCK_K;
   p.kb_main = p.taps * p.cin_blocks;
   p.kb_total = p.kb_main + (a.x2 ? a.cin2 / BLOCK_K : 0);
-  p.cout = a.cout;
-  p.up2 = a.up2;
-  p.cout_real = a.up2 ? a.cout / 4 : a.cout;
-  p.bias = a.bias;
-  p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec;
-  p.res = (const bf16*)a.res; p.ldres = a.ldres;
-  p.y = (bf16*)a.y; p.ldy = a.ldy;
-  p.fin_w = a.fin_w; p.fin_b = a.fin_b; p.fin_out = a.fin_out; p.fin_cout = a.fin_cout;
+  e.cout = a.cout;
+  e.up2 = a.up2;
+  e.cout_real = a.up2 ? a.cout / 4 : a.cout;
+  e.bias = a.bias;
+  e.rowvec = a.rowvec; e.ld_rowvec = a.ld_rowvec;
+  e.res = (const bf16*)a.res; e.ldres = a.ldres; e.res_mod = 0;
+  e.y = (bf16*)a.y; e.ldy = a.ldy;
+  e.fin_w = a.fin_w; e.fin_b = a.fin_b; e.fin_out = a.fin_out; e.fin_cout = a.fin_cout;
   { const char* d = getenv("LDM_TC_DEBUG"); p.debug = d ? atoi(d) : 0; }
-  LDM_REQUIRE(!a.fin_out || (a.fin_cout >= 1 && a.fin_cout <= 8 && !a.up2 && (a.cout == 64 || a.cout == 128 || a.cout == 256)),
-              "conv_tc: fused projection needs Cout in {64,128,256} and <= 8 outputs");
+  e.debug = p.debug | ((getenv("LDM_EPI_DEBUG") ? atoi(getenv("LDM_EPI_DEBUG")) : 0) << 16);
+  LDM_REQUIRE(!a.fin_out || (a.fin_cout >= 1 && a.fin_cout <= 8 && !a.up2 && (a.cout == 64 || a.cout == 128 || a.cout == 256) &&
+                             a.fin_cout * a.cout <= 768),
+              "conv_tc: fused projection needs Cout in {64,128,256} and fin_cout * Cout <= 768");
   LDM_REQUIRE(a.y || a.fin_out, "conv_tc: no output requested");
   const int ktot = p.kb_total * BLOCK_K;
 
   // tile-N: the widest of 256/128/64 that divides Cout (and the up2 quadrant) and still yields >= 1 wave
   int block_n = 64;
-  const int nlimit = p.cout_real;
+  const int nlimit = e.cout_real;
   if (a.fin_out) block_n = a.cout;  // the whole channel row must sit in one accumulator tile
   else
   for (int bn : {256, 128}) {
     if (a.cout % bn == 0 && nlimit % bn == 0 && (int64_t)p.num_m_tiles * (a.cout / bn) >= g_num_sms) { block_n = bn; break; }
   }
   LDM_REQUIRE(nlimit % block_n == 0, "conv_tc: output channels (%d) must be a multiple of %d", nlimit, block_n);
+  // two M-tiles per CTA when that still leaves every SM at least two work units
+  static const int mt_env = getenv("LDM_TC_MT") ? atoi(getenv("LDM_TC_MT")) : 2;
+  bool pair = mt_env == 2 && block_n <= 128 && !a.fin_out && (int64_t)(p.num_m_tiles / 2) * (a.cout / block_n) >= 2 * g_num_sms;
+
+  // ---- fused GroupNorm plan (conv_epilogue.cuh)
+  const ConvGn& g = a.gn;
+  e.gn_mode = g.mode;
+  e.gn_G = 1; e.gn_cpg = a.cout; e.gn_silu = 0; e.gn_nvar = 1; e.gn_var_rows = 0; e.gn_nslots = 1; e.gn_cross = 0; e.gn_upt = 1;
+  e.gn_eps = g.eps; e.gn_tag = g.tag; e.gn_gamma = g.gamma; e.gn_beta = g.beta; e.gn_rowvec = g.rowvec; e.gn_ld_rowvec = g.ld_rowvec;
+  e.gn_res = (const bf16*)g.res; e.gn_ldres = g.ldres; e.gn_scratch = g.scratch;
+  if (g.mode) {
+    LDM_REQUIRE(g.mode == 1 || g.mode == 2, "conv_tc: GroupNorm epilogue mode %d unknown", g.mode);
+    LDM_REQUIRE(!a.up2 && !a.fin_out && a.y, "conv_tc: the GroupNorm epilogue needs a plain NHWC output");
+    LDM_REQUIRE(g.groups >= 1 && a.cout % g.groups == 0 && (a.cout / g.groups) % 8 == 0, "conv_tc: GroupNorm groups %d vs Cout %d", g.groups, a.cout);
+    LDM_REQUIRE(g.nvar == 1, "conv_tc: GroupNorm variants are only implemented in the halo kernel");
+    LDM_REQUIRE(g.mode == 1 || (g.gamma && g.beta && !a.res && !a.rowvec), "conv_tc: GroupNorm mode 2 takes gamma/beta and no pre-norm residual / row vector");
+    LDM_REQUIRE(!g.res || g.ldres % 8 == 0, "conv_tc: GroupNorm residual stride must be a multiple of 8");
+    const int cpg = a.cout / g.groups, hw = H * W;
+    if (g.groups > 1) while (block_n % cpg != 0 && block_n < 256) block_n *= 2;   // a group never straddles N tiles
+    LDM_REQUIRE(g.groups == 1 || (block_n % cpg == 0 && a.cout % block_n == 0), "conv_tc: GroupNorm groups of %d channels do not fit an N tile", cpg);
+    int n_tiles = a.cout / block_n;
+    auto geometry_ok = [&](int mt) {
+      const int ru = TILE_M * mt;
+      return hw >= ru ? hw % ru == 0 : (ru % hw == 0 && ru / hw <= 8 && hw >= 16 && mt == 1);
+    };
+    if (pair && !geometry_ok(2)) pair = false;
+    LDM_REQUIRE(geometry_ok(pair ? 2 : 1), "conv_tc: GroupNorm epilogue does not support %dx%d images", H, W);
+    LDM_REQUIRE(g.mode == 1 || a.cout <= EPI_FULL_VEC, "conv_tc: GroupNorm mode 2 supports at most %d channels", EPI_FULL_VEC);
+    const int upt = hw >= TILE_M ? hw / TILE_M : 1;          // M tiles per sample
+    const int spu = hw >= TILE_M ? 1 : TILE_M / hw;          // samples per M tile
+    // {a, b} / row-vector rows the epilogue keeps per unit: one per sample in the tile
+    if (spu > epi_vec_rows(block_n)) block_n = 128;
+    auto is_cross = [&](int mt, int bn) { return (hw > TILE_M * mt || (g.groups == 1 && a.cout / bn > 1)) ? 1 : 0; };
+    int cross = is_cross(pair ? 2 : 1, block_n);
+    if (g.mode == 2 && cross) {
+      // deferred second pass: needs the 4-deep accumulator ring (MT * BLOCK_N <= 128)
+      if (pair && block_n > 64) pair = false;
+      if (block_n > 128) block_n = 128;
+      cross = is_cross(pair ? 2 : 1, block_n);
+    }
+    LDM_REQUIRE(a.cout % block_n == 0 && (g.groups == 1 || block_n % cpg == 0), "conv_tc: GroupNorm tile plan failed (Cout %d, tile %d)", a.cout, block_n);
+    n_tiles = a.cout / block_n;
+    e.gn_G = g.groups; e.gn_cpg = cpg; e.gn_silu = g.silu; e.gn_upt = upt; e.gn_cross = g.mode == 2 ? cross : 0;
+    e.gn_nslots = upt * (g.groups == 1 ? a.cout / 64 : 1);
+    if (g.mode == 1)   // warp-local partial sums: (32-row block, or a whole small sample) x (group, or 32-column chunk)
+      e.gn_nslots = (hw >= 32 ? hw / 32 : 1) * (g.groups == 1 ? a.cout / 32 : (cpg > 32 ? cpg / 32 : 1));
+    LDM_REQUIRE(g.mode != 2 || !cross || spu * (g.groups == 1 ? 1 : block_n / cpg) * e.gn_nslots <= 256, "conv_tc: GroupNorm packet fan-in too large");
+    LDM_REQUIRE(!(cross && g.rowvec && spu > 1), "conv_tc: GroupNorm row vectors with several samples per tile need whole groups per tile");
+    if (g.mode == 1) {
+      LDM_REQUIRE(g.scratch && g.scratch_bytes >= (int64_t)a.batch * g.groups * e.gn_nslots * 8, "conv_tc: GroupNorm statistics buffer too small");
+    } else if (cross) {
+      LDM_REQUIRE(g.scratch && g.tag != 0 && g.scratch_bytes >= (int64_t)a.batch * g.groups * e.gn_nslots * 16 && ((uintptr_t)g.scratch & 15) == 0,
+                  "conv_tc: GroupNorm packet buffer missing / too small (need %lld bytes)", (long long)a.batch * g.groups * e.gn_nslots * 16);
+    }
+    if (g.nslots_out) *g.nslots_out = e.gn_nslots;
+  }
   p.num_n_tiles = a.cout / block_n;
+  e.num_m_tiles = p.num_m_tiles; e.num_n_tiles = p.num_n_tiles;
 
   CUtensorMap ma, ma2, mb;
   if (int rc = make_act_map(&ma, a.x, a.ldx, a.cin, a.batch, H, W, HB, NB)) return rc;
@@ -500,9 +415,6 @@ int k_conv_tc(const ConvArgs& a, cudaStream_t st) {
     ma2 = ma;
   }
   if (int rc = make_weight_map(&mb, a.w, a.cout, ktot, block_n)) return rc;
-  // two M-tiles per CTA when that still leaves every SM at least two work units
-  static const int mt_env = getenv("LDM_TC_MT") ? atoi(getenv("LDM_TC_MT")) : 2;
-  const bool pair = mt_env == 2 && block_n <= 128 && !a.fin_out && (int64_t)(p.num_m_tiles / 2) * p.num_n_tiles >= 2 * g_num_sms;
   switch (block_n) {
     case 256: return launch_tc<256, 1>(ma, ma2, mb, p, st);
     case 128: return pair ? launch_tc<128, 2>(ma, ma2, mb, p, st) : launch_tc<128, 1>(ma, ma2, mb, p, st);

@@ -179,11 +179,13 @@ __global__ void p_sample_kernel(const float4* __restrict__ xt, const float4* __r
                                 const float4* __restrict__ eu, float cfg, const int64_t* __restrict__ t_dev,
                                 int t_stride, const float4* __restrict__ coef, int T, const float* __restrict__ noise,
                                 int64_t noise_t_stride, uint64_t seed, uint64_t sample_offset,
-                                float4* __restrict__ out, int64_t n4, int64_t total4) {
+                                const uint64_t* __restrict__ seed_dev, float4* __restrict__ out, int64_t n4, int64_t total4) {
   pdl_wait();
   pdl_trigger();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
+  // device-resident {seed, sample_offset}: a captured sampler step is replayed with fresh seeds without re-capturing
+  if (seed_dev) { seed = seed_dev[0]; sample_offset = seed_dev[1]; }
   // the reference gathers alpha/alpha_bar per sample but takes the noise branch on t[0] (src/DDPM.py:74-85)
   int64_t t = t_dev[0];
   t = t < 0 ? 0 : (t >= T ? T - 1 : t);
@@ -215,13 +217,13 @@ __global__ void p_sample_kernel(const float4* __restrict__ xt, const float4* __r
 }
 int k_p_sample(const float* xt, const float* eps_c, const float* eps_u, float cfg_scale, const int64_t* t_dev,
                int t_stride, const float* coef, int n_steps, const float* noise, int64_t noise_t_stride, uint64_t seed,
-               uint64_t sample_offset, float* out, int batch, int64_t n_per_sample, cudaStream_t st) {
+               uint64_t sample_offset, float* out, int batch, int64_t n_per_sample, cudaStream_t st, const uint64_t* seed_dev) {
   LDM_REQUIRE(n_per_sample % 4 == 0, "p_sample: n_per_sample must be a multiple of 4");
   int64_t n4 = n_per_sample / 4, total4 = n4 * batch;
   if (total4 == 0) return 0;
   LDM_CUDA(ldm_launch_pdl(p_sample_kernel, dim3((unsigned)ceil_div64(total4, 256)), dim3(256), 0, st, (const float4*)xt,
                           (const float4*)eps_c, (const float4*)eps_u, cfg_scale, t_dev, t_stride, (const float4*)coef, n_steps, noise,
-                          noise_t_stride, seed, sample_offset, (float4*)out, n4, total4));
+                          noise_t_stride, seed, sample_offset, seed_dev, (float4*)out, n4, total4));
   LDM_LAUNCHED("p_sample");
   return 0;
 }

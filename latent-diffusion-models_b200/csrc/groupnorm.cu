@@ -264,7 +264,22 @@ gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int l
   const int n = blockIdx.y;
   const int cpp = C / V, cpg = cpp / G;
   const bf16* xs = x + (int64_t)(x_mod > 0 ? n % x_mod : n) * HW * ldx;
-  if (threadIdx.x < G) {
+  if (threadIdx.x < G && splits < 0) {
+    // un-pivoted sums {S, Q} left by the producing convolution's epilogue (conv_epilogue.cuh, mode 1):
+    // part[(n * G + g) * nslots + slot], nslots = -splits
+    const int gg = threadIdx.x, ns = -splits;
+    double a = 0.0, b = 0.0;
+    for (int sp = 0; sp < ns; ++sp) {
+      const float2 v = part[((int64_t)n * G + gg) * ns + sp];
+      a += (double)v.x; b += (double)v.y;
+    }
+    const double cnt = (double)HW * (double)(cpg * V);
+    const double m1 = a / cnt;
+    double var = b / cnt - m1 * m1;
+    if (var < 0.0) var = 0.0;
+    s_mean[gg] = (float)m1;
+    s_rstd[gg] = (float)(1.0 / sqrt(var + (double)eps));
+  } else if (threadIdx.x < G) {
     const int gg = threadIdx.x;
     float a = 0.f, b = 0.f;
     for (int sp = 0; sp < splits; ++sp) {  // fixed order
@@ -629,6 +644,26 @@ int gn_launch(const void* x, int ldx, void* y, int ldy, const void* res, int ldr
 }
 
 }  // namespace
+
+// Apply only (bf16, streaming kernel): the statistics are the un-pivoted {S, Q} slots a convolution epilogue left
+// (ConvGn mode 1): part[(n * groups + g) * nslots + slot].
+int k_group_norm_apply_raw(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
+                           const float* beta, int batch, int hw, int channels, int groups, float eps, int silu, const void* part,
+                           int nslots, cudaStream_t st) {
+  LDM_REQUIRE(channels % groups == 0 && (channels / groups) % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && (!res || ldres % 8 == 0) &&
+                  channels / 8 <= GS_THREADS && part && nslots >= 1 && groups <= GN_MAX_GROUPS,
+              "group_norm_apply_raw: unsupported shape");
+  if (batch == 0 || hw == 0) return 0;
+  int threads, ppi, splits, pps;
+  gn_stream_geometry(hw, channels, threads, ppi, splits, pps);
+  int ppb = ppi * 8;
+  if (ppb > hw) ppb = hw;
+  const dim3 grid((hw + ppb - 1) / ppb, batch);
+  LDM_CUDA(ldm_launch_pdl(gn_apply_kernel<false>, grid, dim3(threads), 0, st, (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)res,
+                          ldres, gamma, beta, (const float*)nullptr, 0, (const float2*)part, -nslots, hw, channels, groups, eps, silu, ppb, 0));
+  LDM_LAUNCHED("gn_apply");
+  return 0;
+}
 
 // Statistics only (bf16, no rowvec): part[(n*splits + s)*groups + g] = {sum(x-K), sum((x-K)^2)} with the pivot
 // K = x[n][pixel 0][first channel of group g].  Consumers rebuild mean / rstd from it (see gn_apply_kernel).

@@ -18,7 +18,8 @@ int k_q_sample(const float* x0, const int64_t* t, const float* alpha_bar, int n_
 // t_stride: 0 = one batch-constant timestep at t_dev[0]; 1 = per-sample t_dev[b] (noise branch still on t_dev[0])
 int k_p_sample(const float* xt, const float* eps_c, const float* eps_u, float cfg_scale, const int64_t* t_dev,
                int t_stride, const float* coef, int n_steps, const float* noise, int64_t noise_t_stride, uint64_t seed,
-               uint64_t sample_offset, float* out, int batch, int64_t n_per_sample, cudaStream_t st);
+               uint64_t sample_offset, float* out, int batch, int64_t n_per_sample, cudaStream_t st,
+               const uint64_t* seed_dev = nullptr);   // seed_dev: device {seed, sample_offset} overriding the two values
 int k_set_i64(int64_t* p, int64_t v, cudaStream_t st);
 int k_add_i64(int64_t* p, int64_t v, cudaStream_t st);
 
@@ -66,6 +67,9 @@ int k_group_norm_mod(const void* x, int ldx, void* y, int ldy, const void* res, 
                      const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
                      float eps, int silu, int dtype, void* workspace, int x_mod, cudaStream_t st);
 bool k_group_norm_streams(int hw, int channels, int dtype);
+int k_group_norm_apply_raw(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
+                           const float* beta, int batch, int hw, int channels, int groups, float eps, int silu, const void* part,
+                           int nslots, cudaStream_t st);
 
 // ---- attention.cu
 int k_linear_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, cudaStream_t st);
@@ -84,6 +88,25 @@ int k_fold_prenorm_qkv(const float* wqkv /*[384][cin] fp32*/, const float* gamma
 int k_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, cudaStream_t st);
 
 // ---- conv (conv_simt.cu / conv_tc.cu)
+// GroupNorm fused into the epilogue of the tcgen05 convolutions (conv_epilogue.cuh): the conv that PRODUCES a tensor also
+// takes its GroupNorm statistics (mode 1) or stores it already normalised (mode 2) -- src/UNet.py:52-58,106,147,20.
+struct ConvGn {
+  int mode = 0;                  // 0 off | 1 statistics only -> scratch | 2 normalise (+SiLU) (+residual) before the store
+  int groups = 1;
+  int silu = 0;
+  int nvar = 1, var_rows = 0;    // mode 2, halo kernel: sample n is normalised nvar times with rowvec row n + k*var_rows and
+                                 // stored as image n + k*var_rows (the sampler's cond / uncond halves share the convolution)
+  float eps = 1e-5f;
+  const float* gamma = nullptr; const float* beta = nullptr;   // [cout]
+  const float* rowvec = nullptr; int ld_rowvec = 0;            // per-image channel vector added BEFORE the statistics
+  const void* res = nullptr; int ldres = 0;                    // NHWC tensor added AFTER the normalisation (Residual)
+  // mode 1: float2 [batch][groups][nslots] partial sums {S, Q} of the stored values (consumer adds the slots in order)
+  // mode 2: 16-byte packets [batch][groups][nvar][nslots]; the caller zeroes the area before the first launch that uses
+  //         it and gives every launch since then a different non-zero tag
+  void* scratch = nullptr; int64_t scratch_bytes = 0;
+  unsigned tag = 0;
+  int* nslots_out = nullptr;     // receives nslots
+};
 struct ConvArgs {
   const void* x; int ldx; int cin;        // main source, NHWC [batch,H,W,*]
   const void* x2; int ldx2; int cin2;     // optional K-concatenated 1x1 source (same spatial size)
@@ -97,6 +120,7 @@ struct ConvArgs {
   float* fin_out = nullptr;
   int fin_cout = 0;
   int res_mod = 0;                        // > 0: the residual of image n is read from image n % res_mod (halo kernel only)
+  ConvGn gn;                              // fused GroupNorm epilogue (tcgen05 kernels only)
   int cout;                               // GEMM N (for up2: 4 * output channels)
   int batch, height, width;
   int ksize;                              // 1 or 3 (pad = ksize/2)

@@ -26,13 +26,13 @@ struct ldm_sampler {
   cudaStream_t own = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   long long step_kernels = 0;  // kernels inside one captured step (for ldm_launch_count under graph replay)
-  // capture key: everything baked into the graph's kernel arguments
+  // capture key: everything baked into the graph's kernel arguments.  The Philox seed and the global sample offset are
+  // NOT part of it: they live in device memory next to the step counter, so one captured step serves every call
+  // (generate_images.py makes ten batch-1 calls with fresh seeds: one capture instead of ten)
   struct Key {
     const void *x, *y, *coef, *noise, *ws;
-    uint64_t seed, sample_offset;
     bool operator==(const Key& o) const {
-      return x == o.x && y == o.y && coef == o.coef && noise == o.noise && ws == o.ws && seed == o.seed &&
-             sample_offset == o.sample_offset;
+      return x == o.x && y == o.y && coef == o.coef && noise == o.noise && ws == o.ws;
     }
   } key{};
 };
@@ -84,7 +84,7 @@ static int sampler_step(ldm_sampler* s, float* x, const int64_t* y, const float*
                                ws + s->off_unet, s->total - s->off_unet, st);
   if (rc) return rc;
   rc = k_p_sample(x, eps, cfg ? eps + (int64_t)B * s->n : nullptr, s->d.cfg_scale, tdev, 0, coef, s->d.n_steps, noise,
-                  noise ? (int64_t)B * s->n : 0, seed, sample_offset, x, B, s->n, st);
+                  noise ? (int64_t)B * s->n : 0, seed, sample_offset, x, B, s->n, st, (const uint64_t*)(tdev + 1));
   if (rc) return rc;
   return k_add_i64(tdev, -1, st);
 }
@@ -130,6 +130,8 @@ static int sampler_run_on(ldm_sampler* s, float* x, int x_is_init, const int64_t
   if (num_steps == 0) return 0;
   int rc = k_set_i64((int64_t*)(ws + s->off_t), first_step, st);
   if (rc) return rc;
+  if ((rc = k_set_i64((int64_t*)(ws + s->off_t) + 1, (int64_t)seed, st))) return rc;
+  if ((rc = k_set_i64((int64_t*)(ws + s->off_t) + 2, (int64_t)sample_offset, st))) return rc;
   if (!s->d.use_graph) {
     for (int i = 0; i < num_steps; ++i) {
       rc = sampler_step(s, x, y, coef, noise, seed, sample_offset, ws, st);
@@ -137,7 +139,7 @@ static int sampler_run_on(ldm_sampler* s, float* x, int x_is_init, const int64_t
     }
     return 0;
   }
-  ldm_sampler::Key key{x, y, coef, noise, workspace, seed, sample_offset};
+  ldm_sampler::Key key{x, y, coef, noise, workspace};
   int done = 0;
   if (!s->exec || !(key == s->key)) {
     if (s->exec) { cudaGraphExecDestroy(s->exec); s->exec = nullptr; }

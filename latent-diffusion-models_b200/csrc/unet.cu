@@ -198,7 +198,7 @@ int64_t layout_all(ldm_unet* h, uint8_t* base) {
 
 // workspace plan for one forward of `batch` rows
 struct Plan {
-  int64_t temb, tproj, temb_tab, tproj_tab, gnws, qkv, s[4], total;
+  int64_t temb, tproj, temb_tab, tproj_tab, gnws, gnpk, gnpk_bytes, gnst, gnst_bytes, qkv, s[4], total;
   std::vector<int64_t> hin;  // [L+1]
   std::vector<int64_t> cat;  // [L]
 };
@@ -213,6 +213,12 @@ Plan make_plan(const ldm_unet* h, int batch) {
   p.temb_tab = take((int64_t)(h->d.num_classes + 1) * (h->D > 0 ? h->D : 1) * 4);
   p.tproj_tab = take((int64_t)(h->d.num_classes + 1) * (h->tproj_total > 0 ? h->tproj_total : 1) * 4);
   p.gnws = take(k_group_norm_ws_bytes(batch, 8));
+  // fused GroupNorm epilogues (conv_epilogue.cuh): 16-byte packets (<= 256 per sample: groups x variants x tiles) and
+  // statistics slots (<= 640 per sample: 8 groups x 2 variants x 36 row blocks)
+  p.gnpk_bytes = (int64_t)batch * 256 * 16;
+  p.gnpk = take(p.gnpk_bytes);
+  p.gnst_bytes = (int64_t)batch * 640 * 8;
+  p.gnst = take(p.gnst_bytes);
   int64_t max_elems = 0;
   for (int i = 0; i < L; ++i) {
     int64_t R = S >> i;
@@ -485,6 +491,35 @@ struct Fwd {
   Prof* prof = nullptr;
   cudaEvent_t join_event = nullptr;  // side-stream time embedding: waited for right before its first consumer
   int res_mod = 0;                   // residual row aliasing for the next conv (shared CFG prefix)
+  // GroupNorm fused into the producing convolution (conv_epilogue.cuh)
+  bool fuse_gn = false;
+  unsigned gn_tag = 0;               // packets: one tag per launch since the per-forward memset
+  int st_slots = 0;                  // > 0: gnst holds the PreNorm statistics of the last ResNetBlock output (that many slots)
+  bool want_stats = false;           // the next resblock() leaves PreNorm statistics of its output
+  // images of R x R pixels the fused epilogue can handle in either tile configuration (whole samples per work unit, or
+  // whole work units per sample)
+  bool gn_ok(int R) const {
+    const int hw = R * R;
+    return fuse_gn && hw >= 16 && (hw < 128 ? 128 % hw == 0 : hw % 256 == 0);
+  }
+  // Normalising in the producer's epilogue (mode 2) pays where a work unit holds whole samples; where a sample spans many
+  // tiles (32x32: packets, deferred second pass) the epilogue becomes the kernel's bottleneck -- measured in round 2
+  // (profiles/README.md): those layers keep separate GroupNorm kernels fed by epilogue statistics.
+  int norm_max_hw = 64;
+  bool gn_norm_ok(int R) const { return gn_ok(R) && R * R <= norm_max_hw; }
+  ConvGn gn_norm(const float* gamma, const float* beta, int groups, int silu, const float* rowvec, int ldrv, const void* res,
+                 int ldres, int nvar = 1, int var_rows = 0) {
+    ConvGn g;
+    g.mode = 2; g.groups = groups; g.silu = silu; g.eps = GN_EPS; g.gamma = gamma; g.beta = beta; g.rowvec = rowvec;
+    g.ld_rowvec = ldrv; g.res = res; g.ldres = ldres; g.nvar = nvar; g.var_rows = var_rows;
+    g.scratch = ws + plan.gnpk; g.scratch_bytes = plan.gnpk_bytes; g.tag = ++gn_tag;
+    return g;
+  }
+  ConvGn gn_stats() {
+    ConvGn g;
+    g.mode = 1; g.groups = 1; g.eps = GN_EPS; g.scratch = ws + plan.gnst; g.scratch_bytes = plan.gnst_bytes; g.nslots_out = &st_slots;
+    return g;
+  }
   const float* fin_w = nullptr; const float* fin_b = nullptr; float* fin_out = nullptr; int fin_cout = 0;
   void* s(int i) { return ws + plan.s[i]; }
   void* gnws() { return ws + plan.gnws; }
@@ -507,8 +542,9 @@ struct Fwd {
   }
   int conv(const void* x, int ldx, int cin, const void* x2, int ldx2, int cin2, const void* w, const float* bias,
            const float* rowvec, int ldrv, const void* res, int ldres, void* y, int ldy, int cout, int R, int ksize,
-           int up2 = 0) {
+           int up2 = 0, const ConvGn* gn = nullptr) {
     ConvArgs a;
+    if (gn) a.gn = *gn;
     a.x = x; a.ldx = ldx; a.cin = cin; a.x2 = x2; a.ldx2 = ldx2; a.cin2 = cin2; a.w = w; a.bias = bias;
     a.rowvec = rowvec; a.ld_rowvec = ldrv; a.res = res; a.ldres = ldres; a.y = y; a.ldy = ldy; a.cout = cout;
     a.batch = B; a.height = R; a.width = R; a.ksize = ksize; a.up2 = up2; a.dtype = dt; a.res_mod = res_mod;
@@ -527,20 +563,34 @@ struct Fwd {
   // x_rows > 0: x holds only x_rows distinct images and output row n belongs to image n % x_rows (the sampler's cond and
   // uncond halves are identical up to the first time-embedding add): norm1 + conv1 run once per distinct image.
   int resblock(const ResW& r, const void* x, int ldx, void* out, int ldo, int R, bool use_t, int x_rows = 0) {
+    const bool stats = want_stats && gn_ok(R);   // leave GroupNorm(1, C) statistics of the block output for the PreNorm that follows
+    want_stats = false;
+    st_slots = 0;
     if (x_rows > 0) {
       const int full = B;
+      const float* rvm = (use_t && r.tproj_off >= 0) ? tproj + r.tproj_off : nullptr;
       B = x_rows;
       RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
-      RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3));
-      B = full;
-      const float* rvm = (use_t && r.tproj_off >= 0) ? tproj + r.tproj_off : nullptr;
-      if (rvm && join_event) {
-        LDM_CUDA(cudaStreamWaitEvent(st, join_event, 0));
-        join_event = nullptr;
+      const bool fuse2 = gn_norm_ok(R) && rvm != nullptr;
+      if (fuse2) {
+        // block2's GroupNorm + SiLU in conv1's epilogue, once per time-embedding variant (cond / uncond halves)
+        if (join_event) { LDM_CUDA(cudaStreamWaitEvent(st, join_event, 0)); join_event = nullptr; }
+        ConvGn g2 = gn_norm(r.g2, r.be2, 8, 1, rvm, h->tproj_total, nullptr, 0, full / x_rows, x_rows);
+        RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3, 0, &g2));
+        B = full;
+      } else {
+        RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3));
+        B = full;
+        if (rvm && join_event) {
+          LDM_CUDA(cudaStreamWaitEvent(st, join_event, 0));
+          join_event = nullptr;
+        }
+        RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1, rvm, h->tproj_total, x_rows));
       }
-      RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1, rvm, h->tproj_total, x_rows));
       res_mod = x_rows;   // identity shortcut read from the shared images
-      int rc = conv(s(0), r.cout, r.cout, nullptr, 0, 0, r.w2, r.b2, nullptr, 0, x, ldx, out, ldo, r.cout, R, 3);
+      ConvGn gs = gn_stats();
+      int rc = conv(fuse2 ? s(1) : s(0), r.cout, r.cout, nullptr, 0, 0, r.w2, r.b2, nullptr, 0, x, ldx, out, ldo, r.cout, R, 3, 0,
+                    stats ? &gs : nullptr);
       res_mod = 0;
       return rc;
     }
@@ -566,45 +616,71 @@ struct Fwd {
       return conv(s(0), r.cout, r.cout, nullptr, 0, 0, r.w2c, r.b2, nullptr, 0, x, ldx, out, ldo, r.cout, 1, 1);
     }
     RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
-    // the time-embedding projection (h = h + mlp_t(t), :88-93) is a per-sample channel vector: it is added where
-    // block2's GroupNorm loads h (one 8-float vector per thread), not in the conv epilogue
+    // the time-embedding projection (h = h + mlp_t(t), :88-93) is a per-sample channel vector: it enters block2's
+    // GroupNorm statistics and shift, not the convolution
     const float* rv = (use_t && r.tproj_off >= 0) ? tproj + r.tproj_off : nullptr;
-    RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3));
     if (rv && join_event) {
       LDM_CUDA(cudaStreamWaitEvent(st, join_event, 0));
       join_event = nullptr;
     }
-    RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1, rv, h->tproj_total));
+    const void* h2 = s(0);
+    if (gn_norm_ok(R)) {
+      // block2's GroupNorm + SiLU in conv1's epilogue: conv1's raw output never exists in memory
+      ConvGn g2 = gn_norm(r.g2, r.be2, 8, 1, rv, h->tproj_total, nullptr, 0);
+      RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3, 0, &g2));
+      h2 = s(1);
+    } else {
+      RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3));
+      RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1, rv, h->tproj_total));
+    }
+    ConvGn gs = gn_stats();
+    const ConvGn* gsp = (stats && out != nullptr) ? &gs : nullptr;
     if (r.has_sc)  // 1x1 shortcut conv K-concatenated into the second 3x3 GEMM
-      RC(conv(s(0), r.cout, r.cout, x, ldx, r.cin, r.w2, r.b2, nullptr, 0, nullptr, 0, out, ldo, r.cout, R, 3));
+      RC(conv(h2, r.cout, r.cout, x, ldx, r.cin, r.w2, r.b2, nullptr, 0, nullptr, 0, out, ldo, r.cout, R, 3, 0, gsp));
     else           // identity shortcut added in the epilogue
-      RC(conv(s(0), r.cout, r.cout, nullptr, 0, 0, r.w2, r.b2, nullptr, 0, x, ldx, out, ldo, r.cout, R, 3));
+      RC(conv(h2, r.cout, r.cout, nullptr, 0, 0, r.w2, r.b2, nullptr, 0, x, ldx, out, ldo, r.cout, R, 3, 0, gsp));
     return 0;
   }
   // Residual(PreNorm(dim, LinearAttention | Attention))  src/UNet.py:14-20,102-164.  d must not alias s0/s1/out.
   int attn_block(const AttnW& a, const void* d, int ldd, void* out, int ldo, int R) {
     void* qkv = ws + plan.qkv;
+    const int slots = st_slots;   // > 0: the producing ResNetBlock left GroupNorm(1, C) statistics of d in gnst
+    st_slots = 0;
+    // x + GroupNorm(1,C)(to_out(att)): the GroupNorm and the residual add ride in the to_out convolution's epilogue
+    auto to_out = [&](const void* att) -> int {
+      if (gn_norm_ok(R)) {
+        ConvGn g = gn_norm(a.og, a.ob, 1, 0, nullptr, 0, d, ldd);
+        return conv(att, HIDDEN, HIDDEN, nullptr, 0, 0, a.wout, a.bout, nullptr, 0, nullptr, 0, out, ldo, a.dim, R, 1, 0, &g);
+      }
+      RC(conv(att, HIDDEN, HIDDEN, nullptr, 0, 0, a.wout, a.bout, nullptr, 0, nullptr, 0, s(1), a.dim, a.dim, R, 1));
+      return gn(s(1), a.dim, out, ldo, d, ldd, a.og, a.ob, R, a.dim, 1, 0);
+    };
     if (a.linear && impl == 0 && k_linear_attention_qkv_applicable(a.dim, R * R, dt)) {
       // PreNorm statistics, then to_qkv + both softmaxes + both einsums in one kernel that reads the RAW block input:
       // neither the normalised tensor nor the 384-channel qkv tensor ever exists
       const double N = (double)R * R;
       int splits = 1;
-      PROF(LDM_FAM_GROUP_NORM, 0, (double)B * N * a.dim * es, k_group_norm_stats(d, ldd, B, R * R, a.dim, 1, gnws(), &splits, st));
+      if (slots > 0) splits = -slots;   // statistics left by the producing convolution's epilogue
+      else PROF(LDM_FAM_GROUP_NORM, 0, (double)B * N * a.dim * es, k_group_norm_stats(d, ldd, B, R * R, a.dim, 1, gnws(), &splits, st));
       PROF(LDM_FAM_LINEAR_ATTENTION, (double)B * (2.0 * N * 3 * HIDDEN * a.dim + 4 * 2 * 2.0 * N * 32 * 32),
            (double)B * N * (a.dim + HIDDEN) * es,
-           k_linear_attention_qkv_prenorm(d, ldd, a.dim, a.wfold, a.uv, gnws(), splits, GN_EPS, qkv, B, R * R, dt, st));
-      RC(conv(qkv, HIDDEN, HIDDEN, nullptr, 0, 0, a.wout, a.bout, nullptr, 0, nullptr, 0, s(1), a.dim, a.dim, R, 1));
-      RC(gn(s(1), a.dim, out, ldo, d, ldd, a.og, a.ob, R, a.dim, 1, 0));  // x + GroupNorm(1,C)(to_out(...))
-      return 0;
+           k_linear_attention_qkv_prenorm(d, ldd, a.dim, a.wfold, a.uv, slots > 0 ? (const void*)(ws + plan.gnst) : gnws(), splits,
+                                          GN_EPS, qkv, B, R * R, dt, st));
+      return to_out(qkv);
     }
-    RC(gn(d, ldd, s(0), a.dim, nullptr, 0, a.ng, a.nb, R, a.dim, 1, 0));
+    if (slots > 0 && dt == LDM_DT_BF16 && k_group_norm_streams(R * R, a.dim, dt)) {
+      // PreNorm apply only: the statistics came out of the producing convolution's epilogue
+      PROF(LDM_FAM_GROUP_NORM, 0, (double)B * R * R * a.dim * es * 2,
+           k_group_norm_apply_raw(d, ldd, s(0), a.dim, nullptr, 0, a.ng, a.nb, B, R * R, a.dim, 1, GN_EPS, 0, ws + plan.gnst, slots, st));
+    } else {
+      RC(gn(d, ldd, s(0), a.dim, nullptr, 0, a.ng, a.nb, R, a.dim, 1, 0));
+    }
     RC(conv(s(0), a.dim, a.dim, nullptr, 0, 0, a.wqkv, nullptr, nullptr, 0, nullptr, 0, qkv, 3 * HIDDEN, 3 * HIDDEN, R, 1));
     if (a.linear) {
       // 2 GEMMs of 32x32xN per head (ctx = k v^T, out = ctx^T q): 2 * 2*N*32*32 * 4 heads
       PROF(LDM_FAM_LINEAR_ATTENTION, (double)B * 4 * 2 * 2.0 * R * R * 32 * 32, (double)B * R * R * (3 + 1) * HIDDEN * es,
            k_linear_attention(qkv, s(0), B, R * R, dt, st));
-      RC(conv(s(0), HIDDEN, HIDDEN, nullptr, 0, 0, a.wout, a.bout, nullptr, 0, nullptr, 0, s(1), a.dim, a.dim, R, 1));
-      RC(gn(s(1), a.dim, out, ldo, d, ldd, a.og, a.ob, R, a.dim, 1, 0));  // x + GroupNorm(1,C)(to_out(...))
+      return to_out(s(0));
     } else {
       PROF(LDM_FAM_ATTENTION, (double)B * 4 * 2 * 2.0 * R * R * R * R * 32, (double)B * R * R * (3 + 1) * HIDDEN * es,
            k_attention(qkv, s(0), B, R * R, dt, st));
@@ -680,6 +756,10 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
               (long long)workspace_bytes, (long long)f.plan.total);
   LDM_REQUIRE(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
   f.ws = (uint8_t*)workspace;
+  f.fuse_gn = f.dt == LDM_DT_BF16 && f.impl == 0 && getenv("LDM_NO_GN_FUSE") == nullptr;
+  if (const char* e = getenv("LDM_GN_NORM_MAXHW")) f.norm_max_hw = atoi(e);
+  if (f.fuse_gn)   // packet area of the fused GroupNorm epilogues: zero = no packet; every launch below gets its own tag
+    LDM_CUDA(cudaMemsetAsync(f.ws + f.plan.gnpk, 0, f.plan.gnpk_bytes, f.st));
   const int L = h->L, S = h->d.image_size;
   float* temb = (float*)(f.ws + f.plan.temb);
   float* tproj = (float*)(f.ws + f.plan.tproj);
@@ -750,6 +830,7 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
     uint8_t* cat = f.ws + f.plan.cat[j];
     void* skip = cat + (int64_t)h->dims[i] * f.es;    // skip occupies channels [dims[i], catc)
     void* hin = f.ws + f.plan.hin[i];
+    f.want_stats = true;
     RC(f.resblock(h->enc_res[i], hin, h->dims[i], f.s(2), cout, R, true, (i == 0 && share_prefix) ? x_batch : 0));
     RC(f.tap(("enc" + std::to_string(i) + ".res").c_str(), f.s(2), cout, cout, R));
     RC(f.attn_block(h->enc_attn[i], f.s(2), cout, skip, catc, R));
@@ -785,6 +866,7 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
       a.batch = batch; a.height = Rin; a.width = Rin; a.ksize = 1; a.up2 = 1; a.dtype = f.dt;
       RC(f.conv_args(a));
     }
+    f.want_stats = true;
     RC(f.resblock(h->dec_res[j], cat, catc, f.s(2), u.cout, R, true));
     RC(f.attn_block(h->dec_attn[j], f.s(2), u.cout, f.s(3), u.cout, R));
     RC(f.tap(("dec" + std::to_string(j)).c_str(), f.s(3), u.cout, u.cout, R));

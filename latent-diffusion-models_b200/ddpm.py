@@ -9,6 +9,7 @@ timestep, and nothing synchronises with the host until the final ``.cpu()``.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -54,7 +55,27 @@ class Diffusion(nn.Module):
         self.sigma2 = self.beta
         self.n_steps = self.beta.numel()
         self._coef = None
-        self._samplers.clear()
+        self._destroy_samplers()
+
+    def _destroy_samplers(self, dead_only: bool = False) -> None:
+        """Free native samplers (all, or those whose UNet object is gone)."""
+        try:
+            lib = _lib.load()
+        except Exception:
+            return
+        for key in list(self._samplers):
+            ent = self._samplers[key]
+            if dead_only and ent["unet"]() is not None:
+                continue
+            lib.ldm_sampler_destroy(ent["s"])
+            del self._samplers[key]
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_samplers"] = {}       # native handles belong to this object only
+        state["_coef"] = None
+        state.pop("_abar_dev", None)
+        return state
 
     def _require_cuda(self, t: torch.Tensor) -> None:
         if not t.is_cuda:
@@ -162,9 +183,11 @@ class Diffusion(nn.Module):
                 x_init = 0
             z = noise.detach().to(dev, torch.float32).contiguous() if noise is not None else None
             h = unet.native(S, dev)
-            key = (h, B, float(cfg_scale), y_len, bool(use_graph))
+            # keyed by the UNet OBJECT's identity (handle addresses and id() are reused after garbage collection)
+            key = (unet._uid, h, B, float(cfg_scale), y_len, bool(use_graph))
             ent = self._samplers.get(key)
             if ent is None:
+                self._destroy_samplers(dead_only=True)
                 d = _lib.SamplerDesc(batch=B, n_steps=self.n_steps, cfg_scale=float(cfg_scale), y_len=y_len,
                                      use_graph=int(use_graph))
                 sp = C.c_void_p()
@@ -174,7 +197,7 @@ class Diffusion(nn.Module):
                 # persistent buffers so that the captured graph can be replayed across calls
                 xbuf = torch.empty(shape, dtype=torch.float32, device=dev)
                 ybuf = torch.zeros(max(y_len, 1), dtype=torch.int64, device=dev)
-                ent = {"s": sp.value, "ws": ws, "nbytes": nbytes, "x": xbuf, "y": ybuf}
+                ent = {"s": sp.value, "ws": ws, "nbytes": nbytes, "x": xbuf, "y": ybuf, "unet": weakref.ref(unet)}
                 self._samplers[key] = ent
             ws = ent["ws"]
             off = (-ws.data_ptr()) % 1024
@@ -219,8 +242,6 @@ class Diffusion(nn.Module):
 
     def __del__(self):
         try:
-            lib = _lib.load()
-            for ent in self._samplers.values():
-                lib.ldm_sampler_destroy(ent["s"])
+            self._destroy_samplers()
         except Exception:
             pass

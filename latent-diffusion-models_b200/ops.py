@@ -100,6 +100,40 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, ksize: int, bias: Optional[t
     return out
 
 
+def conv2d_gn(x: torch.Tensor, w_packed: torch.Tensor, ksize: int, bias: Optional[torch.Tensor], *, mode: int, groups: int,
+              gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None, silu: bool = False,
+              eps: float = 1e-5, x2: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
+              gn_rowvec: Optional[torch.Tensor] = None, gn_res: Optional[torch.Tensor] = None, nvar: int = 1,
+              out: Optional[torch.Tensor] = None, scratch: Optional[torch.Tensor] = None, tag: int = 1):
+    """Convolution with the GroupNorm that follows it fused into the tcgen05 epilogue (bf16 NHWC; csrc/conv_epilogue.cuh).
+    mode 1 -> (y, stats) with stats float32 [B, groups, nslots, 2] partial sums {S, Q} of the stored y;
+    mode 2 -> y = [silu](GroupNorm(conv(x) + gn_rowvec)) [+ gn_res]; with nvar = 2 the output holds 2B images
+    (image n normalised with row vectors n and n + B)."""
+    _cuda(x, w_packed, bias, x2, res, gamma, beta, gn_rowvec, gn_res)
+    B, H, W, cin = x.shape
+    cout = w_packed.shape[0]
+    cin2 = x2.shape[3] if x2 is not None else 0
+    assert w_packed.shape[1] == ksize * ksize * cin + cin2 and x.dtype == torch.bfloat16
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(B * nvar, H, W, cout, dtype=x.dtype, device=x.device)
+    if scratch is None:
+        scratch = torch.zeros(lib.ldm_conv2d_gn_scratch_bytes(B * nvar), dtype=torch.uint8, device=x.device)
+    import ctypes
+    nslots = ctypes.c_int(0)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ldm_conv2d_gn(
+            x.data_ptr(), x.stride(2), cin, _lib.ptr(x2), x2.stride(2) if x2 is not None else 0, cin2, w_packed.data_ptr(),
+            _lib.ptr(bias), _lib.ptr(res), res.stride(2) if res is not None else 0, out.data_ptr(), out.stride(2), cout, B, H, W,
+            ksize, mode, groups, eps, int(silu), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(gn_rowvec),
+            gn_rowvec.stride(0) if gn_rowvec is not None else 0, _lib.ptr(gn_res), gn_res.stride(2) if gn_res is not None else 0,
+            nvar, B if nvar > 1 else 0, scratch.data_ptr(), scratch.numel(), tag, ctypes.byref(nslots), _lib.stream_ptr()))
+    if mode == 1:
+        stats = scratch[: B * groups * nslots.value * 8].view(torch.float32).view(B, groups, nslots.value, 2)
+        return out, stats
+    return out
+
+
 def conv_transpose2x2(x: torch.Tensor, w_iohw: torch.Tensor, bias: torch.Tensor, impl: int = 0,
                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ConvTranspose2d(k=2, s=2) on NHWC x (src/UNet.py:231-233)."""

@@ -8,6 +8,7 @@ construction order so that the same ``torch.manual_seed`` yields bit-identical d
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import os
 from typing import Dict, List, Optional, Tuple, Union
 
@@ -17,6 +18,7 @@ from torch import nn
 from . import _lib
 
 _HIDDEN = 128  # 4 heads x 32 (src/UNet.py:114,140)
+_UID = itertools.count(1)   # identity of a UNet object's native state (never reused, unlike id() / handle addresses)
 
 
 # ----------------------------------------------------------------------------- parameter holders
@@ -121,11 +123,27 @@ class UNet(nn.Module):
                            nn.ConvTranspose2d(rd[i], rd[i + 1], 2, 2)])
             for i in range(len(rd) - 1)])
         self.final_conv = nn.Sequential(_ResParams(channels, channels, None), nn.Conv2d(channels, out_channels, 1))
-        # ---- native state (not part of state_dict)
+        self._reset_native()
+
+    def _reset_native(self) -> None:
+        """Native state (not part of state_dict): owned by exactly one Python object, rebuilt lazily."""
         self._handles: Dict[Tuple[int, int], int] = {}      # (image_size, device index) -> ldm_unet*
-        self._loaded: Dict[Tuple[int, int], tuple] = {}     # handle key -> parameter fingerprint
+        self._loaded: Dict[int, tuple] = {}                 # handle -> parameter fingerprint
         self._ws: Dict[int, torch.Tensor] = {}               # device index -> workspace bytes
+        self._uid = next(_UID)
         self.last_launches = 0
+
+    def __getstate__(self):
+        # copy.deepcopy / pickle / torch.save(model): the copy must not share ldm_unet* handles (two owners would repack each
+        # other's weights behind stale fingerprints and double-free in __del__); it builds its own on first use
+        state = self.__dict__.copy()
+        for k in ("_handles", "_loaded", "_ws", "_uid"):
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._reset_native()
 
     # ------------------------------------------------------------------ native plumbing
     def _handle(self, image_size: int, device: torch.device) -> int:

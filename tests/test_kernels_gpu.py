@@ -175,6 +175,113 @@ def test_conv_bf16_tcgen05(case):
     assert rel_l2(out, out_s) < 3e-3
 
 
+# ------------------------------------------------------------------ GroupNorm fused into the conv epilogue
+# (csrc/conv_epilogue.cuh): Block = GroupNorm(8) -> SiLU on conv1's output incl. the time-embedding row (src/UNet.py:52-58,
+# 88-93), LinearAttention.to_out's GroupNorm(1, C) + Residual (:147,:20), and PreNorm statistics (:106)
+GN_FUSE_CASES = [
+    # B, cin, cout, R, k, groups, silu, rowvec, gn_res, second
+    (3, 64, 64, 32, 3, 8, True, True, False, 0),       # halo kernel: 9 tiles per sample exchange packets
+    (40, 64, 64, 32, 3, 8, True, True, False, 0),      # several tiles per persistent CTA, deferred second pass wraps the ring
+    (2, 128, 64, 32, 3, 8, True, False, False, 0),
+    (3, 64, 128, 16, 3, 8, True, True, False, 0),      # conv_tc, two M tiles per sample
+    (300, 64, 128, 16, 3, 8, True, True, False, 0),    # paired M tiles (MT = 2): a work unit is one whole sample
+    (3, 192, 64, 16, 3, 8, True, True, False, 0),
+    (5, 128, 256, 8, 3, 8, True, True, False, 0),      # two samples per tile
+    (5, 256, 512, 4, 3, 8, True, True, False, 0),      # eight samples per tile, several N tiles
+    (20, 768, 256, 4, 3, 8, True, True, False, 0),
+    (3, 128, 64, 32, 1, 1, False, False, True, 0),     # to_out: GroupNorm(1, C) + residual, 8 tiles per sample
+    (160, 128, 64, 32, 1, 1, False, False, True, 0),   # ... paired tiles
+    (3, 128, 128, 16, 1, 1, False, False, True, 0),
+    (5, 128, 256, 8, 1, 1, False, False, True, 0),
+    (9, 128, 512, 4, 1, 1, False, False, True, 0),     # GroupNorm(1, 512) over four N tiles of eight samples
+    (80, 128, 512, 4, 1, 1, False, False, True, 0),
+]
+
+
+def _gn_fuse_inputs(B, cin, cout, R, k, second, seed=0):
+    from ldm_b200 import ops
+    g = torch.Generator().manual_seed(seed + cin + cout + R + B)
+    x = torch.randn(B, cin, R, R, generator=g).to(dev())
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev())
+    b = torch.randn(cout, generator=g).to(dev())
+    conv = F.conv2d(nhwc_ref(x, "bf16"), nhwc_ref(w, "bf16"), b, padding=k // 2)
+    x2h = w2 = None
+    if second:
+        x2 = torch.randn(B, second, R, R, generator=g).to(dev())
+        w2 = (torch.randn(cout, second, 1, 1, generator=g) / second ** 0.5).to(dev())
+        conv = conv + F.conv2d(nhwc_ref(x2, "bf16"), nhwc_ref(w2, "bf16"))
+        x2h = ops.to_nhwc(x2, "bf16")
+    return g, ops.to_nhwc(x, "bf16"), ops.pack_conv_weight(w, "bf16", w2), b, x2h, conv
+
+
+@pytest.mark.parametrize("case", GN_FUSE_CASES)
+def test_conv_gn_fused_normalise(case):
+    from ldm_b200 import ops
+    B, cin, cout, R, k, G, silu, rowvec, gn_res, second = case
+    g, xh, wp, b, x2h, conv = _gn_fuse_inputs(B, cin, cout, R, k, second)
+    gamma = (1 + 0.3 * torch.randn(cout, generator=g)).to(dev())
+    beta = (0.3 * torch.randn(cout, generator=g)).to(dev())
+    rv = torch.randn(B, cout + 64, generator=g).to(dev())[:, 64:] if rowvec else None
+    pre = conv + (rv[:, :, None, None] if rowvec else 0)
+    ref = F.group_norm(pre, G, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    rh = None
+    if gn_res:
+        r = torch.randn(B, cout, R, R, generator=g).to(dev())
+        ref = ref + nhwc_ref(r, "bf16")
+        rh = ops.to_nhwc(r, "bf16")
+    # strided output slice, as the skip half of the decoder's concat buffer
+    wide = torch.zeros(B, R, R, cout + 64, dtype=torch.bfloat16, device=dev())
+    ops.conv2d_gn(xh, wp, k, b, mode=2, groups=G, gamma=gamma, beta=beta, silu=silu, x2=x2h, gn_rowvec=rv, gn_res=rh,
+                  out=wide[..., 64:])
+    out = ops.to_nchw(wide[..., 64:], channels=cout, ld=cout + 64)
+    assert rel_l2(out, ref) < 6e-3
+    assert float(wide[..., :64].float().abs().max()) == 0.0
+    # same bits whatever the batch the sample sits in (fixed-order sums): the first sample alone
+    one = ops.conv2d_gn(xh[:1].contiguous(), wp, k, b, mode=2, groups=G, gamma=gamma, beta=beta, silu=silu,
+                        x2=x2h[:1].contiguous() if x2h is not None else None, gn_rowvec=rv[:1] if rowvec else None,
+                        gn_res=rh[:1].contiguous() if rh is not None else None)
+    assert torch.equal(one[0], wide[0, ..., 64:])
+
+
+def test_conv_gn_fused_two_variants():
+    """conv1 of the first ResNetBlock runs once for the cond / uncond halves; its epilogue normalises twice."""
+    from ldm_b200 import ops
+    B, cin, cout, R, k = 5, 64, 64, 32, 3
+    g, xh, wp, b, _, conv = _gn_fuse_inputs(B, cin, cout, R, k, 0)
+    gamma = (1 + 0.3 * torch.randn(cout, generator=g)).to(dev())
+    beta = (0.3 * torch.randn(cout, generator=g)).to(dev())
+    rv = torch.randn(2 * B, cout, generator=g).to(dev())
+    out = ops.conv2d_gn(xh, wp, k, b, mode=2, groups=8, gamma=gamma, beta=beta, silu=True, gn_rowvec=rv, nvar=2)
+    ref = F.silu(F.group_norm(torch.cat([conv, conv]) + rv[:, :, None, None], 8, gamma, beta, 1e-5))
+    assert rel_l2(ops.to_nchw(out), ref) < 6e-3
+
+
+@pytest.mark.parametrize("case", [(3, 64, 64, 32, 3, 0, True), (3, 64, 64, 32, 3, 128, False), (300, 128, 128, 16, 3, 64, False),
+                                  (5, 256, 256, 8, 3, 128, False), (9, 512, 512, 4, 3, 256, False), (2, 256, 256, 4, 3, 768, False)])
+def test_conv_gn_fused_statistics(case):
+    """conv2 (+ shortcut / residual) leaves GroupNorm(1, C) partial sums of its output for the PreNorm that follows."""
+    from ldm_b200 import ops
+    B, cin, cout, R, k, second, res = case
+    g, xh, wp, b, x2h, conv = _gn_fuse_inputs(B, cin, cout, R, k, second)
+    rh = None
+    if res:
+        r = torch.randn(B, cout, R, R, generator=g).to(dev())
+        conv = conv + nhwc_ref(r, "bf16")
+        rh = ops.to_nhwc(r, "bf16")
+    y, stats = ops.conv2d_gn(xh, wp, k, b, mode=1, groups=1, x2=x2h, res=rh)
+    assert rel_l2(ops.to_nchw(y), conv) < 4e-3
+    s = stats.double().sum(dim=2)[:, 0]                       # [B, 2]
+    n = cout * R * R
+    mean = s[:, 0] / n
+    var = s[:, 1] / n - mean ** 2
+    ref_mean = conv.double().mean(dim=(1, 2, 3))
+    ref_var = conv.double().var(dim=(1, 2, 3), unbiased=False)
+    assert float((mean - ref_mean).abs().max()) < 2e-3 * float(ref_var.sqrt().max())
+    assert float((var / ref_var - 1).abs().max()) < 2e-3
+
+
 @pytest.mark.parametrize("dtype,impl", [("fp32", 0), ("bf16", 0), ("bf16", 1)])
 @pytest.mark.parametrize("B,cin,cout,R", [(2, 512, 256, 2), (3, 64, 64, 16), (2, 128, 64, 8)])
 def test_conv_transpose(dtype, impl, B, cin, cout, R):
