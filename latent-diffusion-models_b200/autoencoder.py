@@ -287,5 +287,10 @@ class Autoencoder(nn.Module):                    # :388-462
         return out
 
     def forward(self, img: torch.Tensor, epsilon: Optional[torch.Tensor] = None):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # the reference never trains its autoencoder on a live path (train_autoencoder.py / AutoencoderTrainer are dead
+            # code); this class is inference-only and says so instead of returning detached tensors
+            raise _lib.LdmError("ldm_b200.Autoencoder is inference-only (no backward kernels): call it under torch.no_grad() "
+                                "or freeze its parameters with requires_grad_(False)")
         self.distribution = self.encode(img, epsilon)
         return self.decode(self.distribution.sample()), self.distribution.mu, self.distribution.log_var

@@ -267,10 +267,12 @@ gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int l
   if (threadIdx.x < G && splits < 0) {
     // un-pivoted sums {S, Q} left by the producing convolution's epilogue (conv_epilogue.cuh, mode 1):
     // part[(n * G + g) * nslots + slot], nslots = -splits
+    // (x_mod > 0: sample n is variant n / x_mod of image n % x_mod -- part[((image * G + g) * nvar + variant) * nslots + slot])
     const int gg = threadIdx.x, ns = -splits;
+    const int nv = x_mod > 0 ? gridDim.y / x_mod : 1, img = x_mod > 0 ? n % x_mod : n, kk = x_mod > 0 ? n / x_mod : 0;
     double a = 0.0, b = 0.0;
     for (int sp = 0; sp < ns; ++sp) {
-      const float2 v = part[((int64_t)n * G + gg) * ns + sp];
+      const float2 v = part[(((int64_t)img * G + gg) * nv + kk) * ns + sp];
       a += (double)v.x; b += (double)v.y;
     }
     const double cnt = (double)HW * (double)(cpg * V);
@@ -648,10 +650,11 @@ int gn_launch(const void* x, int ldx, void* y, int ldy, const void* res, int ldr
 // Apply only (bf16, streaming kernel): the statistics are the un-pivoted {S, Q} slots a convolution epilogue left
 // (ConvGn mode 1): part[(n * groups + g) * nslots + slot].
 int k_group_norm_apply_raw(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
-                           const float* beta, int batch, int hw, int channels, int groups, float eps, int silu, const void* part,
-                           int nslots, cudaStream_t st) {
+                           const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
+                           float eps, int silu, const void* part, int nslots, int x_mod, cudaStream_t st) {
   LDM_REQUIRE(channels % groups == 0 && (channels / groups) % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && (!res || ldres % 8 == 0) &&
-                  channels / 8 <= GS_THREADS && part && nslots >= 1 && groups <= GN_MAX_GROUPS,
+                  channels / 8 <= GS_THREADS && part && nslots >= 1 && groups <= GN_MAX_GROUPS && batch <= 65535 &&
+                  (x_mod == 0 || batch % x_mod == 0),
               "group_norm_apply_raw: unsupported shape");
   if (batch == 0 || hw == 0) return 0;
   int threads, ppi, splits, pps;
@@ -659,8 +662,12 @@ int k_group_norm_apply_raw(const void* x, int ldx, void* y, int ldy, const void*
   int ppb = ppi * 8;
   if (ppb > hw) ppb = hw;
   const dim3 grid((hw + ppb - 1) / ppb, batch);
-  LDM_CUDA(ldm_launch_pdl(gn_apply_kernel<false>, grid, dim3(threads), 0, st, (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)res,
-                          ldres, gamma, beta, (const float*)nullptr, 0, (const float2*)part, -nslots, hw, channels, groups, eps, silu, ppb, 0));
+  if (rowvec)
+    LDM_CUDA(ldm_launch_pdl(gn_apply_kernel<true>, grid, dim3(threads), 0, st, (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)res,
+                            ldres, gamma, beta, rowvec, ld_rowvec, (const float2*)part, -nslots, hw, channels, groups, eps, silu, ppb, x_mod));
+  else
+    LDM_CUDA(ldm_launch_pdl(gn_apply_kernel<false>, grid, dim3(threads), 0, st, (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)res,
+                            ldres, gamma, beta, (const float*)nullptr, 0, (const float2*)part, -nslots, hw, channels, groups, eps, silu, ppb, x_mod));
   LDM_LAUNCHED("gn_apply");
   return 0;
 }

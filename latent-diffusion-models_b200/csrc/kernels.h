@@ -68,8 +68,8 @@ int k_group_norm_mod(const void* x, int ldx, void* y, int ldy, const void* res, 
                      float eps, int silu, int dtype, void* workspace, int x_mod, cudaStream_t st);
 bool k_group_norm_streams(int hw, int channels, int dtype);
 int k_group_norm_apply_raw(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
-                           const float* beta, int batch, int hw, int channels, int groups, float eps, int silu, const void* part,
-                           int nslots, cudaStream_t st);
+                           const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
+                           float eps, int silu, const void* part, int nslots, int x_mod, cudaStream_t st);
 
 // ---- attention.cu
 int k_linear_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, cudaStream_t st);

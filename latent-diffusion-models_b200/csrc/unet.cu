@@ -217,7 +217,8 @@ Plan make_plan(const ldm_unet* h, int batch) {
   // statistics slots (<= 640 per sample: 8 groups x 2 variants x 36 row blocks)
   p.gnpk_bytes = (int64_t)batch * 256 * 16;
   p.gnpk = take(p.gnpk_bytes);
-  p.gnst_bytes = (int64_t)batch * 640 * 8;
+  // (8 groups x 2 variants x (36 or S*S/32) row blocks of the full-resolution level)
+  p.gnst_bytes = (int64_t)batch * std::max<int64_t>(640, ((int64_t)S * S / 32 + 4) * 16) * 8;
   p.gnst = take(p.gnst_bytes);
   int64_t max_elems = 0;
   for (int i = 0; i < L; ++i) {
@@ -515,6 +516,13 @@ struct Fwd {
     g.scratch = ws + plan.gnpk; g.scratch_bytes = plan.gnpk_bytes; g.tag = ++gn_tag;
     return g;
   }
+  // GroupNorm(8, C) statistics of conv1's output + time-embedding row(s), for the apply-only kernel that follows
+  ConvGn gn_stats8(const float* rowvec, int ldrv, int nvar, int var_rows, int* nslots) {
+    ConvGn g;
+    g.mode = 1; g.groups = 8; g.eps = GN_EPS; g.rowvec = rowvec; g.ld_rowvec = ldrv; g.nvar = nvar; g.var_rows = var_rows;
+    g.scratch = ws + plan.gnst; g.scratch_bytes = plan.gnst_bytes; g.nslots_out = nslots;
+    return g;
+  }
   ConvGn gn_stats() {
     ConvGn g;
     g.mode = 1; g.groups = 1; g.eps = GN_EPS; g.scratch = ws + plan.gnst; g.scratch_bytes = plan.gnst_bytes; g.nslots_out = &st_slots;
@@ -578,6 +586,16 @@ struct Fwd {
         ConvGn g2 = gn_norm(r.g2, r.be2, 8, 1, rvm, h->tproj_total, nullptr, 0, full / x_rows, x_rows);
         RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3, 0, &g2));
         B = full;
+      } else if (gn_ok(R) && rvm != nullptr && k_group_norm_streams(R * R, r.cout, dt)) {
+        // conv1's epilogue takes block2's GroupNorm statistics (per time-embedding variant); one apply kernel follows
+        if (join_event) { LDM_CUDA(cudaStreamWaitEvent(st, join_event, 0)); join_event = nullptr; }
+        int ns = 0;
+        ConvGn g1 = gn_stats8(rvm, h->tproj_total, full / x_rows, x_rows, &ns);
+        RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3, 0, &g1));
+        B = full;
+        PROF(LDM_FAM_GROUP_NORM, 0, (double)B * R * R * r.cout * es * 2,
+             k_group_norm_apply_raw(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, rvm, h->tproj_total, B, R * R, r.cout, 8, GN_EPS, 1,
+                                    ws + plan.gnst, ns, x_rows, st));
       } else {
         RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3));
         B = full;
@@ -629,6 +647,14 @@ struct Fwd {
       ConvGn g2 = gn_norm(r.g2, r.be2, 8, 1, rv, h->tproj_total, nullptr, 0);
       RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3, 0, &g2));
       h2 = s(1);
+    } else if (gn_ok(R) && k_group_norm_streams(R * R, r.cout, dt)) {
+      // conv1's epilogue takes block2's GroupNorm statistics (of h + time-embedding row); one apply kernel follows
+      int ns = 0;
+      ConvGn g1 = gn_stats8(rv, h->tproj_total, 1, 0, &ns);
+      RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3, 0, &g1));
+      PROF(LDM_FAM_GROUP_NORM, 0, (double)B * R * R * r.cout * es * 2,
+           k_group_norm_apply_raw(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, rv, h->tproj_total, B, R * R, r.cout, 8, GN_EPS, 1,
+                                  ws + plan.gnst, ns, 0, st));
     } else {
       RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3));
       RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1, rv, h->tproj_total));
@@ -671,7 +697,7 @@ struct Fwd {
     if (slots > 0 && dt == LDM_DT_BF16 && k_group_norm_streams(R * R, a.dim, dt)) {
       // PreNorm apply only: the statistics came out of the producing convolution's epilogue
       PROF(LDM_FAM_GROUP_NORM, 0, (double)B * R * R * a.dim * es * 2,
-           k_group_norm_apply_raw(d, ldd, s(0), a.dim, nullptr, 0, a.ng, a.nb, B, R * R, a.dim, 1, GN_EPS, 0, ws + plan.gnst, slots, st));
+           k_group_norm_apply_raw(d, ldd, s(0), a.dim, nullptr, 0, a.ng, a.nb, nullptr, 0, B, R * R, a.dim, 1, GN_EPS, 0, ws + plan.gnst, slots, 0, st));
     } else {
       RC(gn(d, ldd, s(0), a.dim, nullptr, 0, a.ng, a.nb, R, a.dim, 1, 0));
     }

@@ -112,5 +112,7 @@ def sync_gradients(params: Iterable[torch.nn.Parameter], bucket: Optional[torch.
     params = list(params)
     bucket = flatten_grads(params, bucket)
     allreduce_mean_(bucket)
-    unflatten_grads(params, bucket)
+    # every parameter receives the reduced gradient, also those without a local one (a rank whose label-drop coin fell
+    # differently has no label_emb gradient; Adam leaves all-zero gradients' parameters untouched, as the reference does)
+    unflatten_grads(params, bucket, skip_none=False)
     return bucket

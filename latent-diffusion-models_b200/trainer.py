@@ -13,6 +13,8 @@ CUDA only: there is no CPU path.
 """
 from __future__ import annotations
 
+import os
+import sys
 from typing import Callable, Iterable, List, Optional
 
 import numpy as np
@@ -145,28 +147,74 @@ def val_step(model, diffusion, data: torch.Tensor, targets: Optional[torch.Tenso
     return mse_loss(noise, eps)
 
 
+class NoOpGradScaler:
+    """What ``torch.cuda.amp.GradScaler`` is to the reference's fp16 autocast (src/Trainer.py:43,
+    src/DiffusionModelTrainer.py:57-60) when the reduced-precision kernels are bf16: bf16 has fp32's exponent range, so
+    there is nothing to scale -- the object keeps the call protocol (scale / step / update) and changes no number."""
+
+    def scale(self, loss):
+        return loss
+
+    def unscale_(self, optimizer) -> None:
+        return None
+
+    def step(self, optimizer, *args, **kwargs):
+        return optimizer.step(*args, **kwargs)
+
+    def update(self, new_scale=None) -> None:
+        return None
+
+    def get_scale(self) -> float:
+        return 1.0
+
+    def state_dict(self) -> dict:
+        return {}
+
+    def load_state_dict(self, sd) -> None:
+        return None
+
+
 class DiffusionModelTrainer:
-    """Compute methods of ``src.DiffusionModelTrainer.DiffusionModelTrainer`` on the native path.
+    """Compute methods of ``src.DiffusionModelTrainer.DiffusionModelTrainer`` on the native path, with the reference's
+    constructor order ``(config, model, train_loader, val_loader, classes, diffusion, cfg_scale)`` (:14-17).
 
     ``config`` needs ``lr``, ``epochs`` and ``data.image_channels`` / ``data.image_size`` (mapping or attribute access).
+    ``config["use_amp"]`` is honoured as the reference means it (src/Trainer.py:43, :40): True -> reduced-precision kernels
+    (bf16 here, with a no-op scaler object in ``self.scaler``), False -> the fp32 kernels and ``self.scaler is None``; when the
+    key is absent the model keeps the dtype it was built with.
     The reference's wandb logging, early stopping and checkpoint writing are the caller's business."""
 
-    def __init__(self, config, model, diffusion, train_loader=None, val_loader=None, classes=None, cfg_scale: float = 0.0,
-                 device=None, rng: Optional[np.random.Generator] = None, use_cuda_graphs: bool = True):
+    def __init__(self, config, model, train_loader=None, val_loader=None, classes=None, diffusion=None, cfg_scale: float = 0.0,
+                 *, device=None, rng: Optional[np.random.Generator] = None, use_cuda_graphs: bool = True):
+        if diffusion is None:
+            raise TypeError("DiffusionModelTrainer: `diffusion` is required (reference order: config, model, train_loader, "
+                            "val_loader, classes, diffusion, cfg_scale)")
         get = (lambda k: config[k]) if hasattr(config, "__getitem__") else (lambda k: getattr(config, k))
         self.config, self.model, self.diffusion = config, model, diffusion
         self.train_loader, self.val_loader = train_loader, val_loader
         self.classes, self.cfg_scale = classes, cfg_scale
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         self.epochs = int(get("epochs")) if self._has(config, "epochs") else 1
+        self.scaler = None
+        if self._has(config, "use_amp"):
+            self.use_amp = bool(get("use_amp"))
+            want = "bf16" if self.use_amp else "fp32"
+            if hasattr(model, "set_compute_dtype"):
+                model.set_compute_dtype(want)       # native handles are rebuilt lazily in the new precision
+            self.scaler = NoOpGradScaler() if self.use_amp else None
+        else:
+            self.use_amp = getattr(model, "compute_dtype", "bf16") == "bf16"
         self.optimizer = FlatAdam(model.parameters(), lr=float(get("lr")))
         self.loss_fn = torch.nn.functional.mse_loss
-        self._rng = rng if rng is not None else np.random.default_rng()
+        # the label-drop coin (:44) must fall the same way on every rank of a data-parallel job (a rank that drops its labels
+        # has no label_emb gradient): one seed for all ranks unless the caller passes a generator
+        self._rng = rng if rng is not None else np.random.default_rng(0x5EED)
         self._get = get
         # forward + backward of the UNet captured as CUDA graphs, one pair per (batch shape, labels given?): a step is
         # ~560 kernel launches, and at the reference's batch 64 issuing them from Python takes twice as long as running them
         self.use_cuda_graphs = use_cuda_graphs
         self._graphed: dict = {}
+        self.graph_capture_error: Optional[str] = None
 
     @staticmethod
     def _has(config, key) -> bool:
@@ -188,7 +236,12 @@ class DiffusionModelTrainer:
             try:
                 noise, xt, t = self.diffusion(data)
                 self._graphed[key] = make_graphed(self.model, xt, t, targets)
-            except Exception:   # noqa: BLE001 -- capture is an optimisation; the eager autograd path is always there
+            except Exception as e:   # noqa: BLE001 -- capture is an optimisation; the eager autograd path is always there
+                if os.environ.get("LDM_STRICT_GRAPHS"):
+                    raise
+                self.graph_capture_error = f"{type(e).__name__}: {e}"
+                sys.stderr.write(f"ldm_b200: CUDA-graph capture of the training step failed ({self.graph_capture_error}); "
+                                 "running eagerly (about 2x slower at batch 64). LDM_STRICT_GRAPHS=1 re-raises.\n")
                 self._graphed[key] = None
         return self._graphed[key]
 

@@ -133,6 +133,24 @@ class UNet(nn.Module):
         self._uid = next(_UID)
         self.last_launches = 0
 
+    def _destroy_native(self) -> None:
+        try:
+            lib = _lib.load()
+            for h in getattr(self, "_handles", {}).values():
+                lib.ldm_unet_destroy(h)
+        except Exception:
+            pass
+
+    def set_compute_dtype(self, dtype: str) -> None:
+        """Switch the kernel precision ('bf16' | 'fp32'); native handles are rebuilt on the next call."""
+        dtype = dtype.lower()
+        if dtype not in _lib.DTYPES:
+            raise ValueError(f"dtype must be one of {sorted(_lib.DTYPES)}")
+        if _lib.DTYPES[dtype] != _lib.DTYPES[self.compute_dtype]:
+            self._destroy_native()
+            self._reset_native()
+        self.compute_dtype = dtype
+
     def __getstate__(self):
         # copy.deepcopy / pickle / torch.save(model): the copy must not share ldm_unet* handles (two owners would repack each
         # other's weights behind stale fingerprints and double-free in __del__); it builds its own on first use
@@ -210,7 +228,10 @@ class UNet(nn.Module):
     def forward(self, x_noisy: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor] = None) -> torch.Tensor:
         if not x_noisy.is_cuda:
             raise _lib.LdmError("ldm_b200.UNet runs on CUDA tensors only (no CPU fallback)")
-        if torch.is_grad_enabled() and (x_noisy.requires_grad or any(p.requires_grad for p in self.parameters())):
+        if torch.is_grad_enabled() and x_noisy.requires_grad:
+            raise _lib.LdmError("ldm_b200.UNet has no gradient with respect to its input x_noisy (the training step never needs "
+                                "it: src/DiffusionModelTrainer.py:41-63); detach the input")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .train import unet_autograd_forward
             return unet_autograd_forward(self, x_noisy, t, y)
         return self._forward_nograd(x_noisy, t, y)
@@ -267,9 +288,4 @@ class UNet(nn.Module):
                 for i, name in enumerate(_lib.FAMILIES) if prof.family[i].launches}
 
     def __del__(self):
-        try:
-            lib = _lib.load()
-            for h in self._handles.values():
-                lib.ldm_unet_destroy(h)
-        except Exception:
-            pass
+        self._destroy_native()

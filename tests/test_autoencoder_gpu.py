@@ -42,7 +42,10 @@ def test_autoencoder_matches_reference_golden(tag, dtype):
     assert ae.last_launches > 20
     rec = ae.decode(T(g["z"]).to(dev()))                    # teacher-forced: the reference's own latent
     assert rec.shape == img.shape and rel_l2(rec.cpu(), T(g["recon"])) < tol
-    out, mu, lv = ae(img, epsilon=T(g["epsilon"]).to(dev()))
+    with pytest.raises(Exception, match="inference-only"):   # backward does not exist: the module says so
+        ae(img, epsilon=T(g["epsilon"]).to(dev()))
+    with torch.no_grad():
+        out, mu, lv = ae(img, epsilon=T(g["epsilon"]).to(dev()))
     assert rel_l2(out.cpu(), T(g["forward_img"])) < 2 * tol
     assert torch.equal(mu, ae.distribution.mu)
     d2 = ae.encode(img)                                       # own noise: a different sample, same moments

@@ -139,7 +139,7 @@ def test_trainer_epochs_reduce_loss(graphs):
     y = torch.randint(0, 10, (16,), generator=gen)
     loader = [(x0, y)] * 12
     cfg = {"lr": 5e-4, "epochs": 1, "data": {"image_channels": 3, "image_size": 32}}
-    tr = trainer.DiffusionModelTrainer(cfg, model, d, loader, loader[:2], classes=torch.arange(4), cfg_scale=3.0,
+    tr = trainer.DiffusionModelTrainer(cfg, model, loader, loader[:2], torch.arange(4), d, 3.0,
                                        rng=np.random.default_rng(0), use_cuda_graphs=graphs)
     v0 = tr._val_epoch(0)
     first = tr._train_epoch(0)
