@@ -132,6 +132,46 @@ def cpu_sampling_rate(batch: int, timesteps: int, n_steps: int, cfg_scale: float
     return batch / (per_step * n_steps), per_step, torch.get_num_threads()
 
 
+def gpu_library_baseline(dev, batch, n_steps, cfg_scale, stream, timesteps=10):
+    """images/sec of the reference algorithm in eager PyTorch on the GPU: fp32 with cuDNN's TF32 convolutions (torch's
+    default) and bf16 autocast.  `timesteps` reverse steps are timed after 2 warm-up steps and extrapolated x T."""
+    import torch
+    import oracle
+    from oracle import unet_oracle as U, ddpm_oracle as D
+    out = {"sample": f"{timesteps} of {n_steps} timesteps at batch {batch} (2 UNet passes + p_sample each), extrapolated; eager "
+                     f"PyTorch {torch.__version__}, cuDNN {torch.backends.cudnn.version()}"}
+    try:
+        sd = {k: v.to(dev) for k, v in oracle.init_state_dict(42, 3, 3, 64, (1, 2, 4, 8), True, 10).items()}
+        sched = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in D.make_schedule(n_steps).items()}
+        cls = torch.tensor([3], device=dev)
+
+        def one_step(x, step):
+            t = torch.full((batch,), step, dtype=torch.long, device=dev)
+            eps = U.unet_forward(sd, x, t, cls)
+            if cfg_scale > 0:
+                eps = D.cfg_combine(eps, U.unet_forward(sd, x, t, None), cfg_scale)
+            return D.p_sample(sched, x.float(), t, eps.float(), torch.randn(x.shape, device=dev))
+
+        for name, ctx in (("fp32_tf32", torch.autocast("cuda", enabled=False)),
+                          ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+            with torch.cuda.stream(stream), torch.no_grad(), ctx:
+                x = torch.randn(batch, 3, 32, 32, device=dev)
+                for i in range(2):
+                    x = one_step(x, n_steps - 1 - i)
+                torch.cuda.synchronize(dev)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for i in range(timesteps):
+                    x = one_step(x, n_steps - 3 - i)
+                b.record(stream)
+                torch.cuda.synchronize(dev)
+            per_step = a.elapsed_time(b) / timesteps
+            out[name] = {"ms_per_timestep": per_step, "images_per_sec": batch / (per_step / 1e3 * n_steps)}
+    except Exception as exc:   # noqa: BLE001 -- context only: never let the library baseline break the bench line
+        out["error"] = f"{type(exc).__name__}: {exc}"
+    return out
+
+
 def run_reference(args):
     """The reference algorithm on the host CPU (oracle port), bounded sample; rank 0 only."""
     rank = int(os.environ.get("RANK", 0))
@@ -352,6 +392,49 @@ def run_ours(args):
                 model, classes_host, shape, dev, cfg_scale=cfg, x_T=x_T_host, seed=99, sample_offset=offset,
                 return_device=True), "save_image").cpu())
 
+            # ---- bounded-sample variants: K of the T timesteps are timed (every timestep costs the same: one 2B-row UNet
+            # pass + the fused update) and the rate is extrapolated to the full trajectory, x T / K
+            def rate_bounded(diff, mdl, shp, k, scale=cfg, reps=1):
+                def go():
+                    return diff.sample(mdl, classes_dev, shp, dev, cfg_scale=scale, seed=11, sample_offset=offset,
+                                       first_step=diff.n_steps - 1, num_steps=k, return_device=True)
+                go()
+                torch.cuda.synchronize(dev)
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(reps):
+                    go()
+                b.record(stream)
+                torch.cuda.synchronize(dev)
+                barrier()
+                ms = ldist.max_over_ranks(a.elapsed_time(b), dev) / reps
+                return shp[0] * world / (ms / 1e3 * diff.n_steps / k)
+
+            # BASELINE config 5 (augmentation-scale generation sweep): batch 64 ... 8192 per GPU
+            K = 20
+            sweep = {}
+            for bb in (64, 256, 1024, 4096, 8192):
+                try:
+                    sweep[str(bb)] = rate_bounded(diffusion, model, (bb, 3, 32, 32), K)
+                except Exception as exc:   # noqa: BLE001 -- e.g. not enough memory on a shared device: say so, keep going
+                    sweep[str(bb)] = f"failed: {exc}"
+                torch.cuda.empty_cache()
+            variants["batch_sweep_images_per_sec"] = dict(sweep, sample=f"{K} of {T} timesteps timed, extrapolated x{T}/{K}")
+            # BASELINE config 1: the MNIST-shaped model (1 channel; 32x32 because 28 is not divisible by 2^4)
+            torch.manual_seed(44)
+            mn = ldm_b200.UNet(1, 1, 64, (1, 2, 4, 8), True, 10, dtype=args.dtype).to(dev)
+            mn.requires_grad_(False)
+            variants["mnist_shaped_1x32x32_images_per_sec"] = rate_bounded(diffusion, mn, (B, 1, 32, 32), K)
+            del mn
+            # the fp32 parity path (FFMA implicit GEMM, <= 1e-4 against the reference): reported once, not optimised
+            torch.manual_seed(42)
+            m32 = ldm_b200.UNet(3, 3, 64, (1, 2, 4, 8), True, 10, dtype="fp32").to(dev)
+            m32.requires_grad_(False)
+            variants["fp32_parity_path_images_per_sec"] = rate_bounded(diffusion, m32, (64, 3, 32, 32), 4)
+            del m32
+            torch.cuda.empty_cache()
+
         # ---- roofline leg: every launch of one 2B-row UNet pass timed with CUDA events on this stream
         prof = None
         if rank == 0:
@@ -367,6 +450,13 @@ def run_ours(args):
                     for kk in a:
                         a[kk] += v[kk]
             prof = {k: {kk: vv / reps for kk, vv in v.items()} for k, v in acc.items()}
+
+    # ---- context: the same algorithm in eager PyTorch on this GPU (cuDNN / cuBLAS / ATen: "the Blackwell library stack",
+    # SURVEY.md 8(d)) -- the oracle's functional restatement of src/UNet.py + src/DDPM.py on CUDA tensors, outside every
+    # timed region of ours, on a bounded sample; a baseline, never a fallback
+    lib_base = None
+    if rank == 0 and not args.no_variants:
+        lib_base = gpu_library_baseline(dev, B, T, cfg, stream)
 
     # ---- secondary: the training step of the reference config (batch 64 per GPU, q_sample + fwd + bwd + grad
     # all-reduce + Adam), reported beside the headline, never instead of it
@@ -385,7 +475,7 @@ def run_ours(args):
     passes = 2 if cfg > 0 else 1
     unet_tflops = images * T * passes * UNET_GFLOP_PER_IMAGE / 1e3 / (ms_total / 1e3)
     conv_name = "conv_tc" if "conv_tc" in prof else "conv_ffma"
-    conv = prof[conv_name]
+    conv = prof.get(conv_name) or {"ms": 1e-9, "flops": 0.0, "bytes": 0.0, "launches": 1}
     total_ms = sum(v["ms"] for v in prof.values())
     achieved = conv["flops"] / (conv["ms"] / 1e3) / 1e12
     traffic = None
@@ -431,7 +521,12 @@ def run_ours(args):
                 "d2h_bytes_per_step": x_T_host.numel() * 4, "steps": e2e_steps},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_rec,
         "unet_tflops": unet_tflops, "variants": variants, "train": train, "train_batch256": train256,
+        "gpu_library_baseline": lib_base,
     }
+    if lib_base:
+        for k in ("fp32_tf32", "bf16_autocast"):
+            if isinstance(lib_base.get(k), dict):
+                lib_base[k]["ours_over_it"] = value / world / lib_base[k]["images_per_sec"]
     emit(line)
 
 

@@ -475,8 +475,12 @@ struct Prof {
     for (auto& r : recs) { if (r.e0) cudaEventDestroy(r.e0); if (r.e1) cudaEventDestroy(r.e1); }
   }
 };
+// LDM_SKIP_FAM (bit mask over the profile families; timing experiments only, results are wrong): the masked launches are
+// not issued, so the difference of two graph-replayed runs is a family's true cost inside the step
+static const int g_skip_fam = getenv("LDM_SKIP_FAM") ? atoi(getenv("LDM_SKIP_FAM")) : 0;
 #define PROF(fam, flops, bytes, call)                                   \
   do {                                                                  \
+    if (g_skip_fam & (1 << (fam))) break;                               \
     if (prof) RC(prof->begin((fam), (double)(flops), (double)(bytes))); \
     RC(call);                                                           \
     if (prof) RC(prof->end());                                          \

@@ -1,6 +1,7 @@
 """CPU: host-side logic -- the C-ABI library loads and exports every symbol include/ldm_b200.h declares,
 the drop-in classes keep the reference's surface, errors are loud (no fallback), and the multi-rank helpers
 work under a world_size-2 gloo group."""
+import importlib.util
 import os
 import re
 import sys
@@ -9,7 +10,7 @@ import pytest
 import torch
 import torch.multiprocessing as mp
 
-from conftest import ROOT
+from conftest import REFERENCE, ROOT
 
 
 def test_library_exports_every_declared_symbol(lib):
@@ -158,3 +159,77 @@ def test_bench_reference_arm_contract():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference is only mounted in the build container")
+def test_unmodified_generate_images_drives_the_native_classes(tmp_path, monkeypatch):
+    """The reference's own caller (generate_images.py:18-41, unmodified, imported from /root/reference) and its own factory
+    (src/utils.py:48-88) and YAML run over the `src.UNet` / `src.DDPM` shadow: every class the config names resolves to the
+    native implementation and `Diffusion.sample` is driven with the reference's call protocol -- ten batch-1 calls,
+    classes = tensor([i]), shape (1, C, S, S), cfg_scale 3 -- and the PNGs land where the reference writes them.
+    No GPU here: the CUDA entry point is replaced by a recorder (the numerics of that call are the -m gpu suites' job)."""
+    import importlib
+    import yaml
+    import ldm_b200
+    saved = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.") or k == "generate_images"}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REFERENCE)
+    try:
+        importlib.import_module("src")                                   # the reference's package ...
+        shadow = os.path.join(ROOT, "latent-diffusion-models_b200", "src")
+        for name in ("UNet", "DDPM"):                                    # ... with the two hot-path modules shadowed
+            spec = importlib.util.spec_from_file_location(f"src.{name}", os.path.join(shadow, f"{name}.py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[f"src.{name}"] = mod
+            spec.loader.exec_module(mod)
+        gen = importlib.import_module("generate_images")                 # the unmodified caller
+        from src.utils import get_model_from_config                      # the unmodified factory
+        cfg = yaml.safe_load(open(os.path.join(REFERENCE, "config_files", "pixel_diffusion_model_cifar10.yaml")))
+        cfg["diffusion"]["params"]["device"] = "cpu"                     # the YAML says cuda (SURVEY 8c shim)
+        diffusion = get_model_from_config(cfg["diffusion"])
+        model = get_model_from_config(cfg["model"])
+        assert type(model) is ldm_b200.UNet and type(diffusion) is ldm_b200.Diffusion
+        assert diffusion.n_steps == cfg["diffusion"]["params"]["n_steps"]
+        calls = []
+
+        def recorder(self, eps_model, classes, shape, device, cfg_scale=3, **kw):
+            calls.append((eps_model, classes.clone(), tuple(shape), str(device), cfg_scale, kw))
+            return torch.zeros(shape)                                    # a CPU tensor, as src/DDPM.py:128 returns
+
+        monkeypatch.setattr(ldm_b200.Diffusion, "sample", recorder)
+        monkeypatch.chdir(tmp_path)
+        gen.main(model, diffusion, cfg, "cpu")
+        assert len(calls) == model.num_classes == 10
+        for i, (m, classes, shape, device, scale, kw) in enumerate(calls):
+            assert m is model and classes.tolist() == [i] and classes.dtype == torch.int64
+            assert shape == (1, cfg["data"]["image_channels"], cfg["data"]["image_size"], cfg["data"]["image_size"])
+            assert scale == 3 and not kw
+        folder = tmp_path / cfg["diffusion"]["type"] / cfg["project_name"] / "results"
+        assert sorted(p.name for p in folder.iterdir()) == [str(i) for i in range(10)]
+        assert all(any(f.suffix == ".png" for f in (folder / str(i)).iterdir()) for i in range(10))
+    finally:
+        sys.path.remove(REFERENCE)
+        for k in [k for k in sys.modules if k == "src" or k.startswith("src.") or k == "generate_images"]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_native_state_is_not_shared_by_copies():
+    """copy.deepcopy / pickle of a UNet or Diffusion (EMA copies, best-model snapshots, torch.save(model)) must not carry
+    native handles: two Python owners of one ldm_unet* repack each other's weights and double-free."""
+    import copy
+    import pickle
+    import ldm_b200
+    m = ldm_b200.UNet(3, 3, 64, [1, 2], True, 10)
+    m._handles[(32, 0)] = 0xDEAD                      # as if a forward had created a native handle
+    m._loaded[0xDEAD] = ("fingerprint",)
+    for clone in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+        assert clone._handles == {} and clone._loaded == {} and clone._ws == {} and clone._uid != m._uid
+        assert all(torch.equal(a, b) for a, b in zip(clone.state_dict().values(), m.state_dict().values()))
+    m._handles.clear()                                # nothing real to destroy
+    d = ldm_b200.Diffusion(10, "cpu")
+    d._samplers[("key",)] = {"s": 0xBEEF, "unet": lambda: None}
+    c = copy.deepcopy(d)
+    assert c._samplers == {} and torch.equal(c.beta, d.beta)
+    d._samplers.clear()

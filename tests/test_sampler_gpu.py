@@ -118,3 +118,18 @@ def test_full_trajectory_vs_reference(dtype, std_tol, mean_tol, x_tol):
                      return_device=True, seed=0)
     assert rel_l2(x, T(g["out"])) < x_tol
     assert worst_std < std_tol and worst_mean < mean_tol, (worst_std, worst_mean)
+
+
+@pytest.mark.parametrize("dtype,x_tol", [("fp32", 2e-3), ("bf16", 2e-2)])
+def test_free_running_sample_call_vs_reference(dtype, x_tol):
+    """ONE Diffusion.sample() call over all 1000 timesteps (the graph-replayed loop, not 1000 single-step calls) with the
+    reference's x_T and per-step noise lands on the reference's final image (golden G6 `out`)."""
+    import ldm_b200
+    g = golden("g6_trajectory_T1000.npz")
+    Tn, shape = 1000, (2, 3, 32, 32)
+    m, _ = make_model(dtype, seed=int(g["weight_seed"]))
+    x_T, noise = _reference_noise(g, Tn, shape)
+    d = ldm_b200.Diffusion(Tn, dev())
+    out = d.sample(m, torch.tensor([3]), shape, dev(), cfg_scale=3, x_T=x_T, noise=noise.to(dev()), seed=0)
+    assert not out.is_cuda and out.shape == shape            # the reference returns a CPU tensor (src/DDPM.py:128)
+    assert rel_l2(out, T(g["out"])) < x_tol

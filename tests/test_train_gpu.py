@@ -27,7 +27,14 @@ def _oracle_grads(sd, xt, t, y, noise):
     return float(loss), eps.detach(), {k: v.grad for k, v in p.items()}
 
 
-@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-3), ("bf16", 8e-2)])
+# bf16 tolerances = 3x the floor of the REFERENCE's own bf16-autocast gradients against its fp32 gradients on the same inputs
+# (oracle/measure_bf16_grad_floor.py -> tests/golden/bf16_grad_floor.json: |grad| rel. error max 4.6e-3, element-wise
+# rel-L2 max 1.3e-2)
+BF16_NORM_TOL = 1.4e-2
+BF16_L2_TOL = 4e-2
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-3), ("bf16", BF16_NORM_TOL)])
 def test_train_step_gradients_vs_reference(dtype, tol):
     """Golden G5: same inputs as the reference run; loss, eps and per-parameter gradient fingerprints."""
     g = golden("g5_train_grads.npz")
@@ -62,7 +69,7 @@ def test_train_step_gradients_vs_reference(dtype, tol):
     print("worst |grad| error", worst)
 
 
-@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-3), ("bf16", 1e-1)])
+@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-3), ("bf16", BF16_L2_TOL)])
 def test_full_gradients_vs_oracle_autograd(dtype, tol):
     """Every gradient tensor, element-wise, against autograd through the CPU oracle (broadcast label, batch 2)."""
     m, sd = make_model(dtype, seed=3)
@@ -76,15 +83,17 @@ def test_full_gradients_vs_oracle_autograd(dtype, tol):
     loss = torch.nn.functional.mse_loss(noise.to(dev()), eps)
     loss.backward()
     assert abs(float(loss) - loss_ref) / loss_ref < tol
-    bad = []
+    bad, worst = [], 0.0
     for n, p in m.named_parameters():
         ref = grads[n]
         if ref is None:
             assert p.grad is None, n
             continue
         e = rel_l2(p.grad, ref)
+        worst = max(worst, e)
         if e > tol:
             bad.append((n, e))
+    print("worst element-wise gradient rel-L2", dtype, worst)
     assert not bad, bad[:10]
 
 
@@ -127,3 +136,41 @@ def test_adam_steps_reduce_the_loss():
     with torch.no_grad():
         e1 = m(xt, t, y)
     assert abs(float(torch.nn.functional.mse_loss(noise, e1)) - losses[-1]) < 0.5 * losses[0]
+
+
+def test_graphed_training_step_matches_eager_and_reference():
+    """The CUDA-graph-captured forward/backward (what bench.py's training leg and DiffusionModelTrainer time) produces the
+    same gradients as the eager autograd path, and both match golden G5 of the unmodified reference."""
+    from ldm_b200.train import make_graphed
+    g = golden("g5_train_grads.npz")
+    xt, t, y, noise = (T(g[k]).to(dev()) for k in ("xt", "t", "y", "noise"))
+    m, _ = make_model("bf16", seed=int(g["weight_seed"]))
+    m.train()
+    # eager
+    torch.nn.functional.mse_loss(noise, m(xt, t, y)).backward()
+    eager = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad(set_to_none=True)
+    # graphed (captured on other data of the same shape, replayed on G5's inputs)
+    gen = torch.Generator().manual_seed(1)
+    fwd = make_graphed(m, torch.randn(xt.shape, generator=gen).to(dev()), torch.randint(0, 1000, t.shape, generator=gen).to(dev()),
+                       torch.randint(0, 10, y.shape, generator=gen).to(dev()))
+    m.zero_grad(set_to_none=True)
+    eps = fwd(xt, t, y)
+    loss = torch.nn.functional.mse_loss(noise, eps)
+    loss.backward()
+    assert rel_l2(eps, T(g["eps"])) < 2e-2
+    names = [str(n) for n in g["names"]]
+    params = dict(m.named_parameters())
+    worst_e = worst_g = 0.0
+    for i, n in enumerate(names):
+        p = params[n]
+        if not g["has_grad"][i]:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, n      # unused graph input: no gradient
+            continue
+        assert p.grad is not None, n
+        worst_e = max(worst_e, rel_l2(p.grad, eager[n]))
+        want = float(g["grad_norm"][i])
+        worst_g = max(worst_g, abs(float(p.grad.double().norm()) - want) / max(want, 1e-12))
+    print("graphed vs eager rel-L2", worst_e, "graphed |grad| vs reference", worst_g)
+    assert worst_e < 1e-6, "graph replay must reproduce the eager kernels' gradients (same kernels, same order)"
+    assert worst_g < BF16_NORM_TOL
