@@ -322,6 +322,22 @@ int ldm_copy_channels(const void* src, int ld_src, void* dst, int ld_dst, int ch
 int ldm_linear_attention_qkv(const void* xn, int ldx, int cin, const void* wqkv_packed, void* out, int batch, int n_tokens,
                              int dtype, void* stream);
 
+/* Residual(PreNorm(LinearAttention)) up to the attention output, as the sampler runs it on 64-channel sites: GroupNorm(1, C)
+ * statistics of the raw input x [B, N, ldx], the norm folded into to_qkv (w_qkv: fp32 [384][cin], PyTorch layout; gamma / beta:
+ * the PreNorm's affine), both softmaxes and both einsums -> out [B, N, 128]  (src/UNet.py:106-110,145,149-163).
+ *   impl 0: tcgen05 / TMEM / TMA kernel (N % 128 == 0);  impl 1: the mma.sync kernel (N % 16 == 0).
+ *   scratch: ldm_linear_attention_prenorm_scratch_bytes(batch) bytes, 256-byte aligned. */
+int64_t ldm_linear_attention_prenorm_scratch_bytes(int batch);
+int ldm_linear_attention_prenorm(const void* x, int ldx, int cin, const float* w_qkv, const float* gamma, const float* beta,
+                                 float eps, void* out, int batch, int n_tokens, int impl, void* scratch, int64_t scratch_bytes,
+                                 void* stream);
+/* The same with LinearAttention.to_out's 1x1 convolution folded in (src/UNet.py:146; tcgen05 kernel only): y [B, N, ldy] =
+ * to_out.0(attention) incl. bias (64 channels), and ystats (fp32 [batch][n_tokens / 16][2]) = partial sums {S, Q} of y per
+ * (32-token block, 32-channel half) for the GroupNorm(1, C) that follows (:147).  w_out: fp32 [64][128]. */
+int ldm_linear_attention_prenorm_to_out(const void* x, int ldx, int cin, const float* w_qkv, const float* gamma, const float* beta,
+                                        float eps, const float* w_out, const float* b_out, void* y, int ldy, float* ystats,
+                                        int batch, int n_tokens, void* scratch, int64_t scratch_bytes, void* stream);
+
 /* ---- after the hot path: optimizer step, validation loss, image output ----------------- */
 
 /* torch.optim.Adam(params, lr) with its defaults, as src/Trainer.py:68-71 constructs it (no weight decay, no amsgrad),

@@ -116,6 +116,11 @@ SIGNATURES = {
     "ldm_add": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int, vp]),
     "ldm_copy_channels": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp]),
     "ldm_linear_attention_qkv": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "ldm_linear_attention_prenorm_scratch_bytes": (C.c_int64, [C.c_int]),
+    "ldm_linear_attention_prenorm": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, C.c_float, vp, C.c_int, C.c_int, C.c_int, vp,
+                                               C.c_int64, vp]),
+    "ldm_linear_attention_prenorm_to_out": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, C.c_float, vp, vp, vp, C.c_int, vp, C.c_int,
+                                                      C.c_int, vp, C.c_int64, vp]),
     "ldm_upsample_nearest2x": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_downsample_pick": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_attention_single_head": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),

@@ -186,6 +186,86 @@ gn_fused_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, co
   }
 }
 
+// ------------------------------------------------------------------ max-pool 2x2 + GroupNorm (+SiLU), bf16
+// Encoder level transition (src/UNet.py:183,193 MaxPool2d(2,2), then the next ResNetBlock's block1.norm + SiLU, :52-58):
+// one CTA per sample reads the 2x2 windows ONCE, keeps the pooled sample in registers (NJ chunks per thread), writes the
+// pooled tensor (the block's residual / shortcut input) and, after exact two-pass statistics, the normalised one.
+// Replaces three launches (maxpool2, gn_stats, gn_apply) and two re-reads of the pooled tensor.
+template <int NJ>
+__global__ void __launch_bounds__(256)
+pool_gn_kernel(const bf16* __restrict__ x, int ldx, int W, bf16* __restrict__ pool, int ldp, bf16* __restrict__ y, int ldy,
+               const float* __restrict__ gamma, const float* __restrict__ beta, int HW2, int C, int G, float eps, int silu) {
+  constexpr int V = 8;
+  __shared__ float part[256];
+  __shared__ float gsum[GN_MAX_GROUPS];
+  pdl_wait();
+  pdl_trigger();
+  const int n = blockIdx.x;
+  const int cpp = C / V, cpg = cpp / G;
+  const int ci = threadIdx.x % cpp, pl = threadIdx.x / cpp, ppi = blockDim.x / cpp;
+  const int g = ci / cpg;
+  const int W2 = W / 2;
+  const bf16* xs = x + (int64_t)n * (4 * HW2) * ldx + ci * V;     // source image: (2 H2) x W pixels
+  uint4 raw[NJ];
+  float w[V];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int p = pl + j * ppi;
+    raw[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (p < HW2) {
+      const int py = p / W2, px = p - py * W2;
+      const bf16* s0 = xs + ((int64_t)(2 * py) * W + 2 * px) * ldx;
+      const uint4 a = load_raw(s0), b = load_raw(s0 + ldx), c = load_raw(s0 + (int64_t)W * ldx), d = load_raw(s0 + (int64_t)(W + 1) * ldx);
+      const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+      const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+      const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&c);
+      const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&d);
+      __nv_bfloat162* hr = reinterpret_cast<__nv_bfloat162*>(&raw[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hr[i] = __hmax2(__hmax2(ha[i], hb[i]), __hmax2(hc[i], hd[i]));
+      *reinterpret_cast<uint4*>(pool + ((int64_t)n * HW2 + p) * ldp + ci * V) = raw[j];
+      unpack(raw[j], w);
+#pragma unroll
+      for (int i = 0; i < V; ++i) s += w[i];
+    }
+  }
+  const float inv_n = 1.0f / ((float)HW2 * (float)(cpg * V));
+  const float mean = group_reduce(s, part, gsum, G, cpp, cpg, g) * inv_n;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    if (pl + j * ppi < HW2) {
+      unpack(raw[j], w);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { const float d = w[i] - mean; q = fmaf(d, d, q); }
+    }
+  }
+  __syncthreads();
+  const float var = group_reduce(q, part, gsum, G, cpp, cpg, g) * inv_n;
+  const float rstd = 1.0f / sqrtf(var + eps);
+  float a[V], b[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    a[i] = gamma[ci * V + i] * rstd;
+    b[i] = beta[ci * V + i] - mean * a[i];
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int p = pl + j * ppi;
+    if (p < HW2) {
+      unpack(raw[j], w);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float o = fmaf(w[i], a[i], b[i]);
+        if (silu) o = silu_fast(o);
+        w[i] = o;
+      }
+      store_chunk(y + ((int64_t)n * HW2 + p) * ldy + ci * V, w);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ (A) streaming stats + apply, bf16
 constexpr int GS_THREADS = 256;
 constexpr int GS_MAX_SPLITS = 16;
@@ -669,6 +749,27 @@ int k_group_norm_apply_raw(const void* x, int ldx, void* y, int ldy, const void*
     LDM_CUDA(ldm_launch_pdl(gn_apply_kernel<false>, grid, dim3(threads), 0, st, (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)res,
                             ldres, gamma, beta, (const float*)nullptr, 0, (const float2*)part, -nslots, hw, channels, groups, eps, silu, ppb, x_mod));
   LDM_LAUNCHED("gn_apply");
+  return 0;
+}
+
+// max-pool 2x2 of x [B, H, W, ldx] (C channels) -> pool [B, H/2, W/2, ldp] and y = [silu](GroupNorm(pool)) [B, H/2, W/2, ldy]
+bool k_pool_group_norm_applicable(int H, int W, int C, int groups, int dtype) {
+  if (dtype != LDM_DT_BF16 || H % 2 || W % 2 || C % 8 || groups < 1 || groups > GN_MAX_GROUPS) return false;
+  const int cpp = C / 8;
+  if (cpp > 256 || 256 % cpp != 0 || C % groups != 0 || (C / groups) % 8 != 0) return false;
+  const int hw2 = (H / 2) * (W / 2), ppi = 256 / cpp;
+  return (hw2 + ppi - 1) / ppi <= 8 && getenv("LDM_NO_POOL_GN") == nullptr;
+}
+int k_pool_group_norm(const void* x, int ldx, int H, int W, int C, void* pool, int ldp, void* y, int ldy, const float* gamma,
+                      const float* beta, int groups, float eps, int silu, int batch, cudaStream_t st) {
+  LDM_REQUIRE(k_pool_group_norm_applicable(H, W, C, groups, LDM_DT_BF16) && ldx % 8 == 0 && ldp % 8 == 0 && ldy % 8 == 0,
+              "pool_group_norm: unsupported shape %dx%dx%d", H, W, C);
+  if (batch == 0) return 0;
+  const int hw2 = (H / 2) * (W / 2), ppi = 256 / (C / 8), nj = (hw2 + ppi - 1) / ppi;
+#define PG_GO(NJV) LDM_CUDA(ldm_launch_pdl(pool_gn_kernel<NJV>, dim3(batch), dim3(256), 0, st, (const bf16*)x, ldx, W, (bf16*)pool, ldp, (bf16*)y, ldy, gamma, beta, hw2, C, groups, eps, silu))
+  if (nj <= 1) PG_GO(1); else if (nj <= 2) PG_GO(2); else if (nj <= 4) PG_GO(4); else PG_GO(8);
+#undef PG_GO
+  LDM_LAUNCHED("pool_group_norm");
   return 0;
 }
 

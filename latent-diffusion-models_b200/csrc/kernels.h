@@ -67,6 +67,10 @@ int k_group_norm_mod(const void* x, int ldx, void* y, int ldy, const void* res, 
                      const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
                      float eps, int silu, int dtype, void* workspace, int x_mod, cudaStream_t st);
 bool k_group_norm_streams(int hw, int channels, int dtype);
+// max-pool 2x2 + GroupNorm (+SiLU) in one kernel: pooled tensor and its normalised form (encoder level transitions)
+bool k_pool_group_norm_applicable(int H, int W, int C, int groups, int dtype);
+int k_pool_group_norm(const void* x, int ldx, int H, int W, int C, void* pool, int ldp, void* y, int ldy, const float* gamma,
+                      const float* beta, int groups, float eps, int silu, int batch, cudaStream_t st);
 int k_group_norm_apply_raw(const void* x, int ldx, void* y, int ldy, const void* res, int ldres, const float* gamma,
                            const float* beta, const float* rowvec, int ld_rowvec, int batch, int hw, int channels, int groups,
                            float eps, int silu, const void* part, int nslots, int x_mod, cudaStream_t st);
@@ -83,6 +87,19 @@ int k_linear_attention_qkv(const void* xn, int ldx, int cin, const void* wqkv, v
 // statistics left by k_group_norm_stats (groups = 1).
 int k_linear_attention_qkv_prenorm(const void* x, int ldx, int cin, const void* wfold, const float* uv, const void* gn_part,
                                    int gn_splits, float eps, void* out, int batch, int n_tokens, int dtype, cudaStream_t st);
+// The same on tcgen05 / TMEM / TMA (linattn_tc.cu): N % 128 == 0; uv == null: plain to_qkv weights on an already normalised x
+bool k_linear_attention_tc_applicable(int cin, int n_tokens, int dtype);
+// fuse != null: LinearAttention.to_out's 1x1 convolution (src/UNet.py:146) is folded in -- y [B, N, ldy] (64 channels, bf16) =
+// out Wout^T + bout, and ystats receives GroupNorm(1, 64) partial sums {S, Q} of y ([batch][nslots], the ConvGn mode-1 layout)
+struct LinAttnOut {
+  const void* wout;            // packed [64][128] bf16 (k_pack_conv_weight of to_out.0.weight)
+  const float* bout;           // [64]
+  void* y; int ldy;
+  void* ystats; int64_t ystats_bytes;
+  int* nslots_out;
+};
+int k_linear_attention_tc(const void* x, int ldx, const void* wqkv, const float* uv, const void* gn_part, int gn_splits, float eps,
+                          void* out, int batch, int n_tokens, cudaStream_t st, const LinAttnOut* fuse = nullptr);
 int k_fold_prenorm_qkv(const float* wqkv /*[384][cin] fp32*/, const float* gamma, const float* beta, int cin, void* wfold,
                        float* uv, cudaStream_t st);
 int k_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, cudaStream_t st);

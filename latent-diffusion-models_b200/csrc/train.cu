@@ -211,6 +211,53 @@ int ldm_time_proj_backward(const float* temb, const float* w, const float* dtpro
   return 0;
 }
 
+int64_t ldm_linear_attention_prenorm_scratch_bytes(int batch) {
+  return 384 * 64 * 2 + 768 * 4 + 1024 + 64 * 128 * 2 + k_group_norm_ws_bytes(batch > 0 ? batch : 1, 1);
+}
+int ldm_linear_attention_prenorm(const void* x, int ldx, int cin, const float* w_qkv, const float* gamma, const float* beta,
+                                 float eps, void* out, int batch, int n_tokens, int impl, void* scratch, int64_t scratch_bytes,
+                                 void* stream) {
+  LDM_REQUIRE(x && w_qkv && gamma && beta && out && scratch, "ldm_linear_attention_prenorm: null argument");
+  LDM_REQUIRE(cin == 64, "ldm_linear_attention_prenorm: the fused kernels take 64 input channels");
+  LDM_REQUIRE(scratch_bytes >= ldm_linear_attention_prenorm_scratch_bytes(batch) && ((uintptr_t)scratch & 255) == 0,
+              "ldm_linear_attention_prenorm: scratch too small or unaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* s = (uint8_t*)scratch;
+  void* wfold = s;
+  float* uv = (float*)(s + 384 * 64 * 2);
+  void* gnws = s + 384 * 64 * 2 + 768 * 4 + 1024 - ((384 * 64 * 2 + 768 * 4) % 1024);
+  if (int rc = k_fold_prenorm_qkv(w_qkv, gamma, beta, cin, wfold, uv, st)) return rc;
+  int splits = 1;
+  if (int rc = k_group_norm_stats(x, ldx, batch, n_tokens, cin, 1, gnws, &splits, st)) return rc;
+  if (impl == 0) {
+    LDM_REQUIRE(k_linear_attention_tc_applicable(cin, n_tokens, LDM_DT_BF16), "ldm_linear_attention_prenorm: tcgen05 kernel needs N %% 128 == 0");
+    return k_linear_attention_tc(x, ldx, wfold, uv, gnws, splits, eps, out, batch, n_tokens, st);
+  }
+  return k_linear_attention_qkv_prenorm(x, ldx, cin, wfold, uv, gnws, splits, eps, out, batch, n_tokens, LDM_DT_BF16, st);
+}
+int ldm_linear_attention_prenorm_to_out(const void* x, int ldx, int cin, const float* w_qkv, const float* gamma, const float* beta,
+                                        float eps, const float* w_out, const float* b_out, void* y, int ldy, float* ystats,
+                                        int batch, int n_tokens, void* scratch, int64_t scratch_bytes, void* stream) {
+  LDM_REQUIRE(x && w_qkv && gamma && beta && w_out && b_out && y && ystats && scratch, "ldm_linear_attention_prenorm_to_out: null argument");
+  LDM_REQUIRE(cin == 64 && k_linear_attention_tc_applicable(cin, n_tokens, LDM_DT_BF16),
+              "ldm_linear_attention_prenorm_to_out: needs 64 channels and a multiple of 128 tokens");
+  LDM_REQUIRE(scratch_bytes >= ldm_linear_attention_prenorm_scratch_bytes(batch) && ((uintptr_t)scratch & 255) == 0,
+              "ldm_linear_attention_prenorm_to_out: scratch too small or unaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* s = (uint8_t*)scratch;
+  void* wfold = s;
+  float* uv = (float*)(s + 384 * 64 * 2);
+  void* wout = s + 384 * 64 * 2 + 768 * 4 + 1024;                       // packed [64][128] bf16 (16 KB)
+  void* gnws = s + 384 * 64 * 2 + 768 * 4 + 1024 + 64 * 128 * 2;
+  if (int rc = k_fold_prenorm_qkv(w_qkv, gamma, beta, cin, wfold, uv, st)) return rc;
+  if (int rc = k_pack_conv_weight(w_out, 64, 128, 1, nullptr, 0, wout, LDM_DT_BF16, st)) return rc;
+  int splits = 1;
+  if (int rc = k_group_norm_stats(x, ldx, batch, n_tokens, cin, 1, gnws, &splits, st)) return rc;
+  LinAttnOut f;
+  f.wout = wout; f.bout = b_out; f.y = y; f.ldy = ldy; f.ystats = ystats; f.ystats_bytes = (int64_t)batch * (n_tokens / 16) * 8;
+  f.nslots_out = nullptr;
+  return k_linear_attention_tc(x, ldx, wfold, uv, gnws, splits, eps, nullptr, batch, n_tokens, st, &f);
+}
 int ldm_linear_attention_qkv(const void* xn, int ldx, int cin, const void* wqkv_packed, void* out, int batch, int n_tokens,
                              int dtype, void* stream) {
   LDM_REQUIRE(xn && wqkv_packed && out, "ldm_linear_attention_qkv: null argument");

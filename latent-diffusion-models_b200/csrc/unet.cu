@@ -198,7 +198,7 @@ int64_t layout_all(ldm_unet* h, uint8_t* base) {
 
 // workspace plan for one forward of `batch` rows
 struct Plan {
-  int64_t temb, tproj, temb_tab, tproj_tab, gnws, gnpk, gnpk_bytes, gnst, gnst_bytes, qkv, s[4], total;
+  int64_t temb, tproj, temb_tab, tproj_tab, gnws, gnpk, gnpk_bytes, gnst, gnst_bytes, gnst2, gnst2_bytes, qkv, s[4], total;
   std::vector<int64_t> hin;  // [L+1]
   std::vector<int64_t> cat;  // [L]
 };
@@ -220,6 +220,9 @@ Plan make_plan(const ldm_unet* h, int batch) {
   // (8 groups x 2 variants x (36 or S*S/32) row blocks of the full-resolution level)
   p.gnst_bytes = (int64_t)batch * std::max<int64_t>(640, ((int64_t)S * S / 32 + 4) * 16) * 8;
   p.gnst = take(p.gnst_bytes);
+  // GroupNorm(1, C) partial sums the fused attention kernel leaves for to_out's GroupNorm: S*S/16 slots per sample
+  p.gnst2_bytes = (int64_t)batch * std::max<int64_t>(64, (int64_t)S * S / 16) * 8;
+  p.gnst2 = take(p.gnst2_bytes);
   int64_t max_elems = 0;
   for (int i = 0; i < L; ++i) {
     int64_t R = S >> i;
@@ -510,8 +513,15 @@ struct Fwd {
   // Normalising in the producer's epilogue (mode 2) pays where a work unit holds whole samples; where a sample spans many
   // tiles (32x32: packets, deferred second pass) the epilogue becomes the kernel's bottleneck -- measured in round 2
   // (profiles/README.md): those layers keep separate GroupNorm kernels fed by epilogue statistics.
+  // Small batches (generate_images.py: one image per call) are launch-latency bound, not epilogue bound: with
+  // LDM_GN_NORM_SMALL_BATCH=1 every GroupNorm rides in its producing convolution there (~20 launches fewer per timestep,
+  // 724 vs 765 ms per batch-1 image).  Opt-in, because the choice then depends on the batch size and the two paths round
+  // differently (fp32 accumulator vs stored bf16 value): a sample's bits would no longer be independent of its batch.
   int norm_max_hw = 64;
-  bool gn_norm_ok(int R) const { return gn_ok(R) && R * R <= norm_max_hw; }
+  bool small_batch_norm = false;
+  bool gn_norm_ok(int R) const {
+    return gn_ok(R) && (R * R <= norm_max_hw || (small_batch_norm && (int64_t)B * R * R <= 128 * 148));
+  }
   ConvGn gn_norm(const float* gamma, const float* beta, int groups, int silu, const float* rowvec, int ldrv, const void* res,
                  int ldres, int nvar = 1, int var_rows = 0) {
     ConvGn g;
@@ -574,7 +584,8 @@ struct Fwd {
   // ResNetBlock  src/UNet.py:85-99.  x must not alias s0/s1/out.
   // x_rows > 0: x holds only x_rows distinct images and output row n belongs to image n % x_rows (the sampler's cond and
   // uncond halves are identical up to the first time-embedding add): norm1 + conv1 run once per distinct image.
-  int resblock(const ResW& r, const void* x, int ldx, void* out, int ldo, int R, bool use_t, int x_rows = 0) {
+  // x_normed: s(0) already holds SiLU(GroupNorm(8)(x)) (written by the fused max-pool + GroupNorm kernel of the level above)
+  int resblock(const ResW& r, const void* x, int ldx, void* out, int ldo, int R, bool use_t, int x_rows = 0, bool x_normed = false) {
     const bool stats = want_stats && gn_ok(R);   // leave GroupNorm(1, C) statistics of the block output for the PreNorm that follows
     want_stats = false;
     st_slots = 0;
@@ -618,7 +629,7 @@ struct Fwd {
     }
     if (r.dense2 && R == 2 && ldx == r.cin && ldo == r.cout && impl == 0 && dt == LDM_DT_BF16) {
       // [B][4][C] NHWC == [B][4C]: both convs as 1x1 GEMMs over "images" of one pixel with 4C channels
-      RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
+      if (!x_normed) RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
       RC(conv(s(0), 4 * r.cin, 4 * r.cin, nullptr, 0, 0, r.w1d, r.b1d, nullptr, 0, nullptr, 0, s(1), 4 * r.cout, 4 * r.cout, 1, 1));
       const float* rvd = (use_t && r.tproj_off >= 0) ? tproj + r.tproj_off : nullptr;
       if (rvd && join_event) {
@@ -632,12 +643,12 @@ struct Fwd {
       return conv(s(0), 4 * r.cout, 4 * r.cout, nullptr, 0, 0, r.w2d, r.b2d, nullptr, 0, x, 4 * ldx, out, 4 * ldo, 4 * r.cout, 1, 1);
     }
     if (r.dense1 && R == 1 && !(use_t && r.tproj_off >= 0) && impl == 0 && dt == LDM_DT_BF16) {
-      RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
+      if (!x_normed) RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
       RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1c, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, 1, 1));
       RC(gn(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, R, r.cout, 8, 1));
       return conv(s(0), r.cout, r.cout, nullptr, 0, 0, r.w2c, r.b2, nullptr, 0, x, ldx, out, ldo, r.cout, 1, 1);
     }
-    RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
+    if (!x_normed) RC(gn(x, ldx, s(0), r.cin, nullptr, 0, r.g1, r.be1, R, r.cin, 8, 1));
     // the time-embedding projection (h = h + mlp_t(t), :88-93) is a per-sample channel vector: it enters block2's
     // GroupNorm statistics and shift, not the convolution
     const float* rv = (use_t && r.tproj_off >= 0) ? tproj + r.tproj_off : nullptr;
@@ -692,10 +703,31 @@ struct Fwd {
       int splits = 1;
       if (slots > 0) splits = -slots;   // statistics left by the producing convolution's epilogue
       else PROF(LDM_FAM_GROUP_NORM, 0, (double)B * N * a.dim * es, k_group_norm_stats(d, ldd, B, R * R, a.dim, 1, gnws(), &splits, st));
-      PROF(LDM_FAM_LINEAR_ATTENTION, (double)B * (2.0 * N * 3 * HIDDEN * a.dim + 4 * 2 * 2.0 * N * 32 * 32),
-           (double)B * N * (a.dim + HIDDEN) * es,
-           k_linear_attention_qkv_prenorm(d, ldd, a.dim, a.wfold, a.uv, slots > 0 ? (const void*)(ws + plan.gnst) : gnws(), splits,
-                                          GN_EPS, qkv, B, R * R, dt, st));
+      const void* gpart = slots > 0 ? (const void*)(ws + plan.gnst) : gnws();
+      static const bool fold_out = getenv("LDM_LINATTN_NO_TO_OUT") == nullptr;
+      if (k_linear_attention_tc_applicable(a.dim, R * R, dt) && fold_out && k_group_norm_streams(R * R, a.dim, dt)) {
+        // tcgen05 kernel with to_out's 1x1 convolution folded into the per-sample context matrix: it emits to_out's output
+        // (64 channels instead of the 128-channel attention tensor + a conv launch) and the partial sums of to_out's
+        // GroupNorm(1, C); one apply kernel adds the residual
+        int ns = 0;
+        LinAttnOut fo;
+        fo.wout = a.wout; fo.bout = a.bout; fo.y = s(1); fo.ldy = a.dim; fo.ystats = ws + plan.gnst2; fo.ystats_bytes = plan.gnst2_bytes;
+        fo.nslots_out = &ns;
+        PROF(LDM_FAM_LINEAR_ATTENTION, (double)B * (2.0 * N * 3 * HIDDEN * a.dim + 4 * 2 * 2.0 * N * 32 * 32 + 2.0 * N * HIDDEN * a.dim),
+             (double)B * N * (a.dim + a.dim) * es,
+             k_linear_attention_tc(d, ldd, a.wfold, a.uv, gpart, splits, GN_EPS, nullptr, B, R * R, st, &fo));
+        PROF(LDM_FAM_GROUP_NORM, 0, (double)B * N * a.dim * es * 3,
+             k_group_norm_apply_raw(s(1), a.dim, out, ldo, d, ldd, a.og, a.ob, nullptr, 0, B, R * R, a.dim, 1, GN_EPS, 0, ws + plan.gnst2, ns, 0, st));
+        return 0;
+      }
+      if (k_linear_attention_tc_applicable(a.dim, R * R, dt))   // tcgen05 / TMEM kernel (linattn_tc.cu)
+        PROF(LDM_FAM_LINEAR_ATTENTION, (double)B * (2.0 * N * 3 * HIDDEN * a.dim + 4 * 2 * 2.0 * N * 32 * 32),
+             (double)B * N * (a.dim + HIDDEN) * es,
+             k_linear_attention_tc(d, ldd, a.wfold, a.uv, gpart, splits, GN_EPS, qkv, B, R * R, st));
+      else
+        PROF(LDM_FAM_LINEAR_ATTENTION, (double)B * (2.0 * N * 3 * HIDDEN * a.dim + 4 * 2 * 2.0 * N * 32 * 32),
+             (double)B * N * (a.dim + HIDDEN) * es,
+             k_linear_attention_qkv_prenorm(d, ldd, a.dim, a.wfold, a.uv, gpart, splits, GN_EPS, qkv, B, R * R, dt, st));
       return to_out(qkv);
     }
     if (slots > 0 && dt == LDM_DT_BF16 && k_group_norm_streams(R * R, a.dim, dt)) {
@@ -788,6 +820,7 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
   f.ws = (uint8_t*)workspace;
   f.fuse_gn = f.dt == LDM_DT_BF16 && f.impl == 0 && getenv("LDM_NO_GN_FUSE") == nullptr;
   if (const char* e = getenv("LDM_GN_NORM_MAXHW")) f.norm_max_hw = atoi(e);
+  f.small_batch_norm = getenv("LDM_GN_NORM_SMALL_BATCH") != nullptr && atoi(getenv("LDM_GN_NORM_SMALL_BATCH")) != 0;
   if (f.fuse_gn)   // packet area of the fused GroupNorm epilogues: zero = no packet; every launch below gets its own tag
     LDM_CUDA(cudaMemsetAsync(f.ws + f.plan.gnpk, 0, f.plan.gnpk_bytes, f.st));
   const int L = h->L, S = h->d.image_size;
@@ -853,6 +886,7 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
   RC(f.tap("initial", hin0, h->dims[0], h->dims[0], S));
   f.join_event = time_forked ? h->ev_join : nullptr;
   // ---- encoder  src/UNet.py:200-209
+  bool pooled_normed = false;   // s(0) holds SiLU(GroupNorm(hin)) of the level about to run
   for (int i = 0; i < L; ++i) {
     const int R = S >> i, cout = h->dims[i + 1];
     const int j = L - 1 - i;                          // decoder level consuming this skip
@@ -861,12 +895,19 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
     void* skip = cat + (int64_t)h->dims[i] * f.es;    // skip occupies channels [dims[i], catc)
     void* hin = f.ws + f.plan.hin[i];
     f.want_stats = true;
-    RC(f.resblock(h->enc_res[i], hin, h->dims[i], f.s(2), cout, R, true, (i == 0 && share_prefix) ? x_batch : 0));
+    RC(f.resblock(h->enc_res[i], hin, h->dims[i], f.s(2), cout, R, true, (i == 0 && share_prefix) ? x_batch : 0, pooled_normed));
     RC(f.tap(("enc" + std::to_string(i) + ".res").c_str(), f.s(2), cout, cout, R));
     RC(f.attn_block(h->enc_attn[i], f.s(2), cout, skip, catc, R));
     RC(f.tap(("enc" + std::to_string(i) + ".attn").c_str(), skip, catc, cout, R));
-    PROF(LDM_FAM_OTHER, 0, (double)batch * R * R * cout * f.es * 1.25,
-         k_maxpool2(skip, catc, f.ws + f.plan.hin[i + 1], cout, batch, R, R, cout, f.dt, f.st));
+    // MaxPool2d(2,2) and the next ResNetBlock's block1.norm + SiLU in one kernel (one CTA per sample holds the pooled sample)
+    const ResW& nxt = i + 1 < L ? h->enc_res[i + 1] : h->bott1;
+    pooled_normed = f.fuse_gn && !h->tap.out && k_pool_group_norm_applicable(R, R, cout, 8, f.dt) && nxt.cin == cout;
+    if (pooled_normed)
+      PROF(LDM_FAM_GROUP_NORM, 0, (double)batch * R * R * cout * f.es * 1.5,
+           k_pool_group_norm(skip, catc, R, R, cout, f.ws + f.plan.hin[i + 1], cout, f.s(0), cout, nxt.g1, nxt.be1, 8, GN_EPS, 1, batch, f.st));
+    else
+      PROF(LDM_FAM_OTHER, 0, (double)batch * R * R * cout * f.es * 1.25,
+           k_maxpool2(skip, catc, f.ws + f.plan.hin[i + 1], cout, batch, R, R, cout, f.dt, f.st));
   }
   if (f.join_event) {  // no encoder block consumed the projection (cannot happen with L >= 1, but a fork must always join)
     LDM_CUDA(cudaStreamWaitEvent(f.st, f.join_event, 0));
@@ -875,7 +916,7 @@ static int forward_impl(ldm_unet* h, const float* x, int x_batch, const int64_t*
   // ---- bottleneck (no time embedding)  src/UNet.py:287-290
   {
     const int R = S >> L, C = h->dims[L];
-    RC(f.resblock(h->bott1, f.ws + f.plan.hin[L], C, f.s(2), C, R, false));
+    RC(f.resblock(h->bott1, f.ws + f.plan.hin[L], C, f.s(2), C, R, false, 0, pooled_normed));
     RC(f.attn_block(h->bott_attn, f.s(2), C, f.s(3), C, R));
     RC(f.resblock(h->bott2, f.s(3), C, f.s(2), C, R, false));
     RC(f.tap("bottleneck", f.s(2), C, C, R));

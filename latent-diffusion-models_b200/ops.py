@@ -161,6 +161,49 @@ def linear_attention(qkv: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def linear_attention_prenorm(x: torch.Tensor, w_qkv: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+                             impl: int = 0) -> torch.Tensor:
+    """PreNorm GroupNorm(1, C) + to_qkv + LinearAttention core on the raw bf16 NHWC input x [B,H,W,64] -> [B,H,W,128]
+    (src/UNet.py:106-110,145,149-163).  impl 0: tcgen05 kernel, 1: mma.sync kernel."""
+    _cuda(x, w_qkv, gamma, beta)
+    B, H, W, cin = x.shape
+    assert x.dtype == torch.bfloat16 and w_qkv.shape[0] == 384
+    lib = _lib.load()
+    w = w_qkv.reshape(384, cin).to(torch.float32).contiguous()
+    out = torch.empty(B, H, W, 128, dtype=x.dtype, device=x.device)
+    nbytes = lib.ldm_linear_attention_prenorm_scratch_bytes(B)
+    scratch = torch.empty(nbytes + 256, dtype=torch.uint8, device=x.device)
+    off = (-scratch.data_ptr()) % 256
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ldm_linear_attention_prenorm(x.data_ptr(), x.stride(2), cin, w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                                    eps, out.data_ptr(), B, H * W, impl, scratch.data_ptr() + off, nbytes,
+                                                    _lib.stream_ptr()))
+    return out
+
+
+def linear_attention_prenorm_to_out(x: torch.Tensor, w_qkv: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                                    w_out: torch.Tensor, b_out: torch.Tensor, eps: float = 1e-5):
+    """PreNorm + to_qkv + LinearAttention + to_out.0 (1x1 conv incl. bias) in the tcgen05 kernel -> (y [B,H,W,64] bf16,
+    stats fp32 [B, H*W/16, 2] partial sums {S, Q} of y for the GroupNorm(1, C) that follows)  (src/UNet.py:106-110,145-163)."""
+    _cuda(x, w_qkv, gamma, beta, w_out, b_out)
+    B, H, W, cin = x.shape
+    lib = _lib.load()
+    w = w_qkv.reshape(384, cin).to(torch.float32).contiguous()
+    wo = w_out.reshape(64, 128).to(torch.float32).contiguous()
+    bo = b_out.to(torch.float32).contiguous()
+    y = torch.empty(B, H, W, 64, dtype=x.dtype, device=x.device)
+    stats = torch.zeros(B, H * W // 16, 2, dtype=torch.float32, device=x.device)
+    nbytes = lib.ldm_linear_attention_prenorm_scratch_bytes(B)
+    scratch = torch.empty(nbytes + 256, dtype=torch.uint8, device=x.device)
+    off = (-scratch.data_ptr()) % 256
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ldm_linear_attention_prenorm_to_out(x.data_ptr(), x.stride(2), cin, w.data_ptr(), gamma.data_ptr(),
+                                                           beta.data_ptr(), eps, wo.data_ptr(), bo.data_ptr(), y.data_ptr(),
+                                                           y.stride(2), stats.data_ptr(), B, H * W, scratch.data_ptr() + off, nbytes,
+                                                           _lib.stream_ptr()))
+    return y, stats
+
+
 def attention(qkv: torch.Tensor) -> torch.Tensor:
     """qkv [B,H,W,384] -> [B,H,W,128] (src/UNet.py:122-135)."""
     _cuda(qkv)

@@ -327,6 +327,60 @@ def test_attention_cores(dtype, name):
     assert rel_l2(out, ref) < TOL[dtype]
 
 
+def _linattn_prenorm_reference(x, w, gamma, beta):
+    """src/UNet.py:106-110 (PreNorm GroupNorm(1, C)), :145 (to_qkv), :149-163 (LinearAttention up to `out`), fp32."""
+    B, C, H, W = x.shape
+    xn = F.group_norm(x, 1, gamma, beta, 1e-5)
+    qkv = F.conv2d(xn, w).reshape(B, 3, 4, 32, H * W)          # "b (h c) x y -> b h c (x y)", chunks q | k | v
+    q, k, v = qkv[:, 0], qkv[:, 1], qkv[:, 2]
+    q = q.softmax(dim=-2) * 32 ** -0.5
+    k = k.softmax(dim=-1)
+    ctx = torch.einsum("bhdn,bhen->bhde", k, v)
+    out = torch.einsum("bhde,bhdn->bhen", ctx, q)
+    return out.reshape(B, 128, H, W)
+
+
+@pytest.mark.parametrize("B,R", [(3, 32), (160, 32), (5, 16)])
+def test_linear_attention_prenorm_to_out_fused(B, R):
+    """... and with to_out.0 folded in (y = conv1x1(attention) + bias, applied to the per-sample context matrix) plus the partial
+    sums the following GroupNorm(1, C) needs."""
+    from ldm_b200 import ops
+    g = torch.Generator().manual_seed(B * 7 + R)
+    x = (torch.randn(B, 64, R, R, generator=g) * 1.7 + 0.4).to(dev())
+    w = (torch.randn(384, 64, 1, 1, generator=g) * 0.25).to(dev())
+    gamma = (1 + 0.3 * torch.randn(64, generator=g)).to(dev())
+    beta = (0.3 * torch.randn(64, generator=g)).to(dev())
+    wo = (torch.randn(64, 128, 1, 1, generator=g) / 128 ** 0.5).to(dev())
+    bo = torch.randn(64, generator=g).to(dev())
+    ref = F.conv2d(_linattn_prenorm_reference(nhwc_ref(x, "bf16"), w, gamma, beta), wo, bo)
+    y, stats = ops.linear_attention_prenorm_to_out(ops.to_nhwc(x, "bf16"), w, gamma, beta, wo, bo)
+    got = ops.to_nchw(y)
+    assert rel_l2(got, ref) < 1.2e-2
+    s = stats.double().sum(dim=1)                               # [B, 2]
+    n = 64 * R * R
+    mean, var = s[:, 0] / n, s[:, 1] / n - (s[:, 0] / n) ** 2
+    assert float((mean - got.double().mean(dim=(1, 2, 3))).abs().max()) < 2e-3 * float(got.double().std())
+    assert float((var / got.double().var(dim=(1, 2, 3), unbiased=False) - 1).abs().max()) < 5e-3
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("B,R", [(3, 32), (160, 32), (5, 16)])
+def test_linear_attention_prenorm_fused(impl, B, R):
+    """PreNorm + to_qkv + LinearAttention in one kernel on the raw block input: tcgen05 / TMEM (impl 0) and mma.sync (impl 1)."""
+    from ldm_b200 import ops
+    g = torch.Generator().manual_seed(B + R)
+    x = (torch.randn(B, 64, R, R, generator=g) * 1.7 + 0.4).to(dev())
+    w = (torch.randn(384, 64, 1, 1, generator=g) * 0.25).to(dev())
+    gamma = (1 + 0.3 * torch.randn(64, generator=g)).to(dev())
+    beta = (0.3 * torch.randn(64, generator=g)).to(dev())
+    ref = _linattn_prenorm_reference(nhwc_ref(x, "bf16"), w, gamma, beta)
+    out = ops.to_nchw(ops.linear_attention_prenorm(ops.to_nhwc(x, "bf16"), w, gamma, beta, impl=impl))
+    assert rel_l2(out, ref) < 1.2e-2, "bf16 operands (x, folded weights, P, V, ctx, softmax(q)) against the fp32 reference"
+    if impl == 0:   # the two kernels round at the same places
+        other = ops.to_nchw(ops.linear_attention_prenorm(ops.to_nhwc(x, "bf16"), w, gamma, beta, impl=1))
+        assert rel_l2(out, other) < 6e-3
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_max_pool(dtype):
     from ldm_b200 import ops
