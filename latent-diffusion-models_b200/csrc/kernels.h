@@ -97,6 +97,8 @@ struct LinAttnOut {
   void* y; int ldy;
   void* ystats; int64_t ystats_bytes;
   int* nslots_out;
+  // optional: to_out's GroupNorm(1, 64) and the Residual add too (src/UNet.py:147,:20): o [B, N, ldo] = x + GroupNorm(y)
+  const float* og = nullptr; const float* ob = nullptr; void* o = nullptr; int ldo = 0; float o_eps = 1e-5f;
 };
 int k_linear_attention_tc(const void* x, int ldx, const void* wqkv, const float* uv, const void* gn_part, int gn_splits, float eps,
                           void* out, int batch, int n_tokens, cudaStream_t st, const LinAttnOut* fuse = nullptr);

@@ -62,6 +62,9 @@ struct LtParams {
   // fused to_out 1x1 convolution (src/UNet.py:146): y = out Wout^T + bout, folded per sample into ctxW = ctxBD Wout^T, plus the
   // GroupNorm(1, C) partial sums {S, Q} of y for the apply kernel that follows (slot = 32-row block * 2 + column half)
   const float* bout; bf16* y; int ldy; float2* ystats;
+  // ... and, when `o` is set, to_out's GroupNorm(1, C) + the Residual add as well (src/UNet.py:147,:20): the CTA owns the whole
+  // sample, so after the last tile it normalises y and writes o = x + GroupNorm(y) itself (y is then only a scratch tensor)
+  const float* og; const float* ob; bf16* o; int ldo; float o_eps;
   int debug;                   // LDM_LA_DEBUG (timing experiments only): 1 skip the max pass, 2 skip the output phase
 };
 
@@ -455,7 +458,10 @@ linattn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             *reinterpret_cast<uint4*>(yrow + j) = o;
           }
           sS = warp_sum(sS); sQ = warp_sum(sQ);
-          if (lane == 0) p.ystats[(int64_t)b * (p.N / 16) + (t * 4 + quarter) * 2 + half] = make_float2(sS, sQ);
+          if (lane == 0) {
+            p.ystats[(int64_t)b * (p.N / 16) + (t * 4 + quarter) * 2 + half] = make_float2(sS, sQ);
+            if (p.o) reinterpret_cast<float2*>(s_max)[(t * 4 + quarter) * 2 + half] = make_float2(sS, sQ);
+          }
           arrive(st_bar, false);
           return;
         }
@@ -481,6 +487,40 @@ linattn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         softmax_step(0);
         for (int t = 1; t < tiles; ++t) { softmax_step(t); store_step(t - 1); }
         store_step(tiles - 1);
+        if (fuse_out && p.o) {
+          // o = x + GroupNorm(1, C)(y): statistics from the per-warp partial sums (added in slot order, in double: the same
+          // numbers the stand-alone apply kernel would use), then one pass over this sample's y (L2 / L1 resident) and x
+          la_bar();                                    // every warp's y rows and partial sums are in place
+          if (et < 64) {
+            double S = 0.0, Q = 0.0;
+            const float2* ps = reinterpret_cast<const float2*>(s_max);
+            for (int sl = 0; sl < p.N / 16; ++sl) { S += (double)ps[sl].x; Q += (double)ps[sl].y; }
+            const double cnt = (double)p.N * 64.0;
+            const double m1 = S / cnt;
+            double var = Q / cnt - m1 * m1;
+            if (var < 0.0) var = 0.0;
+            const float a = __ldg(p.og + et) * (1.0f / sqrtf((float)var + p.o_eps));
+            s_cq[et] = a;
+            s_cv[et] = fmaf(-(float)m1, a, __ldg(p.ob + et));
+          }
+          la_bar();
+          const int64_t row0 = (int64_t)b * p.N;
+          for (int idx = et; idx < p.N * 8; idx += 256) {
+            const int tok = idx >> 3, ch = (idx & 7) * 8;
+            const uint4 yv = *reinterpret_cast<const uint4*>(p.y + (row0 + tok) * p.ldy + ch);
+            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(p.x + (row0 + tok) * p.ldx + ch));
+            const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&yv);
+            const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xv);
+            uint32_t w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 yf = __bfloat1622float2(yh[u]), xf = __bfloat1622float2(xh[u]);
+              w[u] = pack2(fmaf(yf.x, s_cq[ch + 2 * u], s_cv[ch + 2 * u]) + xf.x, fmaf(yf.y, s_cq[ch + 2 * u + 1], s_cv[ch + 2 * u + 1]) + xf.y);
+            }
+            *reinterpret_cast<uint4*>(p.o + (row0 + tok) * p.ldo + ch) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          la_bar();                                    // s_cq / s_cv are rewritten at the start of the next sample
+        }
       }
     }
   }
@@ -545,11 +585,15 @@ int k_linear_attention_tc(const void* x, int ldx, const void* wqkv, const float*
   p.uv = uv; p.gn_part = (const float2*)gn_part; p.gn_splits = gn_splits; p.gn_eps = eps;
   p.x = (const bf16*)x; p.ldx = ldx; p.out = (bf16*)out;
   p.bout = nullptr; p.y = nullptr; p.ldy = 0; p.ystats = nullptr;
+  p.og = nullptr; p.ob = nullptr; p.o = nullptr; p.ldo = 0; p.o_eps = 1e-5f;
   if (fuse) {
     LDM_REQUIRE(fuse->wout && fuse->bout && fuse->y && fuse->ystats && fuse->ldy % 8 == 0 && ((uintptr_t)fuse->wout & 15) == 0 &&
                     ((uintptr_t)fuse->y & 15) == 0 && fuse->ystats_bytes >= (int64_t)batch * (n_tokens / 16) * 8,
                 "linear_attention_tc: fused to_out needs packed weights, bias, an output and a statistics buffer");
     p.bout = fuse->bout; p.y = (bf16*)fuse->y; p.ldy = fuse->ldy; p.ystats = (float2*)fuse->ystats;
+    LDM_REQUIRE(!fuse->o || (fuse->og && fuse->ob && fuse->ldo % 8 == 0 && ((uintptr_t)fuse->o & 15) == 0 && n_tokens / 16 <= 256),
+                "linear_attention_tc: fused GroupNorm + residual needs gamma / beta, an aligned output and <= 4096 tokens");
+    p.og = fuse->og; p.ob = fuse->ob; p.o = (bf16*)fuse->o; p.ldo = fuse->ldo; p.o_eps = fuse->o_eps;
     if (fuse->nslots_out) *fuse->nslots_out = n_tokens / 16;
   } else {
     LDM_REQUIRE(out, "linear_attention_tc: no output");

@@ -713,11 +713,18 @@ struct Fwd {
         LinAttnOut fo;
         fo.wout = a.wout; fo.bout = a.bout; fo.y = s(1); fo.ldy = a.dim; fo.ystats = ws + plan.gnst2; fo.ystats_bytes = plan.gnst2_bytes;
         fo.nslots_out = &ns;
+        // to_out's GroupNorm(1, C) + the Residual add can ride along too (the CTA owns the whole sample), but the serial
+        // tail of that pass costs more than the stand-alone apply kernel it replaces (measured: 98.3 vs 101.0 img/s): opt-in
+        static const bool fold_gn = getenv("LDM_LINATTN_GN") != nullptr && atoi(getenv("LDM_LINATTN_GN")) != 0;
+        if (fold_gn && R * R / 16 <= 256) {
+          fo.og = a.og; fo.ob = a.ob; fo.o = out; fo.ldo = ldo; fo.o_eps = GN_EPS;
+        }
         PROF(LDM_FAM_LINEAR_ATTENTION, (double)B * (2.0 * N * 3 * HIDDEN * a.dim + 4 * 2 * 2.0 * N * 32 * 32 + 2.0 * N * HIDDEN * a.dim),
              (double)B * N * (a.dim + a.dim) * es,
              k_linear_attention_tc(d, ldd, a.wfold, a.uv, gpart, splits, GN_EPS, nullptr, B, R * R, st, &fo));
-        PROF(LDM_FAM_GROUP_NORM, 0, (double)B * N * a.dim * es * 3,
-             k_group_norm_apply_raw(s(1), a.dim, out, ldo, d, ldd, a.og, a.ob, nullptr, 0, B, R * R, a.dim, 1, GN_EPS, 0, ws + plan.gnst2, ns, 0, st));
+        if (!fo.o)
+          PROF(LDM_FAM_GROUP_NORM, 0, (double)B * N * a.dim * es * 3,
+               k_group_norm_apply_raw(s(1), a.dim, out, ldo, d, ldd, a.og, a.ob, nullptr, 0, B, R * R, a.dim, 1, GN_EPS, 0, ws + plan.gnst2, ns, 0, st));
         return 0;
       }
       if (k_linear_attention_tc_applicable(a.dim, R * R, dt))   // tcgen05 / TMEM kernel (linattn_tc.cu)
