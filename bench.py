@@ -370,6 +370,14 @@ def run_ours(args):
             # generate_images.py (:18-41): one image per call, batch 1 -- latency, not throughput
             one = timed(lambda: diffusion.sample(model, classes_dev, (1, 3, 32, 32), dev, cfg_scale=cfg, seed=7, return_device=True))
             variants["generate_images_batch1_seconds_per_image"] = B * world / one
+            # the same with every GroupNorm riding in its producing convolution (opt-in at small batch: ~20 launches fewer per
+            # timestep, but a sample's bits then depend on the batch it is generated in)
+            os.environ["LDM_GN_NORM_SMALL_BATCH"] = "1"
+            d_small = ldm_b200.Diffusion(T, dev)
+            one_f = timed(lambda: d_small.sample(model, classes_dev, (1, 3, 32, 32), dev, cfg_scale=cfg, seed=7, return_device=True))
+            variants["generate_images_batch1_seconds_per_image_fused_groupnorm"] = B * world / one_f
+            del os.environ["LDM_GN_NORM_SMALL_BATCH"]
+            del d_small
             # BASELINE config 4: Autoencoder(3,4,3,64,[1,2],2) encode -> 1000-step CFG sampling of the [B,4,16,16] latent
             # with the LatentDiffusionModel's sqrt-linear schedule -> decode (scale 0.18215, 0.00085/0.012)
             torch.manual_seed(43)

@@ -1199,22 +1199,23 @@ int k_linear_attention_qkv_prenorm(const void* x, int ldx, int cin, const void* 
 // wfold[o][c] = bf16(w[o][c] gamma[c]);  uv[o] = sum_c float(wfold[o][c]);  uv[384 + o] = sum_c w[o][c] beta[c]
 __global__ void fold_prenorm_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
                                     int cin, bf16* __restrict__ wfold, float* __restrict__ uv) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;   // one warp per output row
   if (o >= 384) return;
   float u = 0.f, v = 0.f;
-  for (int c = 0; c < cin; ++c) {
+  for (int c = lane; c < cin; c += 32) {
     const float wv = w[(int64_t)o * cin + c];
     const bf16 f = __float2bfloat16_rn(wv * gamma[c]);
     wfold[(int64_t)o * cin + c] = f;
     u += __bfloat162float(f);
     v = fmaf(wv, beta[c], v);
   }
-  uv[o] = u;
-  uv[384 + o] = v;
+  u = warp_sum(u);
+  v = warp_sum(v);
+  if (lane == 0) { uv[o] = u; uv[384 + o] = v; }
 }
 int k_fold_prenorm_qkv(const float* wqkv, const float* gamma, const float* beta, int cin, void* wfold, float* uv,
                        cudaStream_t st) {
-  fold_prenorm_kernel<<<3, 128, 0, st>>>(wqkv, gamma, beta, cin, (bf16*)wfold, uv);
+  fold_prenorm_kernel<<<96, 128, 0, st>>>(wqkv, gamma, beta, cin, (bf16*)wfold, uv);
   LDM_LAUNCHED("fold_prenorm_qkv");
   return 0;
 }

@@ -99,7 +99,12 @@ struct LinAttnOut {
   int* nslots_out;
   // optional: to_out's GroupNorm(1, 64) and the Residual add too (src/UNet.py:147,:20): o [B, N, ldo] = x + GroupNorm(y)
   const float* og = nullptr; const float* ob = nullptr; void* o = nullptr; int ldo = 0; float o_eps = 1e-5f;
+  // optional (all three, and no `o`): the optimistic kernel linattn_tc2_kernel runs first -- ucat / c12 from k_fold_to_out,
+  // flags [batch] ints of scratch (samples it could not finish in range are redone by the exact kernel in the same call)
+  const void* ucat = nullptr; const float* c12 = nullptr; int* flags = nullptr;
 };
+int k_fold_to_out(const float* wqkv /*[384][64] fp32*/, const float* gamma, const float* uv /*k_fold_prenorm_qkv's*/,
+                  const float* wout /*[64][128] fp32*/, void* ucat /*bf16 [256][64]*/, float* c12 /*[64]*/, cudaStream_t st);
 int k_linear_attention_tc(const void* x, int ldx, const void* wqkv, const float* uv, const void* gn_part, int gn_splits, float eps,
                           void* out, int batch, int n_tokens, cudaStream_t st, const LinAttnOut* fuse = nullptr);
 int k_fold_prenorm_qkv(const float* wqkv /*[384][cin] fp32*/, const float* gamma, const float* beta, int cin, void* wfold,

@@ -66,6 +66,7 @@ struct LtParams {
   // sample, so after the last tile it normalises y and writes o = x + GroupNorm(y) itself (y is then only a scratch tensor)
   const float* og; const float* ob; bf16* o; int ldo; float o_eps;
   int debug;                   // LDM_LA_DEBUG (timing experiments only): 1 skip the max pass, 2 skip the output phase
+  const int* flag;             // != null: exact-fallback mode behind linattn_tc2_kernel -- only samples with flag[b] != 0 are computed
 };
 
 // MN-major SWIZZLE_128B operand: [k rows][64 elements] per 64-wide block of M / N, blocks `lbo` bytes apart
@@ -114,6 +115,13 @@ linattn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sgen + OFF_BAR + 112);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.flag) {
+    // fallback launch: almost always nothing is flagged -- leave before any set-up
+    pdl_wait();
+    int any = 0;
+    for (int b = blockIdx.x + (int)threadIdx.x * (int)gridDim.x; b < p.B; b += (int)(gridDim.x * blockDim.x)) any |= p.flag[b];
+    if (!__syncthreads_or(any)) return;
+  }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
     prefetch_tmap(&tmap_w);
@@ -155,6 +163,7 @@ linattn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       int stage = 0; uint32_t phase = 0;
       for (int b = blockIdx.x; b < p.B; b += gridDim.x)
         for (int pass = 0; pass < 3; ++pass) {
+          if (p.flag && !p.flag[b]) break;
           if ((pass == 0 && !do_max) || (pass == 2 && !do_out)) continue;
           for (int t = 0; t < tiles; ++t) {
             mbar_wait(xempty + 8 * stage, phase ^ 1);
@@ -207,6 +216,7 @@ linattn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
       };
       for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+        if (p.flag && !p.flag[b]) continue;
         // ---- A1: K_t into a two-deep accumulator ring (columns [0,128) / [128,256)); the epilogue takes the column max
         if (do_max) {
           for (int t = 0; t < tiles; ++t) {
@@ -295,6 +305,7 @@ linattn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       if (lane == 0) mbar_arrive(bar);
     };
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+      if (p.flag && !p.flag[b]) continue;
       // per-sample GroupNorm(1, C) scale / shift (see linattn_qkv_fused_kernel) and the fold constants
       float gr = 1.f, gmu = 0.f;
       if (p.uv) {
@@ -530,6 +541,479 @@ linattn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// =====================================================================================================================
+// linattn_tc2_kernel: the same block (PreNorm + to_qkv + LinearAttention + to_out.0) re-derived so that the epilogue warps --
+// the bottleneck of linattn_tc_kernel (profiles/README.md finding 14) -- touch 5/9 of the elements and never wait for a GEMM:
+//   * V is never projected.  ctx = softmax_t(K)^T V and V = X Wv'^T, so ctx = (P^T X) Wv'^T: the kernel accumulates
+//     G [128 (h,d) x 64 c] += P_t^T X_t  (the x tile that fed the K projection is also the MN-major B operand) and Z += P_t^T 1.
+//   * to_out and Wv are folded into ONE weight-only matrix per head, U_h [c][co] = sum_e Wout[co,(h,e)] Wv'[(h,e),c]
+//     (k_fold_to_out, at weight-load time): per sample M [128 (h,d) x 64 co] = (G / Z - mu) [Ucat], one N = 256 GEMM of which row
+//     (h,d) reads the 64 columns of head h.  The PreNorm mean is taken off G / Z in fp32, BEFORE the bf16 rounding (a weighted
+//     average of x carries the whole mean; rounding it first costs |mu| / sigma in precision).  The remaining constants of the
+//     fold (Wv beta through to_out, to_out's bias) collapse into one vector yc [64] because softmax_d(q) sums to one.
+//   * no max pass: softmax over tokens is shift invariant, the shift is the sample's FIRST token (P_0 = 1, so Z >= 1); the
+//     softmax over the 32 channels of a head is evaluated unshifted.  Either can only fail by overflow / total underflow when
+//     a logit leaves +-88 of its reference -- the sample's y then contains inf / NaN, which the GroupNorm partial sums of the
+//     store step see for free: the sample is flagged and linattn_tc_kernel (exact two-pass softmax) recomputes it right after
+//     (a launch that returns at once when nothing is flagged).
+//   * 16 epilogue warps (TMEM lane quarter x 32-column slice), K / Q accumulators double buffered in TMEM, P / softmax(Q)
+//     double buffered in shared memory, x tiles through a 4-deep TMA ring: projection t+2 is queued while step t is consumed.
+// Work per 128-token tile: K proj (N=128) -> P step -> G, Z;   Q proj (N=128) -> S step -> Y (N=64) -> store step.
+constexpr uint32_t L2_XS = 4;                    // x ring depth
+constexpr uint32_t L2_X = 0;                     // 4 x [128 tok][64 ch] K-major SW128 (TMA)
+constexpr uint32_t L2_WQ = 65536, L2_WK = 81920; // [128][64] each
+constexpr uint32_t L2_U = 98304;                 // Ucat [256 (h,co)][64 c] K-major SW128 (32 KB)
+constexpr uint32_t L2_PS = 131072;               // 2 x 32 KB: P (MN-major, 2 blocks [128 tok][64 ch]) / softmax(Q) (K-major, 2 atoms):
+                                                 // the same bytes either way; G / Z as a K-major A tile aliases the first 16 KB
+constexpr uint32_t L2_PS_STRIDE = 32768;
+constexpr uint32_t L2_MT = 196608;               // M [128 (h,d)][64 co] MN-major B operand (16 KB)
+constexpr uint32_t L2_ONES = 212992;             // 16 k rows x 128 B of bf16 1.0
+constexpr uint32_t L2_BAR = 215040;              // mbarriers + TMEM slot (256 B)
+constexpr uint32_t L2_F = 215296;                // floats: shift [128] | cq2 [2][128] | yc [2][64]
+constexpr uint32_t LA2_SMEM = L2_F + (128 + 256 + 128) * 4 + 1024;
+static_assert(LA2_SMEM <= 227 * 1024, "shared memory plan exceeds 227 KB");
+constexpr uint32_t T2_ACC = 0;                   // K / Q accumulators: [0,128) and [128,256)
+constexpr uint32_t T2_G = 256, T2_Z = 320;       // G [256,320), Z [320,336)
+constexpr uint32_t T2_M = 256;                   // M accumulators [256,512) (G and Z have been read by then)
+constexpr uint32_t T2_Y = 256;                   // Y accumulators [256,320) and [320,384) (M has been read by then)
+
+struct Lt2Params {
+  int B, N, tiles;
+  const float* uv;             // [2][384] fold constants (k_fold_prenorm_qkv)
+  const float2* gn_part; int gn_splits; float gn_eps;
+  const bf16* x; int ldx;
+  const float* bout;           // [64]
+  const float* c12;            // [64]: Wout (Wv beta) (k_fold_to_out)
+  bf16* y; int ldy; float2* ystats;
+  int* flag;                   // [B]: 1 = recompute this sample with the exact kernel
+  int force_flag;              // LDM_LA2_FORCE_FALLBACK (tests): flag every sample
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void la2_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+template <bool TRACE>
+__global__ void __launch_bounds__(576, 1)
+linattn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                   const __grid_constant__ CUtensorMap tmap_u, const Lt2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sb - smem_u32(smem_raw));
+  const uint32_t bar0 = sb + L2_BAR;
+  const uint32_t xfull = bar0, xempty = bar0 + 32, wbar = bar0 + 64, accfull = bar0 + 72, accempty = bar0 + 88, psfull = bar0 + 104,
+                 psempty = bar0 + 120, yfull = bar0 + 136, yempty = bar0 + 152, gfull = bar0 + 168, gnfull = bar0 + 176,
+                 mfull = bar0 + 184, mready = bar0 + 192, tmem_slot = bar0 + 200;
+  float* s_shift = reinterpret_cast<float*>(sgen + L2_F);   // [128] k of the sample's first token, times r log2e
+  float* s_cq2 = s_shift + 128;                              // [2][128] q constants times log2e (by sample parity)
+  float* s_yc = s_cq2 + 256;                                 // [2][64]  output constants (by sample parity)
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sgen + L2_BAR + 200);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // LDM_LA2_TRACE=1 (debug build of the same kernel): CTA 0's MMA thread and two epilogue warps log (tag, clock) pairs
+  constexpr int TR_N = TRACE ? 700 : 1;
+  uint32_t tr[TR_N];
+  int tr_n = 0;
+  const bool tr_on = TRACE && blockIdx.x == 0 && lane == 0 && (warp == 1 || warp == 2 || warp == 11);
+  auto ev = [&](int tag) {
+    if (TRACE) {
+      if (tr_on && tr_n < TR_N) tr[tr_n++] = ((uint32_t)tag << 24) | ((uint32_t)clock64() & 0xffffffu);
+    }
+  };
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_u);
+    for (uint32_t s = 0; s < L2_XS; ++s) { mbar_init(xfull + 8 * s, 1); mbar_init(xempty + 8 * s, 1); }
+    for (uint32_t s = 0; s < 2; ++s) {
+      mbar_init(accfull + 8 * s, 1); mbar_init(accempty + 8 * s, 8);
+      mbar_init(psfull + 8 * s, 8);  mbar_init(psempty + 8 * s, 1);
+      mbar_init(yfull + 8 * s, 1);   mbar_init(yempty + 8 * s, 8);
+    }
+    mbar_init(wbar, 1);
+    mbar_init(gfull, 1);
+    mbar_init(gnfull, 16);
+    mbar_init(mfull, 1);
+    mbar_init(mready, 16);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < 512; i += blockDim.x)
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sb + L2_ONES + 4 * i), "r"(0x3F803F80u) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  pdl_trigger();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int T = p.tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer: weights once, then every sample's x tiles twice (K pass, Q pass) =====================
+    if (lane == 0) {
+      mbar_expect_tx(wbar, 2 * 16384 + 32768);
+      tma_load_2d(sb + L2_WQ, &tmap_w, wbar, 0, 0);
+      tma_load_2d(sb + L2_WK, &tmap_w, wbar, 0, 128);
+      tma_load_2d(sb + L2_U, &tmap_u, wbar, 0, 0);
+      tma_load_2d(sb + L2_U + 16384, &tmap_u, wbar, 0, 128);
+      uint32_t xi = 0;
+      for (int b = blockIdx.x; b < p.B; b += gridDim.x)
+        for (int pass = 0; pass < 2; ++pass)
+          for (int t = 0; t < T; ++t, ++xi) {
+            const uint32_t stage = xi % L2_XS;
+            mbar_wait(xempty + 8 * stage, ((xi / L2_XS) & 1) ^ 1);
+            mbar_expect_tx(xfull + 8 * stage, 16384);
+            tma_load_2d(sb + L2_X + stage * 16384, &tmap_x, xfull + 8 * stage, 0, b * p.N + t * 128);
+          }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t id128 = make_idesc(128), id256 = make_idesc(256);
+      constexpr uint32_t id_gz = make_idesc(80) | (1u << 15) | (1u << 16);      // P^T [X | 1]: both operands MN-major
+      constexpr uint32_t id_y = make_idesc(64) | (1u << 16);                    // softmax(Q) K-major, M MN-major
+      const uint64_t wq = make_sw128_desc(sb + L2_WQ), wk = make_sw128_desc(sb + L2_WK), ud = make_sw128_desc(sb + L2_U);
+      const uint64_t gnd = make_sw128_desc(sb + L2_PS);
+      const uint64_t mtd = make_mn_desc(sb + L2_MT, 16384);
+      mbar_wait(wbar, 0);
+      tc_fence_after();
+      uint32_t xi = 0;                                 // x tiles consumed so far (ring position)
+      uint32_t acc_m = 0, ps_m = 0, y_m = 0;           // bit `buf` = parity of that buffer's next use
+      // projection of ring tile `gi` into accumulator `buf`; `release` frees the x stage with the same commit (Q pass)
+      auto proj = [&](uint32_t gi, int buf, uint64_t w, bool release) {
+        const uint32_t stage = gi % L2_XS;
+        mbar_wait(xfull + 8 * stage, (gi / L2_XS) & 1);
+        ev(1);
+        mbar_wait(accempty + 8 * buf, ((acc_m >> buf) & 1) ^ 1);
+        ev(2);
+        tc_fence_after();
+        const uint64_t xd = make_sw128_desc(sb + L2_X + stage * 16384);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T2_ACC + 128 * buf, xd + 2 * k, w + 2 * k, id128, k ? 1u : 0u);
+        umma_commit(accfull + 8 * buf);
+        if (release) umma_commit(xempty + 8 * stage);
+        acc_m ^= 1u << buf;
+      };
+      uint32_t it = 0;
+      for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
+        const uint32_t sp = it & 1;
+        // ---- K pass: K_t -> (P step) -> [G | Z] += P_t^T [X_t | 1].  Projection t+2 only needs the accumulator to have been
+        // READ by P step t, so it is queued before the wait for P_t itself.
+        const uint32_t xa = xi;
+        proj(xa, 0, wk, false);
+        if (T > 1) proj(xa + 1, 1, wk, false);
+        for (int t = 0; t < T; ++t) {
+          const int buf = t & 1;
+          if (t + 2 < T) proj(xa + t + 2, buf, wk, false);
+          mbar_wait(psfull + 8 * buf, (ps_m >> buf) & 1);
+          ev(3);
+          tc_fence_after();
+          const uint32_t stage = (xa + t) % L2_XS;
+          const uint64_t pmn = make_mn_desc(sb + L2_PS + buf * L2_PS_STRIDE, 16384);
+          // B = [x tile (64 channels) | ones (16 columns)]: N = 80, the second 64-wide block is the 2 KB of ones whatever the
+          // k step, so its distance (LBO) shrinks as the start address advances
+          const uint64_t xmn = make_mn_desc(sb + L2_X + stage * 16384, (L2_ONES - L2_X) - stage * 16384);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem_base + T2_G, pmn + 128 * k, xmn + 128 * k - ((uint64_t)(128 * k) << 16), id_gz, (t == 0 && k == 0) ? 0u : 1u);
+          umma_commit(psempty + 8 * buf);
+          umma_commit(xempty + 8 * stage);
+          ps_m ^= 1u << buf;
+          ev(4);
+        }
+        umma_commit(gfull);
+        xi = xa + T;
+        // ---- the first two Q projections fill the tensor pipe while the epilogue turns G into the A operand of M
+        const uint32_t xb = xi;
+        proj(xb, 0, wq, true);
+        if (T > 1) proj(xb + 1, 1, wq, true);
+        mbar_wait(gnfull, sp);
+        ev(5);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T2_M, gnd + 2 * k, ud + 2 * k, id256, k ? 1u : 0u);
+        umma_commit(mfull);
+        mbar_wait(mready, sp);
+        ev(6);
+        tc_fence_after();
+        // ---- Q pass: Q_t -> (S step) -> Y_t = softmax(Q_t) M -> (store step)
+        for (int t = 0; t < T; ++t) {
+          const int buf = t & 1;
+          if (t + 2 < T) proj(xb + t + 2, buf, wq, true);
+          mbar_wait(psfull + 8 * buf, (ps_m >> buf) & 1);
+          ev(7);
+          mbar_wait(yempty + 8 * buf, ((y_m >> buf) & 1) ^ 1);
+          ev(8);
+          tc_fence_after();
+          const uint64_t sk = make_sw128_desc(sb + L2_PS + buf * L2_PS_STRIDE);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem_base + T2_Y + 64 * buf, sk + (uint64_t)((k >> 2) * 1024 + 2 * (k & 3)), mtd + 128 * k, id_y, k ? 1u : 0u);
+          umma_commit(yfull + 8 * buf);
+          umma_commit(psempty + 8 * buf);
+          ps_m ^= 1u << buf;
+          y_m ^= 1u << buf;
+          ev(9);
+        }
+        xi = xb + T;
+      }
+    }
+  } else {
+    // ===================== epilogue: 16 warps = 2 groups x (TMEM lane quarter) x (64-column half) =====================
+    // Group g owns the tiles t = g (mod 2): its own accumulator, its own P / softmax(Q) buffer, its own Y accumulator.  While one
+    // group waits (for a GEMM, a barrier, a TMEM load) the other one keeps the MUFU pipe busy.
+    const int quarter = warp & 3, cq = (warp - 2) >> 2;
+    const int grp = cq >> 1, half = cq & 1;
+    const int row = quarter * 32 + lane;          // token row of the tile / (h, d) row of G and M
+    const int et = threadIdx.x - 64;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t acc_addr = lane_addr + T2_ACC + 128 * grp + 64 * half;
+    const uint32_t ps_tile = sb + L2_PS + grp * L2_PS_STRIDE + half * 16384;   // P block / softmax(Q) atom of this column half
+    const uint32_t b_accfull = accfull + 8 * grp, b_accempty = accempty + 8 * grp, b_psfull = psfull + 8 * grp,
+                   b_psempty = psempty + 8 * grp, b_yfull = yfull + 8 * grp, b_yempty = yempty + 8 * grp;
+    uint32_t acc_n = 0, ps_n = 0, y_n = 0;        // uses so far of this group's buffers
+    auto wait_bar = [&](uint32_t bar, uint32_t parity) {
+      mbar_wait(bar, parity);                     // every lane probes: no divergence, no warp-level hand-off
+      tc_fence_after();
+    };
+    auto arrive = [&](uint32_t bar, bool wrote_smem) {
+      if (wrote_smem) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> the MMA's async proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    // GroupNorm(1, C) statistics of sample b (left by the producing convolution's epilogue or by k_group_norm_stats): the
+    // slots are spread over the lanes and combined by a butterfly, in double -- one fixed order whatever the batch
+    auto sample_stats = [&](int b, float& gr, float& gmu) {
+      const double cnt = (double)p.N * 64.0;
+      if (p.gn_splits < 0) {
+        double a = 0.0, q2 = 0.0;
+        for (int sp = lane; sp < -p.gn_splits; sp += 32) { const float2 v = __ldg(p.gn_part + (int64_t)b * (-p.gn_splits) + sp); a += (double)v.x; q2 += (double)v.y; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); q2 += __shfl_xor_sync(0xffffffffu, q2, o); }
+        const double m1 = a / cnt;
+        double var = q2 / cnt - m1 * m1;
+        if (var < 0.0) var = 0.0;
+        gmu = (float)m1;
+        gr = (float)(1.0 / sqrt(var + (double)p.gn_eps));
+      } else {
+        float a = 0.f, q2 = 0.f;
+        for (int sp = 0; sp < p.gn_splits; ++sp) { const float2 v = __ldg(p.gn_part + (int64_t)b * p.gn_splits + sp); a += v.x; q2 += v.y; }
+        const float K = __bfloat162float(p.x[(int64_t)b * p.N * p.ldx]);
+        const float inv_n = 1.0f / (float)cnt;
+        const float m1 = a * inv_n;
+        const float var = fmaxf(q2 * inv_n - m1 * m1, 0.f);
+        gmu = K + m1;
+        gr = 1.0f / sqrtf(var + p.gn_eps);
+      }
+    };
+    float gr_n = 1.f, gmu_n = 0.f;
+    if ((int)blockIdx.x < p.B) sample_stats(blockIdx.x, gr_n, gmu_n);
+    uint32_t it = 0;
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
+      ev(10);
+      const uint32_t sp = it & 1;
+      const float gr = gr_n, gmu = gmu_n;
+      const float kscale = gr * kLog2e;
+      float* cq2 = s_cq2 + sp * 128;
+      float* yc = s_yc + sp * 64;
+      if (et < 128) cq2[et] = (p.uv[384 + et] - gr * gmu * p.uv[et]) * kLog2e;
+      else if (et < 192) yc[et - 128] = __ldg(p.bout + et - 128) + kQScale * p.c12[et - 128];
+      if (et == 192) p.flag[b] = p.force_flag;
+      // the shift of the softmax over tokens = k of the sample's first token: group 0 reads it from tile 0's accumulator
+      if (grp == 0) {
+        wait_bar(b_accfull, acc_n & 1);           // (consumed again, with the same parity, by P step 0)
+        if (quarter == 0) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t kr[32];
+            tmem_ld32(acc_addr + 32 * c, kr);
+            tmem_ld_wait();
+            if (lane == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s_shift[64 * half + 32 * c + j] = __uint_as_float(kr[j]) * kscale;
+            }
+          }
+        }
+      }
+      la2_bar();                                  // publishes the shift, cq2 / yc and the flag reset of this sample
+      // ---------------- P step (tiles of this group): P = exp2((k - k[token 0]) r log2e) as bf16 MN-major tiles
+      for (int t = grp; t < T; t += 2) {
+        wait_bar(b_accfull, acc_n & 1); ++acc_n;
+        ev(11);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t kr[32];
+          tmem_ld32(acc_addr + 32 * c, kr);
+          tmem_ld_wait();
+          if (c == 1) arrive(b_accempty, false);
+          const float4* sh4 = reinterpret_cast<const float4*>(s_shift + 64 * half + 32 * c);
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const float4 s0 = sh4[j >> 2], s1 = sh4[(j >> 2) + 1];
+            const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              kr[j + u] = pack2(ex2(fmaf(__uint_as_float(kr[j + 2 * u]), kscale, -sh[2 * u])),
+                                ex2(fmaf(__uint_as_float(kr[j + 2 * u + 1]), kscale, -sh[2 * u + 1])));
+          }
+          if (c == 0) { ev(12); wait_bar(b_psempty, (ps_n & 1) ^ 1); ev(13); }   // the GEMM that read this buffer two tiles ago
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) st_sw128(ps_tile, row, 4 * c + (j >> 3), kr[j], kr[j + 1], kr[j + 2], kr[j + 3]);
+        }
+        ev(14);
+        arrive(b_psfull, true); ++ps_n;
+        ev(15);
+      }
+      // ---------------- G / Z - mu -> bf16 K-major A operand of the M GEMM (row (h,d): this warp's 16 of the 64 x channels)
+      wait_bar(gfull, sp);
+      ev(16);
+      {
+        uint32_t g[16];
+        tmem_ld16(lane_addr + T2_G + 16 * cq, g);
+        const uint32_t zr = tmem_ld1(lane_addr + T2_Z);
+        tmem_ld_wait();
+        const float zinv = 1.0f / __uint_as_float(zr);
+        float gn[16];
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { gn[j] = fmaf(__uint_as_float(g[j]), zinv, -gmu); bad |= !(fabsf(gn[j]) < 3.0e38f); }
+        st_sw128(sb + L2_PS, row, 2 * cq, pack2(gn[0], gn[1]), pack2(gn[2], gn[3]), pack2(gn[4], gn[5]), pack2(gn[6], gn[7]));
+        st_sw128(sb + L2_PS, row, 2 * cq + 1, pack2(gn[8], gn[9]), pack2(gn[10], gn[11]), pack2(gn[12], gn[13]), pack2(gn[14], gn[15]));
+        if (bad) p.flag[b] = 1;
+      }
+      arrive(gnfull, true);
+      ev(17);
+      // the next sample's statistics while the M GEMM runs
+      if (b + (int)gridDim.x < p.B) sample_stats(b + gridDim.x, gr_n, gmu_n);
+      ev(18);
+      // ---------------- M = r 32^-1/2 (G/Z) Ucat, head block of the row -> bf16 MN-major B operand of the output GEMM
+      wait_bar(mfull, sp);
+      ev(19);
+      {
+        uint32_t m[16];
+        tmem_ld16(lane_addr + T2_M + 64 * quarter + 16 * cq, m);
+        tmem_ld_wait();
+        const float f = gr * kQScale;
+        st_sw128(sb + L2_MT, row, 2 * cq, pack2(__uint_as_float(m[0]) * f, __uint_as_float(m[1]) * f), pack2(__uint_as_float(m[2]) * f, __uint_as_float(m[3]) * f),
+                 pack2(__uint_as_float(m[4]) * f, __uint_as_float(m[5]) * f), pack2(__uint_as_float(m[6]) * f, __uint_as_float(m[7]) * f));
+        st_sw128(sb + L2_MT, row, 2 * cq + 1, pack2(__uint_as_float(m[8]) * f, __uint_as_float(m[9]) * f), pack2(__uint_as_float(m[10]) * f, __uint_as_float(m[11]) * f),
+                 pack2(__uint_as_float(m[12]) * f, __uint_as_float(m[13]) * f), pack2(__uint_as_float(m[14]) * f, __uint_as_float(m[15]) * f));
+      }
+      arrive(mready, true);
+      ev(20);
+      // ---------------- S step: softmax over the 32 channels of heads 2 half, 2 half + 1 (one thread = one token row), unshifted
+      const float grl2 = gr * kLog2e;
+      auto softmax_step = [&](int t) {
+        wait_bar(b_accfull, acc_n & 1); ++acc_n;
+        ev(21);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t qr[32];
+          tmem_ld32(acc_addr + 32 * c, qr);
+          tmem_ld_wait();
+          if (c == 1) arrive(b_accempty, false);
+          const float4* c4 = reinterpret_cast<const float4*>(cq2 + 64 * half + 32 * c);
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 cc = c4[j >> 2];
+            float e0 = ex2(fmaf(__uint_as_float(qr[j]), grl2, cc.x)), e1 = ex2(fmaf(__uint_as_float(qr[j + 1]), grl2, cc.y));
+            float e2 = ex2(fmaf(__uint_as_float(qr[j + 2]), grl2, cc.z)), e3 = ex2(fmaf(__uint_as_float(qr[j + 3]), grl2, cc.w));
+            s += (e0 + e1) + (e2 + e3);
+            qr[j] = __float_as_uint(e0); qr[j + 1] = __float_as_uint(e1); qr[j + 2] = __float_as_uint(e2); qr[j + 3] = __float_as_uint(e3);
+          }
+          const float inv = 1.0f / s;
+          if (c == 0) { ev(23); wait_bar(b_psempty, (ps_n & 1) ^ 1); ev(24); }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            st_sw128(ps_tile, row, 4 * c + (j >> 3), pack2(__uint_as_float(qr[j]) * inv, __uint_as_float(qr[j + 1]) * inv),
+                     pack2(__uint_as_float(qr[j + 2]) * inv, __uint_as_float(qr[j + 3]) * inv),
+                     pack2(__uint_as_float(qr[j + 4]) * inv, __uint_as_float(qr[j + 5]) * inv),
+                     pack2(__uint_as_float(qr[j + 6]) * inv, __uint_as_float(qr[j + 7]) * inv));
+        }
+        arrive(b_psfull, true); ++ps_n;
+        ev(25);
+      };
+      // ---------------- store step: y tile t = Y + yc (32 of the 64 channels per thread) + GroupNorm(1, C) partial sums
+      auto store_step = [&](int t) {
+        ev(26);
+        wait_bar(b_yfull, y_n & 1); ++y_n;
+        ev(27);
+        uint32_t r[32];
+        tmem_ld32(lane_addr + T2_Y + 64 * grp + 32 * half, r);
+        tmem_ld_wait();
+        arrive(b_yempty, false);
+        bf16* yrow = p.y + ((int64_t)b * p.N + t * 128 + row) * p.ldy + 32 * half;
+        const float4* c4 = reinterpret_cast<const float4*>(yc + 32 * half);
+        float sS = 0.f, sQ = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const float4 c0 = c4[j >> 2], c1 = c4[(j >> 2) + 1];
+          const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { v[u] = __uint_as_float(r[j + u]) + cc[u]; sS += v[u]; sQ = fmaf(v[u], v[u], sQ); }
+          uint4 o;
+          o.x = pack2(v[0], v[1]); o.y = pack2(v[2], v[3]); o.z = pack2(v[4], v[5]); o.w = pack2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(yrow + j) = o;
+        }
+        sS = warp_sum(sS); sQ = warp_sum(sQ);
+        if (lane == 0) {
+          p.ystats[(int64_t)b * (p.N / 16) + (t * 4 + quarter) * 2 + half] = make_float2(sS, sQ);
+          if (!(sQ < 3.0e38f)) p.flag[b] = 1;      // inf / NaN anywhere in these rows: the exact kernel redoes the sample
+        }
+        ev(28);
+      };
+      // S_t, S_t+2, St_t, S_t+4, St_t+2, ...: the softmax of the group's next tile overlaps the output GEMM of this one
+      if (grp < T) {
+        softmax_step(grp);
+        for (int t = grp + 2; t < T; t += 2) { softmax_step(t); store_step(t - 2); }
+        store_step(grp + ((T - 1 - grp) & ~1));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (TRACE) {
+    if (tr_on)
+      for (int i = 0; i < tr_n; ++i) printf("LA2TRACE w%d %u %u\n", warp, tr[i] >> 24, tr[i] & 0xffffffu);
+  }
+}
+
+// Ucat [(h, co)][c] = bf16(sum_e Wout[co][(h,e)] Wv[(h,e)][c] gamma[c]);  c1[co] = sum_he Wout[co][he] (Wv beta)[he]
+// (Wv beta = uv[384 + 256 + he], left by fold_prenorm_kernel).  One block per output channel co, thread = (h, c) pair.
+__global__ void fold_to_out_kernel(const float* __restrict__ wqkv, const float* __restrict__ gamma, const float* __restrict__ uv,
+                                   const float* __restrict__ wout, bf16* __restrict__ ucat, float* __restrict__ c1) {
+  const int co = blockIdx.x, h = threadIdx.x >> 6, c = threadIdx.x & 63;
+  const float* wv = wqkv + (int64_t)(256 + 32 * h) * 64 + c;   // [32 e] rows, 64 floats apart
+  const float* wo = wout + (int64_t)co * 128 + 32 * h;         // [32 e]
+  float a = 0.f;
+#pragma unroll 8
+  for (int e = 0; e < 32; ++e) a = fmaf(wo[e], wv[e * 64], a);
+  ucat[((int64_t)h * 64 + co) * 64 + c] = __float2bfloat16_rn(a * gamma[c]);
+  __shared__ float s_part[4];
+  float v = threadIdx.x < 128 ? wout[(int64_t)co * 128 + threadIdx.x] * uv[384 + 256 + threadIdx.x] : 0.f;
+  v = warp_sum(v);
+  if (threadIdx.x < 128 && (threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) c1[co] = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 g_encode_la = nullptr;
 int g_sms_la[64] = {};
 
@@ -545,6 +1029,8 @@ int la_init() {
   LDM_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
   LDM_REQUIRE(cc_major == 10, "linattn_tc: tcgen05 kernels need an sm_100-class GPU (found cc %d.x)", cc_major);
   LDM_CUDA(cudaFuncSetAttribute(linattn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_SMEM));
+  LDM_CUDA(cudaFuncSetAttribute(linattn_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA2_SMEM));
+  LDM_CUDA(cudaFuncSetAttribute(linattn_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA2_SMEM));
   int sms = 0;
   LDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   g_encode_la = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
@@ -599,6 +1085,7 @@ int k_linear_attention_tc(const void* x, int ldx, const void* wqkv, const float*
     LDM_REQUIRE(out, "linear_attention_tc: no output");
   }
   { const char* d = getenv("LDM_LA_DEBUG"); p.debug = d ? atoi(d) : 0; }
+  p.flag = nullptr;
   CUtensorMap mx, mw;
   if (int rc = make_rows_map(&mx, x, (int64_t)batch * n_tokens, ldx)) return rc;
   if (int rc = make_rows_map(&mw, wqkv, 384, 64)) return rc;
@@ -617,7 +1104,32 @@ int k_linear_attention_tc(const void* x, int ldx, const void* wqkv, const float*
   LDM_CUDA(cudaGetDevice(&dev));
   const int sms = g_sms_la[dev & 63];
   const int grid = batch < sms ? batch : sms;
+  static const bool v1_only = getenv("LDM_LINATTN_V1") != nullptr && atoi(getenv("LDM_LINATTN_V1")) != 0;
+  if (fuse && !fuse->o && fuse->ucat && fuse->c12 && fuse->flags && uv && !v1_only) {
+    // optimistic kernel (no V projection, no max pass, 16 epilogue warps), then the exact kernel over whatever it flagged
+    LDM_REQUIRE(((uintptr_t)fuse->ucat & 15) == 0, "linear_attention_tc: unaligned Ucat");
+    Lt2Params q;
+    q.B = batch; q.N = n_tokens; q.tiles = n_tokens / 128;
+    q.uv = uv; q.gn_part = (const float2*)gn_part; q.gn_splits = gn_splits; q.gn_eps = eps;
+    q.x = (const bf16*)x; q.ldx = ldx; q.bout = fuse->bout; q.c12 = fuse->c12;
+    q.y = (bf16*)fuse->y; q.ldy = fuse->ldy; q.ystats = (float2*)fuse->ystats; q.flag = fuse->flags;
+    { const char* d = getenv("LDM_LA2_FORCE_FALLBACK"); q.force_flag = d && atoi(d) ? 1 : 0; }
+    CUtensorMap mu;
+    if (int rc = make_rows_map(&mu, fuse->ucat, 256, 64)) return rc;
+    static const bool trace = getenv("LDM_LA2_TRACE") != nullptr;
+    if (trace) LDM_CUDA(ldm_launch_pdl(linattn_tc2_kernel<true>, dim3(grid), dim3(576), (size_t)LA2_SMEM, st, mx, mw, mu, q));
+    else LDM_CUDA(ldm_launch_pdl(linattn_tc2_kernel<false>, dim3(grid), dim3(576), (size_t)LA2_SMEM, st, mx, mw, mu, q));
+    LDM_LAUNCHED("linattn_tc2");
+    p.flag = fuse->flags;
+  }
   LDM_CUDA(ldm_launch_pdl(linattn_tc_kernel, dim3(grid), dim3(320), (size_t)LA_SMEM, st, mx, mw, mwo, p));
   LDM_LAUNCHED("linattn_tc");
+  return 0;
+}
+
+// Weight-only part of the to_out fold of linattn_tc2_kernel (after k_fold_prenorm_qkv, whose uv it reads): ucat bf16 [256][64], c12 fp32 [64]
+int k_fold_to_out(const float* wqkv, const float* gamma, const float* uv, const float* wout, void* ucat, float* c12, cudaStream_t st) {
+  fold_to_out_kernel<<<64, 256, 0, st>>>(wqkv, gamma, uv, wout, (bf16*)ucat, c12);
+  LDM_LAUNCHED("fold_to_out");
   return 0;
 }

@@ -27,21 +27,26 @@ __device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a protocol bug must surface as a trapped kernel (launch error), never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a trapped kernel (launch error), never as a hung GPU.  The first probe carries
+// no time-out bookkeeping: most waits are already satisfied, and the clock reads of a spinning lane cost issue slots that the
+// working warps of the same scheduler need.
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
+  if (mbar_try(bar, parity)) return;
   const long long start = clock64();
-  while (true) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, P1;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
+  while (!mbar_try(bar, parity)) {
     if (clock64() - start > 4000000000LL) __trap();  // ~2 s at 2 GHz
   }
 }

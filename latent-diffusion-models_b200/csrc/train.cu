@@ -212,7 +212,8 @@ int ldm_time_proj_backward(const float* temb, const float* w, const float* dtpro
 }
 
 int64_t ldm_linear_attention_prenorm_scratch_bytes(int batch) {
-  return 384 * 64 * 2 + 768 * 4 + 1024 + 64 * 128 * 2 + k_group_norm_ws_bytes(batch > 0 ? batch : 1, 1);
+  return 384 * 64 * 2 + 768 * 4 + 1024 + 64 * 128 * 2 + 256 * 64 * 2 + 1024 + ((int64_t)(batch > 0 ? batch : 1) * 4 + 255) / 256 * 256 +
+         k_group_norm_ws_bytes(batch > 0 ? batch : 1, 1);
 }
 int ldm_linear_attention_prenorm(const void* x, int ldx, int cin, const float* w_qkv, const float* gamma, const float* beta,
                                  float eps, void* out, int batch, int n_tokens, int impl, void* scratch, int64_t scratch_bytes,
@@ -248,14 +249,20 @@ int ldm_linear_attention_prenorm_to_out(const void* x, int ldx, int cin, const f
   void* wfold = s;
   float* uv = (float*)(s + 384 * 64 * 2);
   void* wout = s + 384 * 64 * 2 + 768 * 4 + 1024;                       // packed [64][128] bf16 (16 KB)
-  void* gnws = s + 384 * 64 * 2 + 768 * 4 + 1024 + 64 * 128 * 2;
+  uint8_t* s2 = s + 384 * 64 * 2 + 768 * 4 + 1024 + 64 * 128 * 2;
+  void* ucat = s2;                                                      // to_out folded over Wv (32 KB) | c12 | flags
+  float* c12 = (float*)(s2 + 256 * 64 * 2);
+  int* flags = (int*)(s2 + 256 * 64 * 2 + 1024);
+  void* gnws = s2 + 256 * 64 * 2 + 1024 + ((int64_t)(batch > 0 ? batch : 1) * 4 + 255) / 256 * 256;
   if (int rc = k_fold_prenorm_qkv(w_qkv, gamma, beta, cin, wfold, uv, st)) return rc;
   if (int rc = k_pack_conv_weight(w_out, 64, 128, 1, nullptr, 0, wout, LDM_DT_BF16, st)) return rc;
+  if (int rc = k_fold_to_out(w_qkv, gamma, uv, w_out, ucat, c12, st)) return rc;
   int splits = 1;
   if (int rc = k_group_norm_stats(x, ldx, batch, n_tokens, cin, 1, gnws, &splits, st)) return rc;
   LinAttnOut f;
   f.wout = wout; f.bout = b_out; f.y = y; f.ldy = ldy; f.ystats = ystats; f.ystats_bytes = (int64_t)batch * (n_tokens / 16) * 8;
   f.nslots_out = nullptr;
+  f.ucat = ucat; f.c12 = c12; f.flags = flags;
   return k_linear_attention_tc(x, ldx, wfold, uv, gnws, splits, eps, nullptr, batch, n_tokens, st, &f);
 }
 int ldm_linear_attention_qkv(const void* xn, int ldx, int cin, const void* wqkv_packed, void* out, int batch, int n_tokens,

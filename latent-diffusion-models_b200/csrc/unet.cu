@@ -46,6 +46,7 @@ struct AttnW {
   int p_qkv = -1, p_ow = -1, p_ob = -1, p_ogw = -1, p_ogb = -1, p_nw = -1, p_nb = -1;
   void* wqkv = nullptr; void* wout = nullptr; float* bout = nullptr;
   void* wfold = nullptr; float* uv = nullptr;  // to_qkv with the PreNorm GroupNorm folded in (fused attention kernel)
+  void* ucat = nullptr; float* c12 = nullptr;  // to_out folded over Wv, per head (k_fold_to_out; linattn_tc2_kernel, dim 64 only)
   float *og = nullptr, *ob = nullptr, *ng = nullptr, *nb = nullptr;
 };
 struct UpW {
@@ -167,6 +168,7 @@ void layout_attn(Bump& b, AttnW& a, int es) {
   b.take(a.wqkv, (int64_t)3 * HIDDEN * a.dim * es);
   b.take(a.wout, (int64_t)a.dim * HIDDEN * es);
   if (a.linear) { b.take(a.wfold, (int64_t)3 * HIDDEN * a.dim * 2); b.take(a.uv, (int64_t)2 * 3 * HIDDEN * 4); }
+  if (a.linear && a.dim == 64) { b.take(a.ucat, (int64_t)256 * 64 * 2); b.take(a.c12, 2 * 64 * 4); }
   b.take(a.bout, a.dim * 4);
   if (a.linear) { b.take(a.og, a.dim * 4); b.take(a.ob, a.dim * 4); }
   b.take(a.ng, a.dim * 4); b.take(a.nb, a.dim * 4);
@@ -198,7 +200,7 @@ int64_t layout_all(ldm_unet* h, uint8_t* base) {
 
 // workspace plan for one forward of `batch` rows
 struct Plan {
-  int64_t temb, tproj, temb_tab, tproj_tab, gnws, gnpk, gnpk_bytes, gnst, gnst_bytes, gnst2, gnst2_bytes, qkv, s[4], total;
+  int64_t temb, tproj, temb_tab, tproj_tab, gnws, gnpk, gnpk_bytes, gnst, gnst_bytes, gnst2, gnst2_bytes, laflag, qkv, s[4], total;
   std::vector<int64_t> hin;  // [L+1]
   std::vector<int64_t> cat;  // [L]
 };
@@ -223,6 +225,7 @@ Plan make_plan(const ldm_unet* h, int batch) {
   // GroupNorm(1, C) partial sums the fused attention kernel leaves for to_out's GroupNorm: S*S/16 slots per sample
   p.gnst2_bytes = (int64_t)batch * std::max<int64_t>(64, (int64_t)S * S / 16) * 8;
   p.gnst2 = take(p.gnst2_bytes);
+  p.laflag = take((int64_t)batch * 4);   // per-sample "redo with the exact kernel" flags of linattn_tc2_kernel
   int64_t max_elems = 0;
   for (int i = 0; i < L; ++i) {
     int64_t R = S >> i;
@@ -404,6 +407,7 @@ int pack_attn(ldm_unet* h, AttnW& a, const float* const* P, cudaStream_t st) {
   if (a.linear) { RC(k_copy_f32(P[a.p_ogw], a.og, a.dim, st)); RC(k_copy_f32(P[a.p_ogb], a.ob, a.dim, st)); }
   RC(k_copy_f32(P[a.p_nw], a.ng, a.dim, st)); RC(k_copy_f32(P[a.p_nb], a.nb, a.dim, st));
   if (a.linear) RC(k_fold_prenorm_qkv(P[a.p_qkv], P[a.p_nw], P[a.p_nb], a.dim, a.wfold, a.uv, st));
+  if (a.linear && a.dim == 64) RC(k_fold_to_out(P[a.p_qkv], P[a.p_nw], a.uv, P[a.p_ow], a.ucat, a.c12, st));
   return 0;
 }
 }  // namespace
@@ -713,6 +717,7 @@ struct Fwd {
         LinAttnOut fo;
         fo.wout = a.wout; fo.bout = a.bout; fo.y = s(1); fo.ldy = a.dim; fo.ystats = ws + plan.gnst2; fo.ystats_bytes = plan.gnst2_bytes;
         fo.nslots_out = &ns;
+        fo.ucat = a.ucat; fo.c12 = a.c12; fo.flags = reinterpret_cast<int*>(ws + plan.laflag);
         // to_out's GroupNorm(1, C) + the Residual add can ride along too (the CTA owns the whole sample), but the serial
         // tail of that pass costs more than the stand-alone apply kernel it replaces (measured: 98.3 vs 101.0 img/s): opt-in
         static const bool fold_gn = getenv("LDM_LINATTN_GN") != nullptr && atoi(getenv("LDM_LINATTN_GN")) != 0;

@@ -363,6 +363,30 @@ def test_linear_attention_prenorm_to_out_fused(B, R):
     assert float((var / got.double().var(dim=(1, 2, 3), unbiased=False) - 1).abs().max()) < 5e-3
 
 
+def test_linear_attention_to_out_exact_fallback():
+    """linattn_tc2_kernel shifts the softmax over tokens by the first token and evaluates the per-head softmax unshifted; a logit
+    88 away from its reference overflows, the sample is flagged and linattn_tc_kernel (two-pass softmax) redoes it in the same
+    call.  Sample 1 is scaled so that its logits span hundreds: it must come out finite and equal to what the exact kernel alone
+    produces (LDM_LINATTN_V1 is read once per process, so 'alone' = the unfused op + a 1x1 conv in torch), the others untouched."""
+    from ldm_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    B, R = 4, 16
+    x = torch.randn(B, 64, R, R, generator=g)
+    x[1, :, 0, 0] *= -3.0                                        # first token far from the rest of the sample
+    x = x.to(dev())
+    w = (torch.randn(384, 64, 1, 1, generator=g) * 6.0).to(dev())   # |q|, |k| ~ 50 sigma: k range > 88 within a channel
+    gamma = torch.ones(64, device=dev())
+    beta = torch.zeros(64, device=dev())
+    wo = (torch.randn(64, 128, 1, 1, generator=g) / 128 ** 0.5).to(dev())
+    bo = torch.randn(64, generator=g).to(dev())
+    y, stats = ops.linear_attention_prenorm_to_out(ops.to_nhwc(x, "bf16"), w, gamma, beta, wo, bo)
+    got = ops.to_nchw(y)
+    assert bool(torch.isfinite(got).all()) and bool(torch.isfinite(stats).all())
+    att = ops.to_nchw(ops.linear_attention_prenorm(ops.to_nhwc(x, "bf16"), w, gamma, beta, impl=0))   # exact tcgen05 kernel
+    ref = F.conv2d(att, wo, bo)
+    assert rel_l2(got, ref) < 2e-2
+
+
 @pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("B,R", [(3, 32), (160, 32), (5, 16)])
 def test_linear_attention_prenorm_fused(impl, B, R):
