@@ -356,6 +356,9 @@ int ldm_images_to_uint8(const float* x_nchw, uint8_t* out_nhwc, int batch, int c
 
 /* F.mse_loss(a, b) (mean reduction; src/Trainer.py:59, src/DiffusionModelTrainer.py:52,105) -> one device float */
 int ldm_mse(const float* a, const float* b, float* out_scalar, int64_t n, void* stream);
+/* ... and its backward through the prediction (loss.backward(), src/DiffusionModelTrainer.py:58-62; src/Trainer.py:60):
+ * dpred = 2 (pred - target) / n * grad_loss[0]; grad_loss is a device scalar (null = 1). */
+int ldm_mse_backward(const float* pred, const float* target, const float* grad_loss, float* dpred, int64_t n, void* stream);
 
 /* ---- first-stage autoencoder (src/Autoencoder.py) ------------------------------------------
  * Its 3x3 / 1x1 convolutions are ldm_conv2d; ldm_group_norm takes GroupNorm(32, C, eps=1e-6) + swish for every group

@@ -128,6 +128,7 @@ SIGNATURES = {
     "ldm_adam_step": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, vp]),
     "ldm_images_to_uint8": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_mse": (C.c_int, [vp, vp, vp, C.c_int64, vp]),
+    "ldm_mse_backward": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp]),
     "ldm_nchw_to_nhwc": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "ldm_nhwc_to_nchw": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
 }

@@ -217,6 +217,7 @@ int k_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double 
                 int step, double grad_scale, cudaStream_t st);
 int k_images_to_u8(const float* x, uint8_t* out, int batch, int C, int hw, int convention, cudaStream_t st);
 int k_mse(const float* a, const float* b, float* out, int64_t n, cudaStream_t st);
+int k_mse_backward(const float* pred, const float* target, const float* gout, float* dpred, int64_t n, cudaStream_t st);
 
 // ---- autoencoder.cu: the first-stage autoencoder's extra pieces (src/Autoencoder.py)
 int k_group_norm_any(const void* x, int ldx, void* y, int ldy, const float* gamma, const float* beta, int batch, int hw,

@@ -294,6 +294,10 @@ int ldm_mse(const float* a, const float* b, float* out_scalar, int64_t n, void* 
   LDM_REQUIRE(a && b && out_scalar, "ldm_mse: null argument");
   return k_mse(a, b, out_scalar, n, (cudaStream_t)stream);
 }
+int ldm_mse_backward(const float* pred, const float* target, const float* grad_loss, float* dpred, int64_t n, void* stream) {
+  LDM_REQUIRE(pred && target && dpred, "ldm_mse_backward: null argument");
+  return k_mse_backward(pred, target, grad_loss, dpred, n, (cudaStream_t)stream);
+}
 
 
 // ---- first-stage autoencoder (src/Autoencoder.py), the pieces beyond the UNet's conv / GroupNorm kernels

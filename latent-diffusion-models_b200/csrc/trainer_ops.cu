@@ -88,6 +88,15 @@ sq_diff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, flo
   }
 }
 
+// d/dpred mean((pred - target)^2) = 2 (pred - target) / n, times the incoming gradient of the (scalar) loss
+__global__ void __launch_bounds__(256)
+mse_backward_kernel(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ gout,
+                    float* __restrict__ dpred, int64_t n, float two_over_n) {
+  const float g = gout ? __ldg(gout) : 1.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dpred[i] = __fmul_rn(__fmul_rn(two_over_n, __fsub_rn(pred[i], target[i])), g);
+}
+
 }  // namespace
 
 int k_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
@@ -103,6 +112,14 @@ int k_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double 
   a.one_minus_beta1 = (float)(1.0 - beta1); a.one_minus_beta2 = (float)(1.0 - beta2);
   adam_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, st>>>(p, g, m, v, n, a);
   LDM_LAUNCHED("adam_step");
+  return 0;
+}
+
+int k_mse_backward(const float* pred, const float* target, const float* gout, float* dpred, int64_t n, cudaStream_t st) {
+  LDM_REQUIRE(n > 0, "mse_backward: empty input");
+  const int grid = (int)((n + 256 * 4 - 1) / (256 * 4));
+  mse_backward_kernel<<<grid < 1184 ? grid : 1184, 256, 0, st>>>(pred, target, gout, dpred, n, 2.0f / (float)n);
+  LDM_LAUNCHED("mse_backward");
   return 0;
 }
 

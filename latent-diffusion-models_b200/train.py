@@ -34,19 +34,26 @@ def _c(t: torch.Tensor) -> torch.Tensor:
 
 
 class _GradArena:
-    """One zero-filled fp32 buffer per training forward from which the backward kernels take their accumulation targets
-    (dW, db, dgamma, dbeta ...): one 81 MB memset instead of ~120 small fills per step.  Slices are 256-byte aligned (the
-    weight-gradient kernel uses 16-byte vector reductions).  Falls back to torch.zeros when no arena is open or it is used up
-    (several backward passes through one forward)."""
+    """One zero-filled fp32 buffer per training forward from which the backward kernels take the accumulation targets that have
+    no slot in an optimizer's gradient bucket (see ``_grad_target``): one memset instead of ~120 small fills per step.  Slices
+    are 256-byte aligned (the weight-gradient kernel uses 16-byte vector reductions).  Falls back to torch.zeros when no arena
+    is open or it is used up (several backward passes through one forward)."""
     buf: Optional[torch.Tensor] = None
     off: int = 0
 
     @classmethod
-    def open(cls, model, device) -> None:
-        n = getattr(model, "_grad_arena_elems", None)
+    def open(cls, model, device, bucketed: bool) -> None:
+        key = "_grad_arena_elems_bucketed" if bucketed else "_grad_arena_elems"
+        n = getattr(model, key, None)
         if n is None:
-            n = sum((p.numel() + 63) // 64 * 64 + 64 for p in model.parameters()) + 4096
-            model._grad_arena_elems = n
+            if bucketed:   # only what never lands in a slot: the concatenated time-projection weights and biases, the
+                # [4*Cout][Cin] staging form of the ConvTranspose weight gradients, the final conv's viewed weight + slack
+                n = sum((p.numel() + 63) // 64 * 64 + 64 for name, p in model.named_parameters() if ".mlp_t." in name)
+                n += sum((m.weight.numel() + 63) // 64 * 64 + 64 for m in model.modules() if isinstance(m, torch.nn.ConvTranspose2d))
+                n += 262144
+            else:
+                n = sum((p.numel() + 63) // 64 * 64 + 64 for p in model.parameters()) + 4096
+            setattr(model, key, n)
         cls.buf = torch.zeros(n, dtype=torch.float32, device=device)
         cls.off = 0
 
@@ -65,6 +72,19 @@ def _zeros(n: int, device) -> torch.Tensor:
     return _GradArena.zeros(int(n), device)
 
 
+def _grad_target(p: torch.Tensor) -> torch.Tensor:
+    """Zero-filled fp32 accumulation target for the gradient of parameter ``p`` (same shape).  When ``p`` belongs to a
+    ``trainer.FlatAdam`` this is its slice of the optimizer's flat gradient bucket: the backward kernel writes where the
+    all-reduce and the Adam kernel read, and autograd adopts the slice as ``p.grad`` (no per-step packing).  Otherwise a
+    slice of the step's arena."""
+    bucket = getattr(p, "_ldm_grad_bucket", None)
+    if bucket is not None:
+        slot = bucket.take_slot(p)
+        if slot is not None:
+            return slot
+    return _zeros(p.numel(), p.device).view_as(p)
+
+
 class _Conv(Function):
     """F.conv2d (3x3 pad 1 / 1x1) on NHWC; dgrad = the same implicit-GEMM kernel with the flipped, transposed filter."""
 
@@ -80,6 +100,7 @@ class _Conv(Function):
         y = ops.conv2d(x, wp, k, bias=b.detach() if b is not None else None, impl=impl)
         ctx.save_for_backward(x, w, wd)
         ctx.has_bias, ctx.impl, ctx.dt = b is not None, impl, dt
+        ctx.bias = b                                # the Parameter itself (not saved: only its gradient slot is looked up)
         return y
 
     @staticmethod
@@ -90,9 +111,8 @@ class _Conv(Function):
         B, H, W, _ = x.shape
         lib = _lb()
         dx = ops.conv2d(dy, wd, k, impl=ctx.impl)
-        buf = _zeros(w.numel() + cout, x.device)   # dW and db, zero-filled
-        dw = buf[:w.numel()].view_as(w)
-        db = buf[w.numel():] if ctx.has_bias else None
+        dw = _grad_target(w)                        # zero-filled: the optimizer's bucket slice, or the step's arena
+        db = _grad_target(ctx.bias) if ctx.has_bias else None
         nscr = lib.ldm_conv2d_wgrad_scratch_bytes(cin, cout, B, H, W, k, ops._dt(x)) if ctx.impl == 0 else 0
         if nscr > 0:   # tcgen05: contraction over pixels on channel-major copies of x and dy
             scr = torch.empty(nscr, dtype=torch.uint8, device=x.device)
@@ -127,8 +147,7 @@ class _GroupNorm(Function):
         dy = _c(dy)
         B, H, W, Cc = x.shape
         dx = torch.empty_like(x)
-        dgb = _zeros(2 * Cc, x.device)   # dgamma and dbeta, zero-filled
-        dg, db = dgb[:Cc], dgb[Cc:]
+        dg, db = _grad_target(gamma), _grad_target(beta)   # zero-filled
         rv = rowvec if ctx.has_rv else None
         drv = torch.empty(B, Cc, dtype=torch.float32, device=x.device) if ctx.has_rv else None
         lib = _lb()
@@ -164,7 +183,7 @@ class _ConvT(Function):
     @staticmethod
     def forward(ctx, x, w, b, impl):
         ctx.save_for_backward(x, w)
-        ctx.impl = impl
+        ctx.impl, ctx.bias = impl, b
         return ops.conv_transpose2x2(x, w.detach(), b.detach(), impl=impl)
 
     @staticmethod
@@ -189,8 +208,9 @@ class _ConvT(Function):
         else:
             _lib.check(lib.ldm_conv2d_wgrad(x.data_ptr(), x.stride(2), cin, dyq.data_ptr(), 4 * cout, 4 * cout, dwq.data_ptr(),
                                             None, B, H, W, 1, ops._dt(x), _st()))
-        dw = dwq.view(2, 2, cout, cin).permute(3, 2, 0, 1).contiguous()                        # layout only
-        db = _zeros(cout, x.device)
+        dw = _grad_target(w)
+        dw.copy_(dwq.view(2, 2, cout, cin).permute(3, 2, 0, 1))                                # layout only
+        db = _grad_target(ctx.bias)
         _lib.check(lib.ldm_column_sum(dy.data_ptr(), dy.stride(2), db.data_ptr(), B * 4 * H * W, cout, ops._dt(x), _st()))
         return dx, dw, db, None
 
@@ -240,6 +260,7 @@ class _InitialConv(Function):
         _lib.check(_lb().ldm_initial_conv(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), B, Cin, cout, H, W,
                                           ops._dt(y), scratch.data_ptr(), _st()))
         ctx.save_for_backward(x, w)
+        ctx.bias = b
         return y
 
     @staticmethod
@@ -248,8 +269,8 @@ class _InitialConv(Function):
         dy = _c(dy)
         B, Cin, H, W = x.shape
         cout = w.shape[0]
-        dw = _zeros(w.numel(), w.device).view_as(w)
-        db = _zeros(cout, x.device)
+        dw = _grad_target(w)
+        db = _grad_target(ctx.bias)
         lib = _lb()
         scr = torch.empty(lib.ldm_initial_conv_wgrad_scratch_bytes(B, Cin, cout, H, W), dtype=torch.uint8, device=x.device)
         _lib.check(lib.ldm_initial_conv_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), B, Cin, cout, H, W,
@@ -297,6 +318,7 @@ class _TimeEmbed(Function):
                                         ws.data_ptr(), _st()))
         ctx.save_for_backward(t, y if y is not None else torch.empty(0), w1, b1, w3, label if label is not None else torch.empty(0))
         ctx.has_y = y is not None
+        ctx.b3 = b3
         return temb
 
     @staticmethod
@@ -304,9 +326,8 @@ class _TimeEmbed(Function):
         t, y, w1, b1, w3, label = ctx.saved_tensors
         dtemb = _c(dtemb)
         B, D = dtemb.shape
-        dw1, db1, dw3 = (_zeros(v.numel(), v.device).view_as(v) for v in (w1, b1, w3))
-        db3 = _zeros(D, w1.device)
-        dlabel = _zeros(label.numel(), label.device).view_as(label) if ctx.has_y else None
+        dw1, db1, dw3, db3 = (_grad_target(v) for v in (w1, b1, w3, ctx.b3))
+        dlabel = _grad_target(label) if ctx.has_y else None
         ws = _time_ws(B, D, 0, w1.device)
         yy = y if ctx.has_y else None
         _lib.check(_lb().ldm_time_embed_backward(t.data_ptr(), _lib.ptr(yy), yy.numel() if yy is not None else 0,
@@ -417,7 +438,10 @@ def unet_autograd_forward(model, x_noisy: torch.Tensor, t: torch.Tensor, y: Opti
             raise _lib.LdmError("UNet parameters must be fp32 tensors on the input's CUDA device (call model.to(device))")
     dt, impl = model.compute_dtype, model.conv_impl
     dt = "bf16" if _lib.DTYPES[dt] == _lib.BF16 else "fp32"
-    _GradArena.open(model, dev)
+    bucket = getattr(next(model.parameters()), "_ldm_grad_bucket", None)   # trainer.FlatAdam's flat gradient buffer, if any
+    if bucket is not None:
+        bucket.begin_step()                    # one memset of the bucket; the backward kernels accumulate into its slices
+    _GradArena.open(model, dev, bucket is not None)
     x = _c(x_noisy.detach().to(torch.float32))
     t = _c(t.detach().to(device=dev, dtype=torch.int64))
     if y is not None:

@@ -29,13 +29,23 @@ class FlatAdam:
     """Adam with torch's defaults (betas 0.9/0.999, eps 1e-8, no weight decay, no amsgrad) over flat buffers.
 
     On construction every parameter's storage is moved into one flat fp32 buffer (``p.data`` becomes a view into it, so
-    the module, its ``state_dict()`` and the native weight re-pack keep working).  ``step()`` packs the ``.grad`` tensors
-    into the flat gradient buffer (zeros for parameters without one, e.g. the reference's four dead bottleneck ``mlp_t``
-    tensors, so every rank reduces the same length), all-reduces it when a process group is up, and launches
-    ``ldm_adam_step`` once.  The 1/world_size of the mean is folded into the kernel's ``grad_scale``.
-    """
+    the module, its ``state_dict()`` and the native weight re-pack keep working); gradients and both moments have flat
+    buffers of the same layout (every parameter starts on a 256-byte boundary; the padding stays zero for ever).
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+    The flat gradient buffer IS the gradient bucket: each parameter carries its slice as ``p._ldm_grad_slot`` and the
+    backward kernels of ``ldm_b200.train`` accumulate dW / db / dgamma / dbeta straight into it (the training forward zeroes
+    the bucket once, ``begin_step``), so after ``loss.backward()`` ``p.grad`` is that slice and ``step()`` has nothing to
+    pack.  Gradients that arrive some other way (a torch-autograd model, the concatenated time-projection weights) are
+    copied in; parameters without one (the reference's four dead bottleneck ``mlp_t`` tensors) contribute zeros, so every
+    rank reduces the same bytes.  ``step()`` all-reduces the bucket in ``n_buckets`` contiguous pieces, LAST piece first
+    (parameters() order is forward order, so the tail -- decoder, final conv -- is what backward finishes first), each
+    piece's Adam launch (``ldm_adam_step``) overlapping the next piece's NCCL all-reduce.  The mean's 1/world_size is folded
+    into the kernel's ``grad_scale``."""
+
+    ALIGN = 64   # elements: 256 bytes (the weight-gradient kernel reduces with 16-byte vector atomics)
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 n_buckets: int = 4):
         self.params: List[torch.nn.Parameter] = [p for p in params]
         if not self.params:
             raise ValueError("FlatAdam: no parameters")
@@ -46,9 +56,10 @@ class FlatAdam:
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.device = dev
         sizes = [p.numel() for p in self.params]
-        self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        padded = [(k + self.ALIGN - 1) // self.ALIGN * self.ALIGN for k in sizes]
+        self.offsets = np.concatenate([[0], np.cumsum(padded)]).astype(np.int64)
         n = int(self.offsets[-1])
-        self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_param = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -58,8 +69,37 @@ class FlatAdam:
                 view = self.flat_param[int(o):int(o) + k].view_as(p)
                 view.copy_(p.data)
                 p.data = view
-                self.grad_views.append(self.flat_grad[int(o):int(o) + k].view_as(p))
+                slot = self.flat_grad[int(o):int(o) + k].view_as(p)
+                self.grad_views.append(slot)
+                p._ldm_grad_slot = slot          # read by ldm_b200.train's backward functions
+                p._ldm_grad_bucket = self
+        # contiguous pieces of about equal size, cut at parameter boundaries
+        n_buckets = max(1, min(int(n_buckets), len(self.params)))
+        cuts = [0]
+        for b in range(1, n_buckets):
+            target = n * b // n_buckets
+            cuts.append(int(self.offsets[int(np.searchsorted(self.offsets, target))]))
+        cuts.append(n)
+        self.bucket_bounds = sorted(set(cuts))
         self.step_count = 0
+        self.generation = 0                      # bumped by begin_step: a slot is handed out once per generation
+        self._slot_gen: dict = {}
+        self._reduce_stream: Optional[torch.cuda.Stream] = None
+
+    # ---- the bucket protocol used by ldm_b200.train
+    def begin_step(self) -> None:
+        """Zero the gradient bucket (one memset; CUDA-graph capturable) and open a new generation of slot hand-outs."""
+        self.flat_grad.zero_()
+        self.generation += 1
+
+    def take_slot(self, p: torch.Tensor) -> Optional[torch.Tensor]:
+        """The zero-filled slice a backward kernel may accumulate ``p``'s gradient into, or None when in-place accumulation
+        would be wrong: the bucket was not zeroed this step, the slot was already handed out (two backward passes through
+        one forward), or ``p.grad`` already holds something (autograd would then ADD the returned tensor to it)."""
+        if self.generation == 0 or p.grad is not None or self._slot_gen.get(id(p)) == self.generation:
+            return None
+        self._slot_gen[id(p)] = self.generation
+        return p._ldm_grad_slot.detach()     # a fresh alias: autograd adopts a gradient only if nobody else holds the object
 
     # torch.optim.Optimizer surface used by the reference (src/DiffusionModelTrainer.py:55-63)
     def zero_grad(self, set_to_none: bool = True) -> None:
@@ -75,7 +115,7 @@ class FlatAdam:
         for p, v in zip(self.params, self.grad_views):
             if p.grad is None:
                 dead.append(v)
-            else:
+            elif p.grad.data_ptr() != v.data_ptr():
                 src.append(p.grad)
                 dst.append(v)
         if dead:
@@ -83,14 +123,26 @@ class FlatAdam:
         if dst:
             torch._foreach_copy_(dst, src)
         scale = float(grad_scale)
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)      # NCCL over NVLink; the mean's 1/world is in the kernel
-            scale /= dist.get_world_size()
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.step_count += 1
+        lib = _lib.load()
+        bounds = self.bucket_bounds
         with torch.cuda.device(self.device):
-            _lib.check(_lib.load().ldm_adam_step(self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
-                                                 self.exp_avg_sq.data_ptr(), self.flat_param.numel(), self.lr, self.betas[0],
-                                                 self.betas[1], self.eps, self.step_count, scale, _lib.stream_ptr()))
+            def adam(lo: int, hi: int) -> None:
+                _lib.check(lib.ldm_adam_step(self.flat_param.data_ptr() + 4 * lo, self.flat_grad.data_ptr() + 4 * lo,
+                                             self.exp_avg.data_ptr() + 4 * lo, self.exp_avg_sq.data_ptr() + 4 * lo, hi - lo,
+                                             self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
+                                             scale / world, _lib.stream_ptr()))
+            if world > 1:
+                # NCCL over NVLink, last bucket first; the all-reduce of piece k runs (on NCCL's stream) under the Adam
+                # launch of piece k+1
+                works = [(lo, hi, dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+                         for lo, hi in reversed(list(zip(bounds[:-1], bounds[1:])))]
+                for lo, hi, w in works:
+                    w.wait()                 # stream-level wait on CUDA: the host does not block
+                    adam(lo, hi)
+            else:
+                adam(0, bounds[-1])
         torch.autograd.graph.increment_version(self.params)   # the kernel wrote through raw pointers: tell torch (and the
         #                                                       UNet's weight re-pack, which keys on ._version)
 
@@ -117,8 +169,45 @@ def mse_loss(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+class _MSELoss(torch.autograd.Function):
+    """``F.mse_loss(input, target)`` (mean) with both directions on the C ABI: ``ldm_mse`` forward, ``ldm_mse_backward``
+    for whichever side needs a gradient -- the training loss of src/DiffusionModelTrainer.py:48 / src/Trainer.py:60."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a32, b32 = a.detach().to(torch.float32).contiguous(), b.detach().to(torch.float32).contiguous()
+        ctx.save_for_backward(a32, b32)
+        ctx.dtypes = (a.dtype, b.dtype)
+        out = torch.empty((), dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            _lib.check(_lib.load().ldm_mse(a32.data_ptr(), b32.data_ptr(), out.data_ptr(), a32.numel(), _lib.stream_ptr()))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b = ctx.saved_tensors
+        g = gout.detach().to(torch.float32).contiguous()
+        lib = _lib.load()
+        grads = [None, None]
+        with torch.cuda.device(a.device):
+            for i, (pred, target) in enumerate(((a, b), (b, a))):
+                if ctx.needs_input_grad[i]:
+                    d = torch.empty_like(pred)
+                    _lib.check(lib.ldm_mse_backward(pred.data_ptr(), target.data_ptr(), g.data_ptr(), d.data_ptr(), pred.numel(),
+                                                    _lib.stream_ptr()))
+                    grads[i] = d.to(ctx.dtypes[i])
+        return tuple(grads)
+
+
+def mse_loss_autograd(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Differentiable ``F.mse_loss(a, b)`` for CUDA tensors of one shape (no CPU path): the default training loss."""
+    if not a.is_cuda or a.shape != b.shape:
+        raise _lib.LdmError("mse_loss_autograd: two CUDA tensors of one shape expected (no CPU path)")
+    return _MSELoss.apply(a, b)
+
+
 def train_step(model, diffusion, optimizer, data: torch.Tensor, targets: Optional[torch.Tensor], *, drop_labels: bool = False,
-               forward: Optional[Callable] = None, loss_fn: Callable = torch.nn.functional.mse_loss) -> torch.Tensor:
+               forward: Optional[Callable] = None, loss_fn: Callable = mse_loss_autograd) -> torch.Tensor:
     """One iteration of ``_train_epoch`` (src/DiffusionModelTrainer.py:36-67): noise, forward, MSE, backward, optimizer.
     ``drop_labels`` is the reference's 10 % coin (:44), drawn by the caller so that all ranks agree.  ``forward`` may be a
     CUDA-graphed callable from ``ldm_b200.train.make_graphed``.  Returns the (device) loss; the caller decides when to sync."""
@@ -205,7 +294,7 @@ class DiffusionModelTrainer:
         else:
             self.use_amp = getattr(model, "compute_dtype", "bf16") == "bf16"
         self.optimizer = FlatAdam(model.parameters(), lr=float(get("lr")))
-        self.loss_fn = torch.nn.functional.mse_loss
+        self.loss_fn = mse_loss_autograd          # F.mse_loss (src/Trainer.py:60) as ldm_mse / ldm_mse_backward
         # the label-drop coin (:44) must fall the same way on every rank of a data-parallel job (a rank that drops its labels
         # has no label_emb gradient): one seed for all ranks unless the caller passes a generator
         self._rng = rng if rng is not None else np.random.default_rng(0x5EED)

@@ -127,6 +127,59 @@ def test_mse_matches_torch():
         assert abs(float(trainer.mse_loss(a, b)) - float(ref)) < 1e-5 * float(ref)
 
 
+def test_mse_autograd_matches_torch_both_sides():
+    """F.mse_loss(noise, eps_theta) as the training step calls it (src/DiffusionModelTrainer.py:48): value and both gradients."""
+    from ldm_b200 import trainer
+    gen = torch.Generator().manual_seed(2)
+    a = torch.randn(4, 3, 32, 32, generator=gen).to(dev()).requires_grad_(True)
+    b = torch.randn(4, 3, 32, 32, generator=gen).to(dev()).requires_grad_(True)
+    ar, br = a.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    (trainer.mse_loss_autograd(a, b) * 3.0).backward()
+    ref = torch.nn.functional.mse_loss(ar, br)
+    (ref * 3.0).backward()
+    assert abs(float(trainer.mse_loss_autograd(a.detach(), b.detach())) - float(ref.detach())) < 1e-6 * float(ref.detach())
+    assert rel_l2(a.grad, ar.grad) < 1e-6 and rel_l2(b.grad, br.grad) < 1e-6
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_backward_kernels_write_into_the_optimizer_bucket(graphs):
+    """FlatAdam's flat gradient buffer is the bucket the backward kernels accumulate into: after a training step's backward,
+    p.grad of (nearly) every live parameter IS its slice of flat_grad -- nothing is packed -- and the values equal the
+    gradients of the same model without an optimizer attached (arena path)."""
+    from ldm_b200 import trainer
+    from ldm_b200.train import make_graphed
+    import ldm_b200
+    a, _ = make_model("bf16", seed=7)
+    b, _ = make_model("bf16", seed=7)
+    opt = trainer.FlatAdam(a.parameters(), lr=0.0)
+    d = ldm_b200.Diffusion(1000, dev())
+    gen = torch.Generator().manual_seed(4)
+    x0 = (torch.rand(6, 3, 32, 32, generator=gen) * 2 - 1).to(dev())
+    y = torch.randint(0, 10, (6,), generator=gen).to(dev())
+    t = torch.randint(0, 1000, (6,), generator=gen).to(dev())
+    noise = torch.randn(6, 3, 32, 32, generator=gen).to(dev())
+    xt = d.q_sample(x0, t, eps=noise)
+    fwd = make_graphed(a, torch.randn_like(xt), t.clone(), y.clone()) if graphs else a
+    for _ in range(2):                                     # twice: the bucket is re-zeroed by every forward
+        loss = trainer.mse_loss_autograd(noise, fwd(xt, t, y))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+    trainer.mse_loss_autograd(noise, b(xt, t, y)).backward()
+    lo, hi = opt.flat_grad.data_ptr(), opt.flat_grad.data_ptr() + 4 * opt.flat_grad.numel()
+    live = [(pa, pb) for pa, pb in zip(a.parameters(), b.parameters()) if pb.grad is not None]
+    in_place = sum(1 for pa, _ in live if pa.grad.data_ptr() == pa._ldm_grad_slot.data_ptr())
+    numel_in_place = sum(pa.numel() for pa, _ in live if pa.grad.data_ptr() == pa._ldm_grad_slot.data_ptr())
+    assert all(pa.grad is not None for pa, _ in live)
+    assert numel_in_place > 0.95 * sum(pa.numel() for pa, _ in live), (in_place, len(live))
+    assert all(lo <= pa.grad.data_ptr() < hi for pa, _ in live if pa.grad.data_ptr() == pa._ldm_grad_slot.data_ptr())
+    ga = torch.cat([pa.grad.reshape(-1) for pa, _ in live])
+    gb = torch.cat([pb.grad.reshape(-1) for _, pb in live])
+    assert rel_l2(ga, gb) < 2e-3                           # same kernels; atomics ordering only
+    opt.step()                                             # lr = 0: packs the few out-of-bucket gradients, changes no weight
+    flat = torch.cat([v.reshape(-1) for v, (pa, pb) in zip(opt.grad_views, zip(a.parameters(), b.parameters())) if pb.grad is not None])
+    assert rel_l2(flat, gb) < 2e-3
+
+
 @pytest.mark.parametrize("graphs", [True, False])
 def test_trainer_epochs_reduce_loss(graphs):
     import ldm_b200
