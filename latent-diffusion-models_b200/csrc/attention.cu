@@ -201,11 +201,46 @@ constexpr float LOG2E = 1.4426950408889634f;
 // of every ldmatrix 8x8 block (and the quad-strided fragment stores) on distinct bank groups
 __device__ __forceinline__ uint32_t lm_off(int r, int c) { return (uint32_t)(r * LM_ROW + ((c ^ ((r >> 1) & 3)) << 4)); }
 
-__global__ void __launch_bounds__(128) linattn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N) {
+// AFF: qkv holds the RAW projection (W diag(gamma)) x of the un-normalised block input; the PreNorm GroupNorm(1, C) is applied
+// here as the per-sample affine map it is (q = r q_raw + cq, k = r k_raw + const, v = r v_raw + cv with r the sample's rstd and
+// cq / cv = fold constants - r mu rowsums: k_fold_prenorm_qkv), so the normalised tensor is never written (src/UNet.py:106-110).
+struct LaAffine {
+  const float* uv;             // [2][384] fold constants
+  const float2* gn_part; int gn_splits; float gn_eps;   // statistics: > 0 pivoted slabs, < 0 raw {S, Q} slots
+  const bf16* x; int ldx;      // raw input (pivot of the slab statistics)
+  int cin;
+};
+template <bool AFF>
+__global__ void __launch_bounds__(128) linattn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N, const LaAffine af) {
   // per warp: [stage][k|v] tiles of 2 KB
   __shared__ __align__(128) uint8_t smem[4][2][2][LM_BUF];
   const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
+  float gr = 1.f, gmu = 0.f;
+  if (AFF) {
+    const double cnt = (double)N * (double)af.cin;
+    if (af.gn_splits < 0) {
+      double a = 0.0, q2 = 0.0;
+      for (int sp = lane; sp < -af.gn_splits; sp += 32) { const float2 v = __ldg(af.gn_part + (int64_t)b * (-af.gn_splits) + sp); a += (double)v.x; q2 += (double)v.y; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); q2 += __shfl_xor_sync(0xffffffffu, q2, o); }
+      const double m1 = a / cnt;
+      double var = q2 / cnt - m1 * m1;
+      if (var < 0.0) var = 0.0;
+      gmu = (float)m1;
+      gr = (float)(1.0 / sqrt(var + (double)af.gn_eps));
+    } else {
+      float a = 0.f, q2 = 0.f;
+      for (int sp = 0; sp < af.gn_splits; ++sp) { const float2 v = __ldg(af.gn_part + (int64_t)b * af.gn_splits + sp); a += v.x; q2 += v.y; }
+      const float K = __bfloat162float(af.x[(int64_t)b * N * af.ldx]);
+      const float inv_n = 1.0f / (float)cnt;
+      const float m1 = a * inv_n;
+      const float var = fmaxf(q2 * inv_n - m1 * m1, 0.f);
+      gmu = K + m1;
+      gr = 1.0f / sqrtf(var + af.gn_eps);
+    }
+  }
+  const float KL = gr * 1.4426950408889634f;     // log2(e) times the sample's rstd (1 when not AFF)
   const bf16* base = qkv + (int64_t)b * N * 384 + h * LA_D;
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&smem[h][0][0][0]);
   auto buf = [&](int stage, int which) { return sbase + (uint32_t)((stage * 2 + which) * LM_BUF); };
@@ -278,9 +313,9 @@ __global__ void __launch_bounds__(128) linattn_mma_kernel(const bf16* __restrict
           }
         mx = quad_max(mx);
         const float nm = fmaxf(m_run[mt][hf], mx);
-        sc[mt][hf] = ex2f((m_run[mt][hf] - nm) * LOG2E);
+        sc[mt][hf] = ex2f((m_run[mt][hf] - nm) * KL);
         m_run[mt][hf] = nm;
-        ml2[mt][hf] = nm * LOG2E;
+        ml2[mt][hf] = nm * KL;
         z[mt][hf] *= sc[mt][hf];
       }
 #pragma unroll
@@ -300,7 +335,7 @@ __global__ void __launch_bounds__(128) linattn_mma_kernel(const bf16* __restrict
           for (int i = 0; i < 4; ++i) {
             const int hf = i & 1;
             float2 x = unpack_bf2(a[st][mt][i]);
-            const float p0 = ex2f(fmaf(x.x, LOG2E, -ml2[mt][hf])), p1 = ex2f(fmaf(x.y, LOG2E, -ml2[mt][hf]));
+            const float p0 = ex2f(fmaf(x.x, KL, -ml2[mt][hf])), p1 = ex2f(fmaf(x.y, KL, -ml2[mt][hf]));
             z[mt][hf] += p0 + p1;
             a[st][mt][i] = pack_bf2(p0, p1);
           }
@@ -335,11 +370,17 @@ __global__ void __launch_bounds__(128) linattn_mma_kernel(const bf16* __restrict
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
-      const float f = 0.17677669529663687f / quad_sum(z[mt][hf]);
+      const float f = 0.17677669529663687f * gr / quad_sum(z[mt][hf]);
       const int d = mt * 16 + hf * 8 + g;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        const uint32_t v = pack_bf2(acc[mt][nt][hf * 2] * f, acc[mt][nt][hf * 2 + 1] * f);
+        float c0 = 0.f, c1 = 0.f;                 // v constants of columns e = 8 nt + 2 tq, + 1 (times 32^-1/2)
+        if (AFF) {
+          const int e = 256 + 32 * h + 8 * nt + 2 * tq;
+          c0 = 0.17677669529663687f * (af.uv[384 + e] - gr * gmu * af.uv[e]);
+          c1 = 0.17677669529663687f * (af.uv[384 + e + 1] - gr * gmu * af.uv[e + 1]);
+        }
+        const uint32_t v = pack_bf2(fmaf(acc[mt][nt][hf * 2], f, c0), fmaf(acc[mt][nt][hf * 2 + 1], f, c1));
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(ctx_s + lm_off(d, nt) + tq * 4), "r"(v) : "memory");
       }
     }
@@ -364,6 +405,15 @@ __global__ void __launch_bounds__(128) linattn_mma_kernel(const bf16* __restrict
       if (tok0 + r < N) cp_async16(buf(stage, 1) + lm_off(r, ch), base + (int64_t)(tok0 + r) * 384 + ch * 8);
     }
   };
+  float2 cq[4];                    // q constants of this lane's channels d = 16 ks + 8 j + 2 tq, + 1 (index 2 ks + j)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    cq[i] = make_float2(0.f, 0.f);
+    if (AFF) {
+      const int d = 32 * h + 16 * (i >> 1) + 8 * (i & 1) + 2 * tq;
+      cq[i] = make_float2(af.uv[384 + d] - gr * gmu * af.uv[d], af.uv[384 + d + 1] - gr * gmu * af.uv[d + 1]);
+    }
+  }
   const uint32_t stg = buf(1, 0);  // 16-token output staging tile
   bf16* obase = out + (int64_t)b * N * 128 + h * LA_D;
   load_q(0, 0);
@@ -390,6 +440,10 @@ __global__ void __launch_bounds__(128) linattn_mma_kernel(const bf16* __restrict
         float2 x[4];
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) { x[2 * ks] = unpack_bf2(aq[ks][hf]); x[2 * ks + 1] = unpack_bf2(aq[ks][hf + 2]); }
+        if (AFF) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { x[i].x = fmaf(x[i].x, gr, cq[i].x); x[i].y = fmaf(x[i].y, gr, cq[i].y); }
+        }
         float mx = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(x[i].x, x[i].y));
@@ -1227,10 +1281,22 @@ int k_linear_attention(const void* qkv, void* out, int batch, int n_tokens, int 
   if (batch == 0 || n_tokens == 0) return 0;
   int grid = batch * LA_HEADS;
   if (dtype == LDM_DT_BF16 && n_tokens % 16 == 0 && getenv("LDM_LINATTN_SIMT") == nullptr)
-    LDM_CUDA(ldm_launch_pdl(linattn_mma_kernel, dim3(batch), dim3(128), 0, st, (const bf16*)qkv, (bf16*)out, n_tokens));
+    LDM_CUDA(ldm_launch_pdl(linattn_mma_kernel<false>, dim3(batch), dim3(128), 0, st, (const bf16*)qkv, (bf16*)out, n_tokens, LaAffine{}));
   else if (dtype == LDM_DT_BF16) linattn_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)qkv, (bf16*)out, n_tokens);
   else linattn_kernel<float><<<grid, 256, 0, st>>>((const float*)qkv, (float*)out, n_tokens);
   LDM_LAUNCHED("linear_attention");
+  return 0;
+}
+
+// LinearAttention core on the RAW to_qkv projection of the un-normalised block input (see LaAffine): bf16, N % 16 == 0
+int k_linear_attention_prenorm_core(const void* qkv_raw, void* out, const float* uv, const void* gn_part, int gn_splits, float eps,
+                                    const void* x, int ldx, int cin, int batch, int n_tokens, cudaStream_t st) {
+  LDM_REQUIRE(n_tokens % 16 == 0 && uv && gn_part && gn_splits != 0, "linear_attention_prenorm_core: needs N %% 16 == 0 and statistics");
+  if (batch == 0 || n_tokens == 0) return 0;
+  LaAffine af;
+  af.uv = uv; af.gn_part = (const float2*)gn_part; af.gn_splits = gn_splits; af.gn_eps = eps; af.x = (const bf16*)x; af.ldx = ldx; af.cin = cin;
+  LDM_CUDA(ldm_launch_pdl(linattn_mma_kernel<true>, dim3(batch), dim3(128), 0, st, (const bf16*)qkv_raw, (bf16*)out, n_tokens, af));
+  LDM_LAUNCHED("linear_attention_prenorm_core");
   return 0;
 }
 

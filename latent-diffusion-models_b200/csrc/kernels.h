@@ -109,6 +109,10 @@ int k_linear_attention_tc(const void* x, int ldx, const void* wqkv, const float*
                           void* out, int batch, int n_tokens, cudaStream_t st, const LinAttnOut* fuse = nullptr);
 int k_fold_prenorm_qkv(const float* wqkv /*[384][cin] fp32*/, const float* gamma, const float* beta, int cin, void* wfold,
                        float* uv, cudaStream_t st);
+// LinearAttention core reading the RAW projection wfold x of the un-normalised block input: the PreNorm GroupNorm(1, C) is the
+// per-sample affine map the kernel applies on the fly (any cin; bf16; N % 16 == 0)
+int k_linear_attention_prenorm_core(const void* qkv_raw, void* out, const float* uv, const void* gn_part, int gn_splits, float eps,
+                                    const void* x, int ldx, int cin, int batch, int n_tokens, cudaStream_t st);
 int k_attention(const void* qkv, void* out, int batch, int n_tokens, int dtype, cudaStream_t st);
 
 // ---- conv (conv_simt.cu / conv_tc.cu)

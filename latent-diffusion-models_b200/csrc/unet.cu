@@ -742,6 +742,19 @@ struct Fwd {
              k_linear_attention_qkv_prenorm(d, ldd, a.dim, a.wfold, a.uv, gpart, splits, GN_EPS, qkv, B, R * R, dt, st));
       return to_out(qkv);
     }
+    static const bool affine_off = getenv("LDM_LINATTN_NO_AFFINE") != nullptr;
+    if (a.linear && impl == 0 && dt == LDM_DT_BF16 && (R * R) % 16 == 0 && !affine_off) {
+      // wider LinearAttention sites: to_qkv runs on the RAW block input with the gamma-folded weights and the attention core
+      // applies the PreNorm GroupNorm(1, C) as the per-sample affine map it is -- the normalised tensor is never written
+      int splits = 1;
+      if (slots > 0) splits = -slots;   // statistics left by the producing convolution's epilogue
+      else PROF(LDM_FAM_GROUP_NORM, 0, (double)B * R * R * a.dim * es, k_group_norm_stats(d, ldd, B, R * R, a.dim, 1, gnws(), &splits, st));
+      const void* gpart = slots > 0 ? (const void*)(ws + plan.gnst) : gnws();
+      RC(conv(d, ldd, a.dim, nullptr, 0, 0, a.wfold, nullptr, nullptr, 0, nullptr, 0, qkv, 3 * HIDDEN, 3 * HIDDEN, R, 1));
+      PROF(LDM_FAM_LINEAR_ATTENTION, (double)B * 4 * 2 * 2.0 * R * R * 32 * 32, (double)B * R * R * (3 + 1) * HIDDEN * es,
+           k_linear_attention_prenorm_core(qkv, s(0), a.uv, gpart, splits, GN_EPS, d, ldd, a.dim, B, R * R, st));
+      return to_out(s(0));
+    }
     if (slots > 0 && dt == LDM_DT_BF16 && k_group_norm_streams(R * R, a.dim, dt)) {
       // PreNorm apply only: the statistics came out of the producing convolution's epilogue
       PROF(LDM_FAM_GROUP_NORM, 0, (double)B * R * R * a.dim * es * 2,
