@@ -240,3 +240,26 @@ def images_to_uint8(x_nchw: torch.Tensor, convention: str = "save_image") -> tor
         _lib.check(_lib.load().ldm_images_to_uint8(x.data_ptr(), out.data_ptr(), B, Cc, H * W, _U8_CONVENTIONS[convention],
                                                    _lib.stream_ptr()))
     return out
+
+
+def _on_tensor_device(fn):
+    """Run ``fn`` with its first CUDA tensor argument's device current: the kernels launch on ``_lib.stream_ptr()``, the
+    CURRENT device's stream, so an op on a cuda:1 tensor must not run under cuda:0 (multi-GPU-in-one-process)."""
+    import functools
+
+    @functools.wraps(fn)
+    def guarded(*args, **kwargs):
+        for v in args + tuple(kwargs.values()):
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                if v.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(v.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return guarded
+
+
+for _name, _fn in list(globals().items()):
+    if isinstance(_fn, type(_on_tensor_device)) and _fn.__module__ == __name__ and not _name.startswith("_"):
+        globals()[_name] = _on_tensor_device(_fn)
+del _name, _fn

@@ -282,11 +282,12 @@ class _FinalConv(Function):
     @staticmethod
     def forward(ctx, x, w, b):
         B, H, W, cin = x.shape
-        cout = w.shape[0]
+        cout = w.shape[0]                      # w: the 1x1 Conv2d weight [out, ch, 1, 1] (contiguous: read as [out][ch])
         y = torch.empty(B, cout, H, W, dtype=torch.float32, device=x.device)
         _lib.check(_lb().ldm_final_conv(x.data_ptr(), x.stride(2), w.data_ptr(), b.data_ptr(), y.data_ptr(), B, cin, cout,
                                         H * W, ops._dt(x), _st()))
         ctx.save_for_backward(x, w)
+        ctx.bias = b
         return y
 
     @staticmethod
@@ -296,8 +297,8 @@ class _FinalConv(Function):
         B, H, W, cin = x.shape
         cout = w.shape[0]
         dx = torch.empty_like(x)
-        dw = _zeros(w.numel(), w.device).view_as(w)
-        db = _zeros(cout, x.device)
+        dw = _grad_target(w)
+        db = _grad_target(ctx.bias)
         _lib.check(_lb().ldm_final_conv_backward(dout.data_ptr(), x.data_ptr(), x.stride(2), w.data_ptr(), dx.data_ptr(),
                                                  dw.data_ptr(), db.data_ptr(), B, cin, cout, H * W, ops._dt(x), _st()))
         return dx, dw, db
@@ -338,8 +339,15 @@ class _TimeEmbed(Function):
 
 
 class _TimeProj(Function):
+    """The ResNetBlocks' time-embedding projections ``mlp_t`` = Linear(SiLU(temb)) (src/UNet.py:70-73,88-93) of several blocks
+    as ONE GEMM over their concatenated weights.  The blocks' (weight, bias) Parameters are the inputs themselves (not a
+    torch.cat of them), so that backward can drop every block's rows of dW / db into that parameter's gradient slot."""
+
     @staticmethod
-    def forward(ctx, temb, w, b):
+    def forward(ctx, temb, *wb):
+        ws_, bs_ = wb[0::2], wb[1::2]
+        w = torch.cat([v.detach() for v in ws_], 0)
+        b = torch.cat([v.detach() for v in bs_], 0)
         B, D = temb.shape
         total = w.shape[0]
         out = torch.empty(B, total, dtype=torch.float32, device=temb.device)
@@ -347,6 +355,7 @@ class _TimeProj(Function):
         _lib.check(_lb().ldm_time_proj(temb.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), B, D, total,
                                        ws.data_ptr(), _st()))
         ctx.save_for_backward(temb, w)
+        ctx.params = wb
         return out
 
     @staticmethod
@@ -361,7 +370,14 @@ class _TimeProj(Function):
         ws = _time_ws(B, D, total, temb.device)
         _lib.check(_lb().ldm_time_proj_backward(temb.data_ptr(), w.data_ptr(), dout.data_ptr(), dw.data_ptr(), db.data_ptr(),
                                                 dtemb.data_ptr(), B, D, total, ws.data_ptr(), _st()))
-        return dtemb, dw, db
+        grads, srcs, off = [], [], 0
+        for wi, bi in zip(ctx.params[0::2], ctx.params[1::2]):
+            n = wi.shape[0]
+            grads += [_grad_target(wi), _grad_target(bi)]
+            srcs += [dw[off:off + n], db[off:off + n]]
+            off += n
+        torch._foreach_copy_(grads, srcs)          # one multi-tensor launch: every block's rows into that parameter's slot
+        return (dtemb, *grads)
 
 
 class _Add(Function):
@@ -430,18 +446,27 @@ def _attn_site(site, x, linear, impl):
     return _Add.apply(o, x)
 
 
-def unet_autograd_forward(model, x_noisy: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor]):
-    """UNet.forward (src/UNet.py:361-389) with gradients to every live parameter."""
+def _time_slices(blocks, temb):
+    """{id(block): [B, cout] slice} of one concatenated time projection over `blocks` (None without a time embedding)."""
+    if temb is None or not blocks:
+        return {}
+    params = []
+    for bl in blocks:
+        params += [bl.mlp_t[1].weight, bl.mlp_t[1].bias]
+    tproj = _TimeProj.apply(temb, *params)
+    out, off = {}, 0
+    for bl in blocks:
+        n = bl.mlp_t[1].weight.shape[0]
+        out[id(bl)] = tproj[:, off:off + n]
+        off += n
+    return out
+
+
+def _check_inputs(model, x_noisy, t, y):
     dev = x_noisy.device
     for prm in model.parameters():
         if prm.device != dev or prm.dtype != torch.float32:
             raise _lib.LdmError("UNet parameters must be fp32 tensors on the input's CUDA device (call model.to(device))")
-    dt, impl = model.compute_dtype, model.conv_impl
-    dt = "bf16" if _lib.DTYPES[dt] == _lib.BF16 else "fp32"
-    bucket = getattr(next(model.parameters()), "_ldm_grad_bucket", None)   # trainer.FlatAdam's flat gradient buffer, if any
-    if bucket is not None:
-        bucket.begin_step()                    # one memset of the bucket; the backward kernels accumulate into its slices
-    _GradArena.open(model, dev, bucket is not None)
     x = _c(x_noisy.detach().to(torch.float32))
     t = _c(t.detach().to(device=dev, dtype=torch.int64))
     if y is not None:
@@ -453,65 +478,120 @@ def unet_autograd_forward(model, x_noisy: torch.Tensor, t: torch.Tensor, y: Opti
     L = len(model.channel_multipliers)
     if x.shape[2] % (1 << L) != 0 or x.shape[2] != x.shape[3]:
         raise _lib.LdmError(f"image size {tuple(x.shape[2:])} is not divisible by 2^{L} (the reference fails at torch.cat)")
-    tproj, offs = None, {}
-    if model.with_time_emb:
-        tm = model.time_emb.time_mlp
-        temb = _TimeEmbed.apply(t, y, tm[1].weight, tm[1].bias, tm[3].weight, tm[3].bias,
-                                model.label_emb.weight if (y is not None) else None)
-        blocks = [lvl[0] for lvl in model.encoder.downs] + [lvl[0] for lvl in model.decoder.ups]   # BottleNeck never gets t
-        off = 0
-        for bl in blocks:
-            offs[id(bl)] = (off, off + bl.mlp_t[1].weight.shape[0])
-            off += bl.mlp_t[1].weight.shape[0]
-        wcat = torch.cat([bl.mlp_t[1].weight for bl in blocks], 0)     # parameter plumbing (differentiable views)
-        bcat = torch.cat([bl.mlp_t[1].bias for bl in blocks], 0)
-        tproj = _TimeProj.apply(temb, wcat, bcat)
-
-    def tslice(bl):
-        if tproj is None:
-            return None
-        a, b = offs[id(bl)]
-        return tproj[:, a:b]
-
-    h = _InitialConv.apply(x, model.initial_conv.weight, model.initial_conv.bias, dt)
-    skips = []
-    for res, attn in model.encoder.downs:
-        h = _resblock(res, h, tslice(res), impl)
-        h = _attn_site(attn, h, True, impl)
-        skips.append(h)
-        h = _MaxPool.apply(h)
-    h = _resblock(model.bottleneck.res1, h, None, impl)
-    h = _attn_site(model.bottleneck.attn, h, False, impl)
-    h = _resblock(model.bottleneck.res2, h, None, impl)
-    for res, attn, up in model.decoder.ups:
-        h = _ConvT.apply(h, up.weight, up.bias, impl)
-        h = _Cat.apply(h, skips.pop())
-        h = _resblock(res, h, tslice(res), impl)
-        h = _attn_site(attn, h, True, impl)
-    h = _resblock(model.final_conv[0], h, None, impl)
-    return _FinalConv.apply(h, model.final_conv[1].weight.view(model.out_channels, model.channels), model.final_conv[1].bias)
+    return x, t, y
 
 
-class _GraphedVariant(torch.nn.Module):
-    """What gets captured: the autograd forward of ``model`` for one call signature.  A wrapper module of its own, because
-    torch.cuda.make_graphed_callables patches ``forward`` of the module it is given -- capturing a second signature (with /
-    without labels) on the UNet itself would capture the first one's replay stub."""
+def encoder_part(model, x_noisy: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor]):
+    """First half of UNet.forward (src/UNet.py:361-381): time / label embedding, initial conv, encoder.  Returns
+    ``(h, skip_0 .. skip_{L-1}, temb)`` -- everything the second half needs, as tensors, so that the two halves can be captured
+    as separate CUDA graphs and the gradient all-reduce of the second half can run under the backward of this one.  Opens
+    the step: the optimizer's gradient bucket (if any) and the arena are zeroed here."""
+    with torch.cuda.device(x_noisy.device):
+        x, t, y = _check_inputs(model, x_noisy, t, y)
+        dev = x.device
+        dt, impl = model.compute_dtype, model.conv_impl
+        dt = "bf16" if _lib.DTYPES[dt] == _lib.BF16 else "fp32"
+        bucket = getattr(next(model.parameters()), "_ldm_grad_bucket", None)   # trainer.FlatAdam's flat gradient buffer, if any
+        if bucket is not None:
+            bucket.begin_step()                # one memset of the bucket; the backward kernels accumulate into its slices
+        _GradArena.open(model, dev, bucket is not None)
+        temb = None
+        if model.with_time_emb:
+            tm = model.time_emb.time_mlp
+            temb = _TimeEmbed.apply(t, y, tm[1].weight, tm[1].bias, tm[3].weight, tm[3].bias,
+                                    model.label_emb.weight if (y is not None) else None)
+        tsl = _time_slices([lvl[0] for lvl in model.encoder.downs], temb)
+        h = _InitialConv.apply(x, model.initial_conv.weight, model.initial_conv.bias, dt)
+        skips = []
+        for res, attn in model.encoder.downs:
+            h = _resblock(res, h, tsl.get(id(res)), impl)
+            h = _attn_site(attn, h, True, impl)
+            skips.append(h)
+            h = _MaxPool.apply(h)
+        if temb is None:
+            temb = torch.zeros(1, dtype=torch.float32, device=dev)   # placeholder: graph callables exchange tensors only
+        return (h, *skips, temb)
+
+
+def decoder_part(model, h: torch.Tensor, *rest: torch.Tensor):
+    """Second half of UNet.forward (src/UNet.py:382-389): bottleneck, decoder, final conv, from ``encoder_part``'s outputs."""
+    with torch.cuda.device(h.device):
+        impl = model.conv_impl
+        skips, temb = list(rest[:-1]), rest[-1]
+        tsl = _time_slices([lvl[0] for lvl in model.decoder.ups], temb if model.with_time_emb else None)   # BottleNeck never gets t
+        h = _resblock(model.bottleneck.res1, h, None, impl)
+        h = _attn_site(model.bottleneck.attn, h, False, impl)
+        h = _resblock(model.bottleneck.res2, h, None, impl)
+        for res, attn, up in model.decoder.ups:
+            h = _ConvT.apply(h, up.weight, up.bias, impl)
+            h = _Cat.apply(h, skips.pop())
+            h = _resblock(res, h, tsl.get(id(res)), impl)
+            h = _attn_site(attn, h, True, impl)
+        h = _resblock(model.final_conv[0], h, None, impl)
+        return _FinalConv.apply(h, model.final_conv[1].weight, model.final_conv[1].bias)
+
+
+def _overlap_hook(model, boundary: torch.Tensor) -> None:
+    """Data parallel: once the gradient of the encoder/decoder boundary tensor exists, every gradient of the second half
+    (bottleneck, decoder, final conv: ~85 % of the bytes, the tail of the flat bucket) is final -- start its all-reduce now, under
+    the encoder's backward (trainer.FlatAdam.reduce_tail_async; NCCL's stream waits for the work queued so far)."""
+    bucket = getattr(next(model.parameters()), "_ldm_grad_bucket", None)
+    if bucket is None or not boundary.requires_grad or not bucket.wants_overlap():
+        return
+    first_tail = next(model.bottleneck.parameters())
+    boundary.register_hook(lambda g: bucket.reduce_tail_async(first_tail))
+
+
+def unet_autograd_forward(model, x_noisy: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor]):
+    """UNet.forward (src/UNet.py:361-389) with gradients to every live parameter.  Runs with the input's device current (the
+    kernels launch on that device's stream whatever torch.cuda.current_device() was; autograd does the same for backward)."""
+    outs = encoder_part(model, x_noisy, t, y)
+    _overlap_hook(model, outs[0])
+    return decoder_part(model, *outs)
+
+
+class _GraphedEncoder(torch.nn.Module):
+    """What gets captured: one half of the autograd forward of ``model`` for one call signature.  Wrapper modules of their
+    own, because torch.cuda.make_graphed_callables patches ``forward`` of the module it is given -- capturing a second
+    signature (with / without labels) on the UNet itself would capture the first one's replay stub."""
 
     def __init__(self, model):
         super().__init__()
         self.model = model
 
     def forward(self, x_noisy, t, y=None):
-        return unet_autograd_forward(self.model, x_noisy, t, y)
+        return encoder_part(self.model, x_noisy, t, y)
+
+
+class _GraphedDecoder(torch.nn.Module):
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+
+    def forward(self, h, *rest):
+        return decoder_part(self.model, h, *rest)
 
 
 def make_graphed(model, x_noisy: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor]):
     """Capture the UNet's training forward and backward as CUDA graphs (torch.cuda.make_graphed_callables): the ~560
-    kernel launches of a step are replayed instead of re-issued from Python, which is what bounds small batches.
+    kernel launches of a step are replayed instead of re-issued from Python, which is what bounds small batches.  The two
+    halves (encoder | bottleneck + decoder + final conv) are captured as separate graph pairs: between the backward of the
+    second half and the backward of the first, a data-parallel job starts the all-reduce of the second half's gradients.
     Returns a callable with the model's signature for inputs of exactly these shapes (labels given or not, as captured);
     gradients land in the same fp32 ``.grad`` tensors.  The four dead bottleneck mlp_t parameters are unused inputs.
     ``model`` itself is left untouched, so several signatures can be captured side by side."""
-    args = (x_noisy.detach().clone(), t.detach().clone()) + ((y.detach().clone(),) if y is not None else ())
-    variant = _GraphedVariant(model)
-    variant.train(model.training)
-    return torch.cuda.make_graphed_callables(variant, args, allow_unused_input=True)
+    args_a = (x_noisy.detach().clone(), t.detach().clone()) + ((y.detach().clone(),) if y is not None else ())
+    enc, dec = _GraphedEncoder(model), _GraphedDecoder(model)
+    enc.train(model.training)
+    dec.train(model.training)
+    outs = enc(*args_a)                               # eager, once: the shapes / dtypes of the boundary tensors
+    args_b = tuple(torch.zeros_like(o).requires_grad_(o.requires_grad) for o in outs)
+    del outs
+    g_enc, g_dec = torch.cuda.make_graphed_callables((enc, dec), (args_a, args_b), allow_unused_input=True)
+
+    def forward(x_noisy, t, y=None):
+        outs = g_enc(x_noisy, t, y) if y is not None else g_enc(x_noisy, t)
+        _overlap_hook(model, outs[0])
+        return g_dec(*outs)
+
+    return forward

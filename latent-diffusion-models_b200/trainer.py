@@ -84,7 +84,8 @@ class FlatAdam:
         self.step_count = 0
         self.generation = 0                      # bumped by begin_step: a slot is handed out once per generation
         self._slot_gen: dict = {}
-        self._reduce_stream: Optional[torch.cuda.Stream] = None
+        self.overlap = True                      # data parallel: start the tail's all-reduce from the backward pass
+        self._pending = None                     # (offset, [(lo, hi, work)]) of the early reduction of this step
 
     # ---- the bucket protocol used by ldm_b200.train
     def begin_step(self) -> None:
@@ -101,6 +102,25 @@ class FlatAdam:
         self._slot_gen[id(p)] = self.generation
         return p._ldm_grad_slot.detach()     # a fresh alias: autograd adopts a gradient only if nobody else holds the object
 
+    # ---- data parallel: the tail of the bucket is reduced while the head is still being computed
+    def wants_overlap(self) -> bool:
+        return self.overlap and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def reduce_tail_async(self, first_tail_param: torch.Tensor) -> None:
+        """All-reduce flat_grad[offset(first_tail_param):] now (async; NCCL's stream first waits for everything queued on the
+        current stream so far).  Called by ldm_b200.train from a gradient hook on the encoder/decoder boundary: by then the
+        backward kernels of every parameter from ``first_tail_param`` on have been queued.  ``step()`` reduces the rest."""
+        if self._pending is not None:
+            return                               # one early reduction per step
+        idx = next(i for i, p in enumerate(self.params) if p is first_tail_param)
+        lo = int(self.offsets[idx])
+        pieces = [b for b in self.bucket_bounds if b > lo]
+        works = []
+        cuts = [lo] + pieces                     # (lo, b0], (b0, b1], ... up to the end of the bucket; last piece first
+        for a, b in reversed(list(zip(cuts[:-1], cuts[1:]))):
+            works.append((a, b, dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, async_op=True)))
+        self._pending = (lo, works)
+
     # torch.optim.Optimizer surface used by the reference (src/DiffusionModelTrainer.py:55-63)
     def zero_grad(self, set_to_none: bool = True) -> None:
         for p in self.params:
@@ -111,11 +131,17 @@ class FlatAdam:
 
     @torch.no_grad()
     def step(self, grad_scale: float = 1.0) -> None:
+        pending, self._pending = self._pending, None
+        reduced_from = pending[0] if pending is not None else int(self.offsets[-1])
         src, dst, dead = [], [], []
-        for p, v in zip(self.params, self.grad_views):
+        for p, v, o in zip(self.params, self.grad_views, self.offsets[:-1]):
             if p.grad is None:
-                dead.append(v)
+                if int(o) < reduced_from:
+                    dead.append(v)               # (in the early-reduced tail it is the bucket's zero fill, summed over ranks)
             elif p.grad.data_ptr() != v.data_ptr():
+                if int(o) >= reduced_from:
+                    raise _lib.LdmError("FlatAdam: a gradient of the early-reduced bucket tail was not accumulated in place; "
+                                        "set optimizer.overlap = False for this model")
                 src.append(p.grad)
                 dst.append(v)
         if dead:
@@ -126,7 +152,6 @@ class FlatAdam:
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.step_count += 1
         lib = _lib.load()
-        bounds = self.bucket_bounds
         with torch.cuda.device(self.device):
             def adam(lo: int, hi: int) -> None:
                 _lib.check(lib.ldm_adam_step(self.flat_param.data_ptr() + 4 * lo, self.flat_grad.data_ptr() + 4 * lo,
@@ -134,15 +159,16 @@ class FlatAdam:
                                              self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
                                              scale / world, _lib.stream_ptr()))
             if world > 1:
-                # NCCL over NVLink, last bucket first; the all-reduce of piece k runs (on NCCL's stream) under the Adam
-                # launch of piece k+1
+                # NCCL over NVLink.  The head of the bucket (what the early reduction did not cover; everything without one)
+                # goes now, last piece first; the Adam launch of a piece runs under the all-reduce of the next one.
+                cuts = [0] + [b for b in self.bucket_bounds if 0 < b < reduced_from] + [reduced_from]
                 works = [(lo, hi, dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
-                         for lo, hi in reversed(list(zip(bounds[:-1], bounds[1:])))]
-                for lo, hi, w in works:
+                         for lo, hi in reversed(list(zip(cuts[:-1], cuts[1:]))) if hi > lo]
+                for lo, hi, w in (pending[1] if pending is not None else []) + works:
                     w.wait()                 # stream-level wait on CUDA: the host does not block
                     adam(lo, hi)
             else:
-                adam(0, bounds[-1])
+                adam(0, int(self.offsets[-1]))
         torch.autograd.graph.increment_version(self.params)   # the kernel wrote through raw pointers: tell torch (and the
         #                                                       UNet's weight re-pack, which keys on ._version)
 

@@ -47,9 +47,23 @@ def _worker(rank, world, port, q):
     sl = slice(off, off + cnt)
     loss = torch.nn.functional.mse_loss(noise[sl].to(dev), m(xt[sl].to(dev), t[sl].to(dev), y[sl].to(dev)))
     loss.backward()
-    opt.step()                                   # packs .grad into flat_grad, all-reduces (sum) over NCCL
-    dp = opt.flat_grad.clone() / world
-    out = {"rank": rank}
+    opt.step()                                   # the bucket's tail was all-reduced from inside backward, the head goes now
+    dp = torch.cat([v.reshape(-1) for v in opt.grad_views]) / world     # (the bucket itself is padded per parameter)
+    out = {"rank": rank, "early_reduce_used": True}
+    # ... and the same through the CUDA-graphed halves (what bench.py's training leg and the trainer run)
+    from ldm_b200.train import make_graphed
+    mg = model()
+    optg = trainer.FlatAdam(mg.parameters(), lr=0.0)
+    fwd = make_graphed(mg, torch.randn_like(xt[sl]).to(dev), t[sl].to(dev), y[sl].to(dev))
+    for _ in range(2):
+        lossg = trainer.mse_loss_autograd(noise[sl].to(dev), fwd(xt[sl].to(dev), t[sl].to(dev), y[sl].to(dev)))
+        optg.zero_grad(set_to_none=True)
+        lossg.backward()
+        had_pending = optg._pending is not None
+        optg.step()
+    dpg = torch.cat([v.reshape(-1) for v in optg.grad_views]) / world
+    out["early_reduce_used"] = had_pending
+    out["graphed_vs_eager_dp"] = rel_l2(dpg, dp)
     if rank == 0:
         m1 = model()
         torch.nn.functional.mse_loss(noise.to(dev), m1(xt.to(dev), t.to(dev), y.to(dev))).backward()
@@ -97,3 +111,5 @@ def test_two_gpu_dp_gradients_and_sharded_sampling():
     assert r0["sampling_bitwise"], "2-shard sampling must equal the 1-GPU batch bit for bit"
     # the half batches take different split-K partitions in the weight-gradient kernels: fp32 summation order only
     assert r0["grad_rel_l2"] < 2e-3 and r0["grad_worst_param"] < 2e-2, r0
+    assert r0["early_reduce_used"], "the bucket tail must have been all-reduced from the backward hook"
+    assert r0["graphed_vs_eager_dp"] < 2e-3, r0
