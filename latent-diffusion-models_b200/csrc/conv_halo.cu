@@ -17,8 +17,14 @@
 //   * weights: [Cout][K] K-major tiles, one per k-block; when the whole filter fits next to the A ring it is loaded
 //     once per CTA and stays resident (all 32x32 layers of the reference UNet), otherwise it streams through a ring.
 //   * an optional second source (the ResNetBlock 1x1 shortcut, K-concatenated) uses the same slab with the centre tap.
-// Roles (320 threads, persistent, 1 CTA/SM): warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue; TMEM holds
-// two accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Roles (384 threads, persistent, 1 CTA/SM): warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue, warps 10..11
+// operand transform (idle unless the source is normalised on the fly); TMEM holds an accumulator ring so the epilogue of
+// tile i overlaps the MMAs of tile i+1.
+//   * on-the-fly GroupNorm (+SiLU) of the main source (src/UNet.py:52-58: Block = conv(act(norm(x)))): the conv reads the RAW
+//     tensor and, between a slab's TMA landing and its MMAs, the two transform warps rewrite the slab in place as
+//     act(a x + b) with per-(image, channel) {a, b} (k_group_norm_coef).  Rows and columns of the zero padding are left
+//     untouched, so the padding is the normalised tensor's.  A lane always meets the same 8 channels (its 16-byte chunk
+//     index XOR the swizzle phase of its pixel rows, which advance by 8), so the coefficients sit in registers.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -61,13 +67,17 @@ struct HaloParams {
   int a_tx_bytes, w_start; // TMA box bytes, first W coordinate (-1)
   int debug;               // profiling knob (LDM_HALO_DEBUG bit 0: no epilogue memory traffic, bit 1: no MMAs)
   int base_offset_mode;    // experiment knob: 0 = descriptor base_offset 0, 1 = (start >> 7) & 7
+  // on-the-fly GroupNorm (+SiLU) of the main source (ConvArgs::xf_ab): table [images][cin] of {a, b}
+  const float2* xf_ab; int xf_silu; int xf_cin; int x_mod; int H, RB;
   EpiP e;                  // everything the epilogue warps need (conv_epilogue.cuh)
 };
 
 constexpr int HALO_NACC = 4;   // accumulator ring depth (the fused GroupNorm defers its second pass by one tile)
 
+constexpr int HALO_THREADS = 384;
+
 template <int BLOCK_N, int GM = 0>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                  const __grid_constant__ CUtensorMap tmap_b, const HaloParams p) {
   constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
@@ -76,9 +86,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t smem_b = smem_base;
   const uint32_t smem_a = smem_b + p.b_stages * B_TILE_BYTES;
   const uint32_t bars = smem_a + p.a_stages * p.a_stage_bytes;
-  // barrier map: afull[8] aempty[8] bfull[32] bempty[32] tfull[4] tempty[4] | tmem slot
+  // barrier map: afull[8] aempty[8] bfull[32] bempty[32] tfull[4] tempty[4] | tmem slot | xfull[8]
   const uint32_t afull = bars, aempty = bars + 64, bfull = bars + 128, bempty = bars + 384, tfull = bars + 640,
-                 tempty = bars + 672, tmem_slot = bars + 704;
+                 tempty = bars + 672, tmem_slot = bars + 704, xfull = bars + 768;
   float* s_epi = reinterpret_cast<float*>(smem_raw + (bars + 1024 - smem_u32(smem_raw)));   // epilogue staging area
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
@@ -88,7 +98,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_a2);
     prefetch_tmap(&tmap_b);
-    for (int s = 0; s < 8; ++s) { mbar_init(afull + 8 * s, 1); mbar_init(aempty + 8 * s, 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(afull + 8 * s, 1); mbar_init(aempty + 8 * s, 1); mbar_init(xfull + 8 * s, 2); }
     for (int s = 0; s < 32; ++s) { mbar_init(bfull + 8 * s, 1); mbar_init(bempty + 8 * s, 1); }
     for (int i = 0; i < HALO_NACC; ++i) { mbar_init(tfull + 8 * i, 1); mbar_init(tempty + 8 * i, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -112,7 +122,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       const int P = p.P, a_stages = p.a_stages, b_stages = p.b_stages, a_stage_bytes = p.a_stage_bytes;
       const int slabs_main = p.slabs_main, slabs_total = p.slabs_total, num_tiles = p.num_tiles;
-      const int tiles_per_image = p.tiles_per_image, w_start = p.w_start;
+      const int tiles_per_image = p.tiles_per_image, w_start = p.w_start, x_mod = p.x_mod;
       const uint32_t a_tx = (uint32_t)p.a_tx_bytes;
       // packed filter K order is (tap, channel block) for the main source, then the second source's blocks;
       // B slots are filled in CONSUMPTION order (slab-major, taps inside)
@@ -141,7 +151,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const bool main_src = s < slabs_main;
           const int c0 = (main_src ? s : s - slabs_main) * BLOCK_K;
           tma_load_4d(smem_a + astage * a_stage_bytes, main_src ? &tmap_a : &tmap_a2, afull + 8 * astage, c0, w_start,
-                      r0 - 1, n);
+                      r0 - 1, (main_src && x_mod > 0) ? n % x_mod : n);
           if (++astage == a_stages) { astage = 0; aphase ^= 1; }
           if (!resident) {
             for (int t = 0; t < (main_src ? 9 : 1); ++t) {
@@ -165,6 +175,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int slabs_main = p.slabs_main, slabs_total = p.slabs_total, num_tiles = p.num_tiles, n_kb = p.n_kb;
       const int tiles_per_image = p.tiles_per_image;
       const bool issue = !(p.debug & 2);
+      const bool xform = p.xf_ab != nullptr;
       const uint32_t bo_mode = p.base_offset_mode;
       // descriptor-unit (16-byte) displacement of each tap inside the slab: (dy*P + dx) pixel rows of 128 bytes
       int tap_delta[9];
@@ -195,7 +206,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t first_mma = 0u;  // accumulate flag of the very first MMA of the tile
         int kb = 0;
         for (int s = 0; s < slabs_total; ++s) {
-          mbar_wait(afull + 8 * astage, aphase);
+          mbar_wait(((xform && s < slabs_main) ? xfull : afull) + 8 * astage, aphase);
           DBG_STAMP(2);
           tc_fence_after();
           const uint32_t a_addr = smem_a + astage * a_stage_bytes + (uint32_t)off0 * 128u;
@@ -248,9 +259,78 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         DBG_STAMP(3);
       }
     }
-  } else {
+  } else if (warp < 10) {
     // ===================== epilogue (warps 2..9): conv_epilogue.cuh =====================
     conv_epilogue<BLOCK_N, 1, HALO_NACC, true, GM>(p.e, tmem_base, tfull, tempty, s_epi, p.num_tiles);
+  } else if (p.xf_ab != nullptr) {
+    // ===================== operand transform (warps 10..11): slab <- act(a x + b), padding untouched =====================
+    const int P = p.P, a_stages = p.a_stages, a_stage_bytes = p.a_stage_bytes;
+    const int slabs_main = p.slabs_main, slabs_total = p.slabs_total, num_tiles = p.num_tiles;
+    const int tiles_per_image = p.tiles_per_image, H = p.H, W = P - 2, npix = p.RB * P, cin = p.xf_cin;
+    const bool silu = p.xf_silu != 0;
+    const int t2 = threadIdx.x - 320;              // 0..63
+    const int chunk = t2 & 7, pl = t2 >> 3;        // physical 16-byte chunk of the pixel row; pixel rows pl, pl + 8, ...
+    const int lch = (chunk ^ pl) * 8;              // logical channels of that chunk: the swizzle phase of row i is i & 7 == pl
+    int astage = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n = tile / tiles_per_image;
+      const int q0 = P + (tile - n * tiles_per_image) * TILE_M;
+      const int lo = q0 - P - 1;
+      const int r0 = lo >= 0 ? lo / P : -1;
+      for (int s = 0; s < slabs_total; ++s) {
+        if (s < slabs_main) {
+          float2 ab[8];                            // issued before the wait: the table reads overlap the slab's TMA
+          const float2* abp = p.xf_ab + (int64_t)n * cin + s * BLOCK_K + lch;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ab[i] = __ldg(abp + i);
+          mbar_wait(afull + 8 * astage, aphase);
+          const uint32_t base = smem_a + astage * a_stage_bytes + chunk * 16;
+          // pixel i = row * P + col of the box = image row r0 - 1 + row, column col - 1.  Four pixel rows (i, i + 8, i + 16,
+          // i + 24) per step: their loads are issued together and the four dependent chains interleave.
+          int row = 0, col = pl;
+          for (int i0 = pl; i0 < ((p.debug & 8) ? 0 : npix); i0 += 32) {
+            uint32_t wv[4][4];
+            bool ok[4];
+            int rr = row, cc = col;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int hh = r0 - 1 + rr;
+              ok[u] = i0 + 8 * u < npix && (unsigned)hh < (unsigned)H && cc >= 1 && cc <= W;
+              if (ok[u])
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(wv[u][0]), "=r"(wv[u][1]), "=r"(wv[u][2]), "=r"(wv[u][3]) : "r"(base + (i0 + 8 * u) * 128));
+              cc += 8;
+              while (cc >= P) { cc -= P; ++rr; }
+            }
+            row = rr; col = cc;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (!ok[u]) continue;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float v0 = fmaf(__uint_as_float(wv[u][k] << 16), ab[2 * k].x, ab[2 * k].y);
+                float v1 = fmaf(__uint_as_float(wv[u][k] & 0xffff0000u), ab[2 * k + 1].x, ab[2 * k + 1].y);
+                if (silu && !(p.debug & 16)) {     // {a, b} are pre-halved: silu(v) = v/2 (1 + tanh(v/2))
+                  float t0, t1;
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(v0));
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(v1));
+                  v0 = fmaf(v0, t0, v0);
+                  v1 = fmaf(v1, t1, v1);
+                }
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                wv[u][k] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + (i0 + 8 * u) * 128), "r"(wv[u][0]), "r"(wv[u][1]),
+                           "r"(wv[u][2]), "r"(wv[u][3]) : "memory");
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> the MMA's async proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive(xfull + 8 * astage);
+        }
+        if (++astage == a_stages) { astage = 0; aphase ^= 1; }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -287,6 +367,8 @@ int halo_init() {
   inited[dev & 63] = true;
   return 0;
 }
+
+inline bool P_ok_for_xform(int P) { return P >= 8; }   // the transform's row/column walk advances 8 pixels per step
 
 int make_slab_map(CUtensorMap* map, const void* x, int ld, int cin, int B, int H, int W, int P, int RB) {
   cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -362,6 +444,9 @@ int k_conv_halo(const ConvArgs& a, cudaStream_t st) {
   p.n_kb = 9 * p.slabs_main + (p.slabs_total - p.slabs_main);
   p.a_stage_bytes = (RB * p.P * 128 + 1023) / 1024 * 1024;
   p.base_offset_mode = g_base_offset_mode;
+  p.xf_ab = (const float2*)a.xf_ab; p.xf_silu = a.xf_silu; p.xf_cin = a.cin; p.x_mod = a.x_mod; p.H = H; p.RB = RB;
+  LDM_REQUIRE(!a.xf_ab || P_ok_for_xform(p.P), "conv_halo: the operand transform needs P <= 8 * 32");
+  LDM_REQUIRE(a.x_mod == 0 || a.batch % a.x_mod == 0, "conv_halo: x_mod must divide the batch");
   { const char* d = getenv("LDM_HALO_DEBUG"); p.debug = d ? atoi(d) : 0; }
   p.a_tx_bytes = RB * p.P * 128; p.w_start = -1;
   {
@@ -417,7 +502,7 @@ int k_conv_halo(const ConvArgs& a, cudaStream_t st) {
   LDM_REQUIRE(p.a_stages >= 2, "conv_halo: shared memory plan failed (cout %d, %d k-blocks)", a.cout, p.n_kb);
   const int smem = p.b_stages * b_tile + p.a_stages * p.a_stage_bytes + fixed;
   CUtensorMap ma, ma2, mb;
-  if (int rc = make_slab_map(&ma, a.x, a.ldx, a.cin, a.batch, a.height, a.width, p.P, RB)) return rc;
+  if (int rc = make_slab_map(&ma, a.x, a.ldx, a.cin, a.x_mod > 0 ? a.x_mod : a.batch, a.height, a.width, p.P, RB)) return rc;
   if (a.x2) {
     if (int rc = make_slab_map(&ma2, a.x2, a.ldx2, a.cin2, a.batch, a.height, a.width, p.P, RB)) return rc;
   } else {
@@ -425,7 +510,7 @@ int k_conv_halo(const ConvArgs& a, cudaStream_t st) {
   }
   if (int rc = make_filter_map(&mb, a.w, a.cout, p.n_kb * BLOCK_K, a.cout)) return rc;
   const int grid = p.num_tiles < g_num_sms_h ? p.num_tiles : g_num_sms_h;
-#define HALO_GO(BN, GMV) LDM_CUDA(ldm_launch_pdl(conv_halo_kernel<BN, GMV>, dim3(grid), dim3(320), (size_t)smem, st, ma, ma2, mb, p))
+#define HALO_GO(BN, GMV) LDM_CUDA(ldm_launch_pdl(conv_halo_kernel<BN, GMV>, dim3(grid), dim3(HALO_THREADS), (size_t)smem, st, ma, ma2, mb, p))
   if (a.cout == 64) {
     if (e.gn_mode == 0) HALO_GO(64, 0); else if (e.gn_mode == 1) HALO_GO(64, 1); else HALO_GO(64, 2);
   } else {

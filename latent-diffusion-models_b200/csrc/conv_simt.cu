@@ -170,8 +170,10 @@ int k_conv_simt(const ConvArgs& a, cudaStream_t st) {
 int k_conv(const ConvArgs& a, int impl, cudaStream_t st) {
   if (a.dtype == LDM_DT_BF16 && impl == 0) {
     if (k_conv_halo_applicable(a)) return k_conv_halo(a, st);
+    LDM_REQUIRE(!a.xf_ab && a.x_mod == 0, "conv: the on-the-fly source GroupNorm / x_mod exist only in the halo kernel");
     return k_conv_tc(a, st);
   }
+  LDM_REQUIRE(!a.xf_ab && a.x_mod == 0, "conv: the on-the-fly source GroupNorm / x_mod exist only in the halo kernel");
   LDM_REQUIRE(a.gn.mode == 0, "conv: the fused GroupNorm epilogue exists only in the tcgen05 kernels (bf16, impl 0)");
   return k_conv_simt(a, st);
 }

@@ -752,6 +752,69 @@ int k_group_norm_apply_raw(const void* x, int ldx, void* y, int ldy, const void*
   return 0;
 }
 
+// Per-(sample, channel) affine form of GroupNorm for a consumer that normalises on the fly (conv_halo.cu's transform warps):
+// the statistics are combined exactly as gn_apply_kernel does (same order, same precision).
+__global__ void __launch_bounds__(256)
+gn_coef_kernel(const float2* __restrict__ part, int splits, const float* __restrict__ gamma, const float* __restrict__ beta,
+               const float* __restrict__ rowvec, int ld_rowvec, int HW, int C, int G, float eps, int x_mod, int rows,
+               const bf16* __restrict__ x, int ldx, int silu, float2* __restrict__ ab) {
+  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  pdl_wait();
+  pdl_trigger();
+  const int n = blockIdx.x;
+  const int cpg = C / G;
+  if ((int)threadIdx.x < G && splits < 0) {
+    const int gg = threadIdx.x, ns = -splits;
+    const int nv = x_mod > 0 ? rows / x_mod : 1, img = x_mod > 0 ? n % x_mod : n, kk = x_mod > 0 ? n / x_mod : 0;
+    double a = 0.0, b = 0.0;
+    for (int sp = 0; sp < ns; ++sp) {
+      const float2 v = part[(((int64_t)img * G + gg) * nv + kk) * ns + sp];
+      a += (double)v.x; b += (double)v.y;
+    }
+    const double cnt = (double)HW * (double)cpg;
+    const double m1 = a / cnt;
+    double var = b / cnt - m1 * m1;
+    if (var < 0.0) var = 0.0;
+    s_mean[gg] = (float)m1;
+    s_rstd[gg] = (float)(1.0 / sqrt(var + (double)eps));
+  } else if ((int)threadIdx.x < G) {
+    const int gg = threadIdx.x;
+    float a = 0.f, b = 0.f;
+    for (int sp = 0; sp < splits; ++sp) {  // fixed order
+      const float2 v = part[((int64_t)n * splits + sp) * G + gg];
+      a += v.x; b += v.y;
+    }
+    const int c_first = gg * cpg;
+    const bf16* xs = x + (int64_t)(x_mod > 0 ? n % x_mod : n) * HW * ldx;
+    const float K = __bfloat162float(xs[c_first]) + (rowvec ? rowvec[(int64_t)n * ld_rowvec + c_first] : 0.f);
+    const float inv_n = 1.0f / ((float)HW * (float)cpg);
+    const float m1 = a * inv_n;
+    const float var = fmaxf(b * inv_n - m1 * m1, 0.f);
+    s_mean[gg] = K + m1;
+    s_rstd[gg] = 1.0f / sqrtf(var + eps);
+  }
+  __syncthreads();
+  const float h = silu ? 0.5f : 1.0f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float a = gamma[c] * s_rstd[g];
+    const float rvi = rowvec ? rowvec[(int64_t)n * ld_rowvec + c] : 0.f;
+    const float b = beta[c] + (rvi - s_mean[g]) * a;
+    ab[(int64_t)n * C + c] = make_float2(h * a, h * b);
+  }
+}
+int k_group_norm_coef(const void* part, int nslots, const float* gamma, const float* beta, const float* rowvec, int ld_rowvec,
+                      int rows, int hw, int channels, int groups, float eps, int x_mod, const void* x, int ldx, int silu,
+                      void* ab_out, cudaStream_t st) {
+  LDM_REQUIRE(part && nslots != 0 && gamma && beta && ab_out && channels % groups == 0 && groups <= GN_MAX_GROUPS &&
+                  (nslots < 0 || x) && (x_mod == 0 || rows % x_mod == 0), "group_norm_coef: unsupported arguments");
+  if (rows == 0) return 0;
+  LDM_CUDA(ldm_launch_pdl(gn_coef_kernel, dim3(rows), dim3(256), 0, st, (const float2*)part, nslots, gamma, beta, rowvec, ld_rowvec, hw,
+                          channels, groups, eps, x_mod, rows, (const bf16*)x, ldx, silu, (float2*)ab_out));
+  LDM_LAUNCHED("gn_coef");
+  return 0;
+}
+
 // max-pool 2x2 of x [B, H, W, ldx] (C channels) -> pool [B, H/2, W/2, ldp] and y = [silu](GroupNorm(pool)) [B, H/2, W/2, ldy]
 bool k_pool_group_norm_applicable(int H, int W, int C, int groups, int dtype) {
   if (dtype != LDM_DT_BF16 || H % 2 || W % 2 || C % 8 || groups < 1 || groups > GN_MAX_GROUPS) return false;

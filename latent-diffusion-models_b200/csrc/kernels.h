@@ -148,6 +148,10 @@ struct ConvArgs {
   float* fin_out = nullptr;
   int fin_cout = 0;
   int res_mod = 0;                        // > 0: the residual of image n is read from image n % res_mod (halo kernel only)
+  // GroupNorm (+SiLU) of the MAIN SOURCE applied on the fly (halo kernel only): x is the RAW tensor and xf_ab [batch][cin] holds
+  // per-(output image, channel) {a, b} from k_group_norm_coef; a transform warp pair rewrites each slab in shared memory as
+  // act(a x + b) between its TMA landing and the MMAs (padding stays zero).  x_mod > 0: image n is read from image n % x_mod.
+  const void* xf_ab = nullptr; int xf_silu = 0; int x_mod = 0;
   ConvGn gn;                              // fused GroupNorm epilogue (tcgen05 kernels only)
   int cout;                               // GEMM N (for up2: 4 * output channels)
   int batch, height, width;
@@ -163,6 +167,12 @@ int k_conv_halo_prepare();
 bool k_conv_halo_applicable(const ConvArgs& a);
 int k_conv_halo(const ConvArgs& a, cudaStream_t st);
 int k_conv(const ConvArgs& a, int impl, cudaStream_t st);
+// {a, b} [rows][channels] (float2) with act(a x + b) == [SiLU](GroupNorm(x + rowvec)) for the statistics in `part`
+// (nslots < 0: raw {S, Q} slots of a convolution epilogue, ConvGn mode 1; > 0: pivoted partial sums of k_group_norm_stats,
+// pivot read from x).  silu: the pair is pre-halved for the tanh form of SiLU used by the halo kernel's transform warps.
+int k_group_norm_coef(const void* part, int nslots, const float* gamma, const float* beta, const float* rowvec, int ld_rowvec,
+                      int rows, int hw, int channels, int groups, float eps, int x_mod, const void* x, int ldx, int silu,
+                      void* ab_out, cudaStream_t st);
 
 // weight packing (pack.cu)
 int k_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, const float* w2_oi11, int cin2,

@@ -200,7 +200,7 @@ int64_t layout_all(ldm_unet* h, uint8_t* base) {
 
 // workspace plan for one forward of `batch` rows
 struct Plan {
-  int64_t temb, tproj, temb_tab, tproj_tab, gnws, gnpk, gnpk_bytes, gnst, gnst_bytes, gnst2, gnst2_bytes, laflag, qkv, s[4], total;
+  int64_t temb, tproj, temb_tab, tproj_tab, gnws, gnpk, gnpk_bytes, gnst, gnst_bytes, gnst2, gnst2_bytes, laflag, gnab, qkv, s[4], total;
   std::vector<int64_t> hin;  // [L+1]
   std::vector<int64_t> cat;  // [L]
 };
@@ -226,6 +226,7 @@ Plan make_plan(const ldm_unet* h, int batch) {
   p.gnst2_bytes = (int64_t)batch * std::max<int64_t>(64, (int64_t)S * S / 16) * 8;
   p.gnst2 = take(p.gnst2_bytes);
   p.laflag = take((int64_t)batch * 4);   // per-sample "redo with the exact kernel" flags of linattn_tc2_kernel
+  p.gnab = take((int64_t)batch * 1024 * 8);   // {a, b} per (image, channel) of a GroupNorm applied inside the consuming conv
   int64_t max_elems = 0;
   for (int i = 0; i < L; ++i) {
     int64_t R = S >> i;
@@ -503,6 +504,21 @@ struct Fwd {
   Prof* prof = nullptr;
   cudaEvent_t join_event = nullptr;  // side-stream time embedding: waited for right before its first consumer
   int res_mod = 0;                   // residual row aliasing for the next conv (shared CFG prefix)
+  const void* xf_ab = nullptr; int xf_silu = 0; int xf_x_mod = 0;   // on-the-fly source GroupNorm of the next conv (one-shot)
+  // A ResNetBlock's second GroupNorm (+SiLU, + time row) applied INSIDE the conv that consumes it (conv_halo.cu's transform
+  // warps) instead of by an apply kernel: conv1's epilogue leaves the statistics, k_group_norm_coef turns them into per-image
+  // {a, b}, conv2 reads conv1's RAW output.  Only where conv2 runs in the halo kernel (3x3, Cout 64 / 128 at 32x32).
+  bool xform_ok(int R, int cin, int cout) const {
+    // Opt-in (LDM_CONV_XFORM=1): measured slower than the apply kernel it removes -- 94.8 -> 166 us for the 64->64 conv at
+    // 32x32 x 512 rows against a 35 us apply kernel (synchronisation alone +2 us, load / FMA / store pass +39 us, tanh +33 us);
+    // the two transform warps are mostly WAITING in the profile, i.e. their shared-memory traffic slows the tensor pipe's
+    // operand reads rather than being the critical path itself (profiles/README.md, finding 19).
+    static const bool on = getenv("LDM_CONV_XFORM") != nullptr && atoi(getenv("LDM_CONV_XFORM")) != 0;
+    if (!on || dt != LDM_DT_BF16 || impl != 0 || cin > 1024) return false;
+    ConvArgs a{};
+    a.dtype = dt; a.ksize = 3; a.up2 = 0; a.cout = cout; a.cin = cin; a.x2 = nullptr; a.cin2 = 0; a.height = R; a.width = R;
+    return k_conv_halo_applicable(a);
+  }
   // GroupNorm fused into the producing convolution (conv_epilogue.cuh)
   bool fuse_gn = false;
   unsigned gn_tag = 0;               // packets: one tag per launch since the per-forward memset
@@ -574,6 +590,8 @@ struct Fwd {
     a.x = x; a.ldx = ldx; a.cin = cin; a.x2 = x2; a.ldx2 = ldx2; a.cin2 = cin2; a.w = w; a.bias = bias;
     a.rowvec = rowvec; a.ld_rowvec = ldrv; a.res = res; a.ldres = ldres; a.y = y; a.ldy = ldy; a.cout = cout;
     a.batch = B; a.height = R; a.width = R; a.ksize = ksize; a.up2 = up2; a.dtype = dt; a.res_mod = res_mod;
+    a.xf_ab = xf_ab; a.xf_silu = xf_silu; a.x_mod = xf_x_mod;
+    xf_ab = nullptr; xf_silu = 0; xf_x_mod = 0;      // one-shot: set by the caller right before the conv that consumes them
     if (y == nullptr) { a.fin_w = fin_w; a.fin_b = fin_b; a.fin_out = fin_out; a.fin_cout = fin_cout; }
     return conv_args(a);
   }
@@ -612,6 +630,18 @@ struct Fwd {
         ConvGn g1 = gn_stats8(rvm, h->tproj_total, full / x_rows, x_rows, &ns);
         RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3, 0, &g1));
         B = full;
+        if (xform_ok(R, r.cout, r.cout)) {
+          // block2's GroupNorm + SiLU ride in conv2's operand path: every output image n reads raw image n % x_rows
+          PROF(LDM_FAM_GROUP_NORM, 0, (double)B * r.cout * 8,
+               k_group_norm_coef(ws + plan.gnst, -ns, r.g2, r.be2, rvm, h->tproj_total, B, R * R, r.cout, 8, GN_EPS, x_rows, nullptr, 0, 1,
+                                 ws + plan.gnab, st));
+          res_mod = x_rows;
+          xf_ab = ws + plan.gnab; xf_silu = 1; xf_x_mod = x_rows;
+          ConvGn gsx = gn_stats();
+          int rcx = conv(s(1), r.cout, r.cout, nullptr, 0, 0, r.w2, r.b2, nullptr, 0, x, ldx, out, ldo, r.cout, R, 3, 0, stats ? &gsx : nullptr);
+          res_mod = 0;
+          return rcx;
+        }
         PROF(LDM_FAM_GROUP_NORM, 0, (double)B * R * R * r.cout * es * 2,
              k_group_norm_apply_raw(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, rvm, h->tproj_total, B, R * R, r.cout, 8, GN_EPS, 1,
                                     ws + plan.gnst, ns, x_rows, st));
@@ -661,6 +691,7 @@ struct Fwd {
       join_event = nullptr;
     }
     const void* h2 = s(0);
+    bool xf_pending = false;
     if (gn_norm_ok(R)) {
       // block2's GroupNorm + SiLU in conv1's epilogue: conv1's raw output never exists in memory
       ConvGn g2 = gn_norm(r.g2, r.be2, 8, 1, rv, h->tproj_total, nullptr, 0);
@@ -671,6 +702,14 @@ struct Fwd {
       int ns = 0;
       ConvGn g1 = gn_stats8(rv, h->tproj_total, 1, 0, &ns);
       RC(conv(s(0), r.cin, r.cin, nullptr, 0, 0, r.w1, r.b1, nullptr, 0, nullptr, 0, s(1), r.cout, r.cout, R, 3, 0, &g1));
+      if (xform_ok(R, r.cout, r.cout)) {
+        // block2's GroupNorm + SiLU ride in conv2's operand path (conv2 reads conv1's raw output)
+        PROF(LDM_FAM_GROUP_NORM, 0, (double)B * r.cout * 8,
+             k_group_norm_coef(ws + plan.gnst, -ns, r.g2, r.be2, rv, h->tproj_total, B, R * R, r.cout, 8, GN_EPS, 0, nullptr, 0, 1,
+                               ws + plan.gnab, st));
+        h2 = s(1);
+        xf_pending = true;
+      } else
       PROF(LDM_FAM_GROUP_NORM, 0, (double)B * R * R * r.cout * es * 2,
            k_group_norm_apply_raw(s(1), r.cout, s(0), r.cout, nullptr, 0, r.g2, r.be2, rv, h->tproj_total, B, R * R, r.cout, 8, GN_EPS, 1,
                                   ws + plan.gnst, ns, 0, st));
@@ -680,6 +719,7 @@ struct Fwd {
     }
     ConvGn gs = gn_stats();
     const ConvGn* gsp = (stats && out != nullptr) ? &gs : nullptr;
+    if (xf_pending) { xf_ab = ws + plan.gnab; xf_silu = 1; xf_x_mod = 0; }
     if (r.has_sc)  // 1x1 shortcut conv K-concatenated into the second 3x3 GEMM
       RC(conv(h2, r.cout, r.cout, x, ldx, r.cin, r.w2, r.b2, nullptr, 0, nullptr, 0, out, ldo, r.cout, R, 3, 0, gsp));
     else           // identity shortcut added in the epilogue
