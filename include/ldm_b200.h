@@ -106,6 +106,7 @@ enum ldm_kernel_family {
   LDM_FAM_ATTENTION = 4,
   LDM_FAM_OTHER = 5,            /* time-embedding MLPs, initial/final conv, max-pool              */
   LDM_FAM_CONV_TC_1X1 = 6,      /* tcgen05 1x1 convolutions and conv-transpose: K <= 768, HBM bound */
+  LDM_FAM_CONV_HALO = 7,        /* the 3x3 convolutions that run in conv_halo_kernel (full resolution)     */
   LDM_FAM_COUNT = 8
 };
 typedef struct ldm_profile_family {

@@ -39,7 +39,7 @@ class Profile(C.Structure):
     _fields_ = [("family", ProfileFamily * 8)]
 
 
-FAMILIES = ["conv_tc", "conv_ffma", "group_norm", "linear_attention", "attention", "other", "conv_tc_1x1"]
+FAMILIES = ["conv_tc", "conv_ffma", "group_norm", "linear_attention", "attention", "other", "conv_tc_1x1", "conv_halo"]
 
 # name -> (restype, argtypes); mirrors include/ldm_b200.h one to one
 SIGNATURES = {

@@ -599,7 +599,8 @@ struct Fwd {
     const double M = (double)a.batch * a.height * a.width, K = (double)a.ksize * a.ksize * a.cin + a.cin2;
     const double bytes = (M * (a.cin + a.cin2) + (double)a.cout * K + M * a.cout + (a.res ? M * a.cout : 0)) * es;
     const bool tc = dt == LDM_DT_BF16 && impl == 0;
-    PROF(tc ? (a.ksize == 3 ? LDM_FAM_CONV_TC : LDM_FAM_CONV_TC_1X1) : LDM_FAM_CONV_FFMA, 2.0 * M * a.cout * K, bytes,
+    PROF(tc ? (a.ksize == 3 ? (k_conv_halo_applicable(a) ? LDM_FAM_CONV_HALO : LDM_FAM_CONV_TC) : LDM_FAM_CONV_TC_1X1) : LDM_FAM_CONV_FFMA,
+         2.0 * M * a.cout * K, bytes,
          k_conv(a, impl, st));
     return 0;
   }
