@@ -310,6 +310,12 @@ __device__ __forceinline__ void conv_epilogue(const EpiP& p, const uint32_t tmem
             for (int j = 0; j < 4; ++j) rn[j] = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + 32) + j);
           }
           tmem_ld_wait();
+          if (!mode2 && (sub == MT - 1 || (!HALO && unit_um(unit) * MT + sub + 1 >= num_m_tiles)) && c0 + 32 >= COLS) {
+            // last read of this unit's accumulator: hand the TMEM buffer back NOW, before the arithmetic and the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_relaxed(tempty_bar + 8 * acc);
+          }
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -426,12 +432,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiP& p, const uint32_t tmem
           epi_bar();  // fx is rewritten by the next sub-tile
         }
       }   // sub-tiles
-      if (!mode2) {
-        // the accumulator has been read: hand the TMEM buffer back before any statistics bookkeeping
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_relaxed(tempty_bar + 8 * acc);
-      }
+      // (!mode2: the TMEM buffer was handed back right after its last read, above)
       if (mode2) {
         epi_bar();   // s_red complete
         // canonical partial sums: fp32 over (statistics unit) x (column block), in (row segment, 8-column block) order
