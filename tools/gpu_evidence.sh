@@ -16,6 +16,6 @@ ncu -i gpurun_out/tmp_halo.ncu-rep --page raw --csv > gpurun_out/r02_ncu_full_co
 timeout 900 ncu --set full --clock-control none -k regex:"linattn_tc2" -s 3 -c 1 -o gpurun_out/tmp_la -f python tools/one_pass.py 512 2 > gpurun_out/ncu_full2.log 2>&1; echo "rc=$?"
 ncu -i gpurun_out/tmp_la.ncu-rep --page raw --csv > gpurun_out/r02_ncu_full_linattn_tc.csv 2>/dev/null; rm -f gpurun_out/tmp_la.ncu-rep
 echo "=== skip-family timing (true in-graph cost per family)"
-for m in 0 4 8 64 32 1; do LDM_SKIP_FAM=$m timeout 300 python bench.py --steps 1 --warmup 2 --no-train --no-cpu-baseline --no-variants --n-steps 400 2> gpurun_out/bench.err | python -c "
+for m in 0 4 8 64 32 128 1; do LDM_SKIP_FAM=$m LDM_BENCH_ALLOW_NONFINITE=1 timeout 300 python bench.py --steps 1 --warmup 2 --no-train --no-cpu-baseline --no-variants --n-steps 400 2> gpurun_out/bench.err | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('LDM_SKIP_FAM=$m ms/timestep', round(d['ms_per_step']/400, 4))"; done | tee gpurun_out/r02_skip_family_ms.txt
 du -sh gpurun_out
