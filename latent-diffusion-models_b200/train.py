@@ -481,11 +481,28 @@ def _check_inputs(model, x_noisy, t, y):
     return x, t, y
 
 
+def _split_levels(model) -> int:
+    """Encoder levels that belong to the FIRST half.  The cut sits after level 1 (of 4): the first half's backward (the two
+    full-resolution levels: most of the encoder's time, 3 % of the parameters) then covers the all-reduce of everything
+    else, and what is left to reduce after backward is small.  LDM_TRAIN_SPLIT overrides (0 .. number of levels)."""
+    import os
+    L = len(model.encoder.downs)
+    v = os.environ.get("LDM_TRAIN_SPLIT")
+    return max(0, min(L, int(v))) if v is not None else min(2, L)
+
+
+def _first_tail_param(model) -> torch.Tensor:
+    k = _split_levels(model)
+    if k < len(model.encoder.downs):
+        return next(model.encoder.downs[k][0].parameters())
+    return next(model.bottleneck.parameters())
+
+
 def encoder_part(model, x_noisy: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor]):
-    """First half of UNet.forward (src/UNet.py:361-381): time / label embedding, initial conv, encoder.  Returns
-    ``(h, skip_0 .. skip_{L-1}, temb)`` -- everything the second half needs, as tensors, so that the two halves can be captured
-    as separate CUDA graphs and the gradient all-reduce of the second half can run under the backward of this one.  Opens
-    the step: the optimizer's gradient bucket (if any) and the arena are zeroed here."""
+    """First half of UNet.forward (src/UNet.py:361-381): time / label embedding, initial conv, the first encoder levels.
+    Returns ``(h, skip_0 .. skip_{k-1}, temb)`` -- everything the second half needs, as tensors, so that the two halves can be
+    captured as separate CUDA graphs and the gradient all-reduce of the second half can run under the backward of this one.
+    Opens the step: the optimizer's gradient bucket (if any) and the arena are zeroed here."""
     with torch.cuda.device(x_noisy.device):
         x, t, y = _check_inputs(model, x_noisy, t, y)
         dev = x.device
@@ -500,10 +517,11 @@ def encoder_part(model, x_noisy: torch.Tensor, t: torch.Tensor, y: Optional[torc
             tm = model.time_emb.time_mlp
             temb = _TimeEmbed.apply(t, y, tm[1].weight, tm[1].bias, tm[3].weight, tm[3].bias,
                                     model.label_emb.weight if (y is not None) else None)
-        tsl = _time_slices([lvl[0] for lvl in model.encoder.downs], temb)
+        levels = list(model.encoder.downs)[:_split_levels(model)]
+        tsl = _time_slices([lvl[0] for lvl in levels], temb)
         h = _InitialConv.apply(x, model.initial_conv.weight, model.initial_conv.bias, dt)
         skips = []
-        for res, attn in model.encoder.downs:
+        for res, attn in levels:
             h = _resblock(res, h, tsl.get(id(res)), impl)
             h = _attn_site(attn, h, True, impl)
             skips.append(h)
@@ -514,11 +532,19 @@ def encoder_part(model, x_noisy: torch.Tensor, t: torch.Tensor, y: Optional[torc
 
 
 def decoder_part(model, h: torch.Tensor, *rest: torch.Tensor):
-    """Second half of UNet.forward (src/UNet.py:382-389): bottleneck, decoder, final conv, from ``encoder_part``'s outputs."""
+    """Second half of UNet.forward (src/UNet.py:376-389): the remaining encoder levels, bottleneck, decoder, final conv, from
+    ``encoder_part``'s outputs."""
     with torch.cuda.device(h.device):
         impl = model.conv_impl
         skips, temb = list(rest[:-1]), rest[-1]
-        tsl = _time_slices([lvl[0] for lvl in model.decoder.ups], temb if model.with_time_emb else None)   # BottleNeck never gets t
+        levels = list(model.encoder.downs)[_split_levels(model):]
+        tsl = _time_slices([lvl[0] for lvl in levels] + [lvl[0] for lvl in model.decoder.ups],
+                           temb if model.with_time_emb else None)   # BottleNeck never gets t
+        for res, attn in levels:
+            h = _resblock(res, h, tsl.get(id(res)), impl)
+            h = _attn_site(attn, h, True, impl)
+            skips.append(h)
+            h = _MaxPool.apply(h)
         h = _resblock(model.bottleneck.res1, h, None, impl)
         h = _attn_site(model.bottleneck.attn, h, False, impl)
         h = _resblock(model.bottleneck.res2, h, None, impl)
@@ -532,13 +558,13 @@ def decoder_part(model, h: torch.Tensor, *rest: torch.Tensor):
 
 
 def _overlap_hook(model, boundary: torch.Tensor) -> None:
-    """Data parallel: once the gradient of the encoder/decoder boundary tensor exists, every gradient of the second half
-    (bottleneck, decoder, final conv: ~85 % of the bytes, the tail of the flat bucket) is final -- start its all-reduce now, under
-    the encoder's backward (trainer.FlatAdam.reduce_tail_async; NCCL's stream waits for the work queued so far)."""
+    """Data parallel: once the gradient of the boundary tensor exists, every gradient of the second half (encoder levels 2+,
+    bottleneck, decoder, final conv: 97 % of the bytes, the tail of the flat bucket) is final -- start its all-reduce now, under
+    the first half's backward (trainer.FlatAdam.reduce_tail_async; NCCL's stream waits for the work queued so far)."""
     bucket = getattr(next(model.parameters()), "_ldm_grad_bucket", None)
     if bucket is None or not boundary.requires_grad or not bucket.wants_overlap():
         return
-    first_tail = next(model.bottleneck.parameters())
+    first_tail = _first_tail_param(model)
     boundary.register_hook(lambda g: bucket.reduce_tail_async(first_tail))
 
 

@@ -45,7 +45,7 @@ class FlatAdam:
     ALIGN = 64   # elements: 256 bytes (the weight-gradient kernel reduces with 16-byte vector atomics)
 
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 n_buckets: int = 4):
+                 n_buckets: int = 3):
         self.params: List[torch.nn.Parameter] = [p for p in params]
         if not self.params:
             raise ValueError("FlatAdam: no parameters")
