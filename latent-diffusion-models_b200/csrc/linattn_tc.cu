@@ -556,8 +556,12 @@ linattn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 //     a logit leaves +-88 of its reference -- the sample's y then contains inf / NaN, which the GroupNorm partial sums of the
 //     store step see for free: the sample is flagged and linattn_tc_kernel (exact two-pass softmax) recomputes it right after
 //     (a launch that returns at once when nothing is flagged).
-//   * 16 epilogue warps (TMEM lane quarter x 32-column slice), K / Q accumulators double buffered in TMEM, P / softmax(Q)
-//     double buffered in shared memory, x tiles through a 4-deep TMA ring: projection t+2 is queued while step t is consumed.
+//   * the K projection is issued transposed (W_k X_t^T: lanes = channels, columns = tokens), so P^T goes straight back into
+//     tensor memory as the A operand of the G GEMM (tcgen05.st; no shared-memory round trip, and that GEMM reads only [X | 1] from
+//     shared memory: the SS form executed in ~106 cycles per MMA on operand fetch alone); the token-0 shift is a per-lane scalar.
+//   * 16 epilogue warps in two groups (TMEM lane quarter x 64-column half; each group owns the tiles of one parity), K / Q
+//     accumulators double buffered in TMEM, softmax(Q) double buffered in shared memory, x tiles through a 4-deep TMA ring:
+//     projection t+2 is queued as soon as the accumulator of step t has been read.
 // Work per 128-token tile: K proj (N=128) -> P step -> G, Z;   Q proj (N=128) -> S step -> Y (N=64) -> store step.
 constexpr uint32_t L2_XS = 4;                    // x ring depth
 constexpr uint32_t L2_X = 0;                     // 4 x [128 tok][64 ch] K-major SW128 (TMA)
@@ -574,6 +578,7 @@ constexpr uint32_t LA2_SMEM = L2_F + (128 + 256 + 128) * 4 + 1024;
 static_assert(LA2_SMEM <= 227 * 1024, "shared memory plan exceeds 227 KB");
 constexpr uint32_t T2_ACC = 0;                   // K / Q accumulators: [0,128) and [128,256)
 constexpr uint32_t T2_G = 256, T2_Z = 320;       // G [256,320), Z [320,336)
+constexpr uint32_t T2_PT = 352;                  // P^T of the two groups, bf16 pairs: [352,416) and [416,480) (K pass only)
 constexpr uint32_t T2_M = 256;                   // M accumulators [256,512) (G and Z have been read by then)
 constexpr uint32_t T2_Y = 256;                   // Y accumulators [256,320) and [320,384) (M has been read by then)
 
@@ -603,6 +608,24 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
   return r;
 }
 __device__ __forceinline__ void la2_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M rows on the lanes, K packed two bf16 per 32-bit column) comes from tensor memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 template <bool TRACE>
 __global__ void __launch_bounds__(576, 1)
@@ -682,7 +705,7 @@ linattn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t id128 = make_idesc(128), id256 = make_idesc(256);
-      constexpr uint32_t id_gz = make_idesc(80) | (1u << 15) | (1u << 16);      // P^T [X | 1]: both operands MN-major
+      constexpr uint32_t id_gz = make_idesc(80) | (1u << 16);                   // P^T (tensor memory) [X | 1] (MN-major)
       constexpr uint32_t id_y = make_idesc(64) | (1u << 16);                    // softmax(Q) K-major, M MN-major
       const uint64_t wq = make_sw128_desc(sb + L2_WQ), wk = make_sw128_desc(sb + L2_WK), ud = make_sw128_desc(sb + L2_U);
       const uint64_t gnd = make_sw128_desc(sb + L2_PS);
@@ -692,6 +715,8 @@ linattn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       uint32_t xi = 0;                                 // x tiles consumed so far (ring position)
       uint32_t acc_m = 0, ps_m = 0, y_m = 0;           // bit `buf` = parity of that buffer's next use
       // projection of ring tile `gi` into accumulator `buf`; `release` frees the x stage with the same commit (Q pass)
+      // `release`: Q pass -- rows = tokens (X W^T); else K pass -- rows = channels (W X^T: the accumulator IS K^T, so that
+      // P^T can go back into tensor memory as the A operand of the G GEMM without a transpose)
       auto proj = [&](uint32_t gi, int buf, uint64_t w, bool release) {
         const uint32_t stage = gi % L2_XS;
         mbar_wait(xfull + 8 * stage, (gi / L2_XS) & 1);
@@ -701,7 +726,8 @@ linattn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         tc_fence_after();
         const uint64_t xd = make_sw128_desc(sb + L2_X + stage * 16384);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T2_ACC + 128 * buf, xd + 2 * k, w + 2 * k, id128, k ? 1u : 0u);
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + T2_ACC + 128 * buf, (release ? xd : w) + 2 * k, (release ? w : xd) + 2 * k, id128, k ? 1u : 0u);
         umma_commit(accfull + 8 * buf);
         if (release) umma_commit(xempty + 8 * stage);
         acc_m ^= 1u << buf;
@@ -721,13 +747,13 @@ linattn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           ev(3);
           tc_fence_after();
           const uint32_t stage = (xa + t) % L2_XS;
-          const uint64_t pmn = make_mn_desc(sb + L2_PS + buf * L2_PS_STRIDE, 16384);
           // B = [x tile (64 channels) | ones (16 columns)]: N = 80, the second 64-wide block is the 2 KB of ones whatever the
           // k step, so its distance (LBO) shrinks as the start address advances
           const uint64_t xmn = make_mn_desc(sb + L2_X + stage * 16384, (L2_ONES - L2_X) - stage * 16384);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem_base + T2_G, pmn + 128 * k, xmn + 128 * k - ((uint64_t)(128 * k) << 16), id_gz, (t == 0 && k == 0) ? 0u : 1u);
+            umma_bf16_ts(tmem_base + T2_G, tmem_base + T2_PT + 64 * buf + 8 * k, xmn + 128 * k - ((uint64_t)(128 * k) << 16), id_gz,
+                         (t == 0 && k == 0) ? 0u : 1u);
           umma_commit(psempty + 8 * buf);
           umma_commit(xempty + 8 * stage);
           ps_m ^= 1u << buf;
@@ -832,49 +858,36 @@ linattn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       if (et < 128) cq2[et] = (p.uv[384 + et] - gr * gmu * p.uv[et]) * kLog2e;
       else if (et < 192) yc[et - 128] = __ldg(p.bout + et - 128) + kQScale * p.c12[et - 128];
       if (et == 192) p.flag[b] = p.force_flag;
-      // the shift of the softmax over tokens = k of the sample's first token: group 0 reads it from tile 0's accumulator
-      if (grp == 0) {
+      // the shift of the softmax over tokens = k of the sample's first token.  The K accumulator is K^T (lane = channel (h,d),
+      // column = token): the 128 lanes of group 0's first column half hold it in column 0 of tile 0
+      if (grp == 0 && half == 0) {
         wait_bar(b_accfull, acc_n & 1);           // (consumed again, with the same parity, by P step 0)
-        if (quarter == 0) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t kr[32];
-            tmem_ld32(acc_addr + 32 * c, kr);
-            tmem_ld_wait();
-            if (lane == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) s_shift[64 * half + 32 * c + j] = __uint_as_float(kr[j]) * kscale;
-            }
-          }
-        }
+        const uint32_t k0 = tmem_ld1(acc_addr);
+        tmem_ld_wait();
+        s_shift[row] = __uint_as_float(k0) * kscale;
       }
       la2_bar();                                  // publishes the shift, cq2 / yc and the flag reset of this sample
-      // ---------------- P step (tiles of this group): P = exp2((k - k[token 0]) r log2e) as bf16 MN-major tiles
+      const float shift = s_shift[row];
+      // ---------------- P step (tiles of this group): P^T = exp2((k - k[token 0]) r log2e), bf16 pairs back into tensor memory
       for (int t = grp; t < T; t += 2) {
         wait_bar(b_accfull, acc_n & 1); ++acc_n;
         ev(11);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 2; ++c) {             // 32 tokens per round
           uint32_t kr[32];
           tmem_ld32(acc_addr + 32 * c, kr);
           tmem_ld_wait();
           if (c == 1) arrive(b_accempty, false);
-          const float4* sh4 = reinterpret_cast<const float4*>(s_shift + 64 * half + 32 * c);
+          uint32_t pw[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const float4 s0 = sh4[j >> 2], s1 = sh4[(j >> 2) + 1];
-            const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              kr[j + u] = pack2(ex2(fmaf(__uint_as_float(kr[j + 2 * u]), kscale, -sh[2 * u])),
-                                ex2(fmaf(__uint_as_float(kr[j + 2 * u + 1]), kscale, -sh[2 * u + 1])));
-          }
+          for (int j = 0; j < 16; ++j)
+            pw[j] = pack2(ex2(fmaf(__uint_as_float(kr[2 * j]), kscale, -shift)), ex2(fmaf(__uint_as_float(kr[2 * j + 1]), kscale, -shift)));
           if (c == 0) { ev(12); wait_bar(b_psempty, (ps_n & 1) ^ 1); ev(13); }   // the GEMM that read this buffer two tiles ago
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) st_sw128(ps_tile, row, 4 * c + (j >> 3), kr[j], kr[j + 1], kr[j + 2], kr[j + 3]);
+          tmem_st16(lane_addr + T2_PT + 64 * grp + 32 * half + 16 * c, pw);
         }
+        tmem_st_wait();
         ev(14);
-        arrive(b_psfull, true); ++ps_n;
+        arrive(b_psfull, false); ++ps_n;
         ev(15);
       }
       // ---------------- G / Z - mu -> bf16 K-major A operand of the M GEMM (row (h,d): this warp's 16 of the 64 x channels)
