@@ -30,6 +30,7 @@
 namespace tc {
 
 struct EpiP {
+  unsigned long long* dbg = nullptr;   // timeline probe (LDM_HALO_DEBUG bit 2): globaltimer stamps of CTA 0's first epilogue warp
   // geometry
   int M, H, W, hw;             // valid GEMM rows (linear geometry), image size, pixels per image
   int P, tiles_per_image;      // halo geometry (P > 0): padded pitch W+2, tiles per padded plane
@@ -137,6 +138,13 @@ __device__ __forceinline__ void conv_epilogue(const EpiP& p, const uint32_t tmem
   // LDM_EPI_DEBUG (timing experiments only; results are wrong): 1 no statistics math, 2 no packet wait, 4 no pass-2 stores,
   // 8 no pass-2 TMEM re-read / math
   const int xdbg = p.debug >> 16;
+  auto stamp = [&](int it, int slot) {
+    if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 32) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.dbg[it * 16 + slot] = t;
+    }
+  };
   // GroupNorm
   constexpr int gmode = GM;
   constexpr bool mode2 = GM == 2;
@@ -280,8 +288,10 @@ __device__ __forceinline__ void conv_epilogue(const EpiP& p, const uint32_t tmem
           for (int j = 0; j < 4; ++j) rr[j] = __ldg(reinterpret_cast<const uint4*>(rrow) + j);
         }
         if (!waited) {
+          stamp(iter, 4);
           if (lane == 0) mbar_wait(tfull_bar + 8 * acc, (iter / NACC) & 1);
           __syncwarp();
+          stamp(iter, 5);
           waited = true;
         }
         tc_fence_after();
@@ -315,6 +325,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiP& p, const uint32_t tmem
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_relaxed(tempty_bar + 8 * acc);
+            stamp(iter, 6);
           }
           float v[32];
 #pragma unroll
@@ -433,6 +444,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiP& p, const uint32_t tmem
         }
       }   // sub-tiles
       // (!mode2: the TMEM buffer was handed back right after its last read, above)
+      stamp(iter, 7);
       if (mode2) {
         epi_bar();   // s_red complete
         // canonical partial sums: fp32 over (statistics unit) x (column block), in (row segment, 8-column block) order

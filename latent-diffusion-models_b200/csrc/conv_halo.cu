@@ -186,11 +186,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kb = 0; kb < n_kb; ++kb) mbar_wait(bfull + 8 * kb, 0);
         tc_fence_after();
       }
-      int astage = 0; uint32_t aphase = 0;
+      int astage = 0;
       int bstage = 0; uint32_t bphase = 0;
       int iter = 0;
       int tin = blockIdx.x % tiles_per_image;  // tile index inside its image, advanced incrementally
       const int tstep = gridDim.x % tiles_per_image;
+      // The waits run ONE SLAB AHEAD of the MMAs: between two bursts the thread used to spend ~0.5 us (commit, index arithmetic,
+      // two satisfied mbarrier waits, fences) during which the tensor pipe sat idle -- a quarter of the tile period.  Now the
+      // accumulator / slab barriers of the NEXT slab (of this tile or of the next tile) are consumed in the middle of the current
+      // slab's taps, while the already queued MMAs keep the pipe busy.
+      int r_tile = blockIdx.x, r_s = 0, r_iter = 0, r_stage = 0;
+      uint32_t r_phase = 0;
+      auto ready_next = [&]() {
+        if (r_tile >= num_tiles) return;
+        if (r_s == 0) mbar_wait(tempty + 8 * (r_iter % HALO_NACC), ((r_iter / HALO_NACC) & 1) ^ 1);
+        mbar_wait(((xform && r_s < slabs_main) ? xfull : afull) + 8 * r_stage, r_phase);
+        tc_fence_after();
+        if (++r_stage == a_stages) { r_stage = 0; r_phase ^= 1; }
+        if (++r_s == slabs_total) { r_s = 0; r_tile += gridDim.x; ++r_iter; }
+      };
+      const bool ahead = !(p.debug & 64);      // LDM_HALO_DEBUG bit 6: wait at the top of each slab instead (A/B)
+      if (ahead) ready_next();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
         const int q0 = P + tin * TILE_M;
         const int lo = q0 - P - 1;
@@ -198,17 +214,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int off0 = q0 - r0 * P;  // slab row of the tile's first output position (centre tap)
         tin += tstep; if (tin >= tiles_per_image) tin -= tiles_per_image;
         const int acc = iter % HALO_NACC;
-        DBG_STAMP(0);
-        mbar_wait(tempty + 8 * acc, ((iter / HALO_NACC) & 1) ^ 1);
-        DBG_STAMP(1);
-        tc_fence_after();
+        DBG_STAMP(2);
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         uint32_t first_mma = 0u;  // accumulate flag of the very first MMA of the tile
         int kb = 0;
         for (int s = 0; s < slabs_total; ++s) {
-          mbar_wait(((xform && s < slabs_main) ? xfull : afull) + 8 * astage, aphase);
-          DBG_STAMP(2);
-          tc_fence_after();
+          if (!ahead) ready_next();
           const uint32_t a_addr = smem_a + astage * a_stage_bytes + (uint32_t)off0 * 128u;
           uint64_t adesc0 = make_sw128_desc(a_addr);
           if (s < slabs_main) {
@@ -224,6 +235,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (t > 0 || k > 0) ? 1u : first_mma);
                 }
                 bdesc += B_DESC_STEP;
+                if (t == 5 && ahead) ready_next();
               }
               kb += 9;
             } else {
@@ -239,6 +251,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 umma_commit(bempty + 8 * bstage);
                 if (++bstage == b_stages) { bstage = 0; bphase ^= 1; }
+                if (t == 5 && ahead) ready_next();
               }
             }
           } else {  // second source: centre tap only
@@ -250,10 +263,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             if (!resident) { umma_commit(bempty + 8 * bstage); if (++bstage == b_stages) { bstage = 0; bphase ^= 1; } }
             ++kb;
+            if (ahead) ready_next();
           }
           first_mma = 1u;
           umma_commit(aempty + 8 * astage);  // the slab is free once its taps' MMAs retire
-          if (++astage == a_stages) { astage = 0; aphase ^= 1; }
+          if (++astage == a_stages) astage = 0;
         }
         umma_commit(tfull + 8 * acc);
         DBG_STAMP(3);
@@ -464,6 +478,8 @@ int k_conv_halo(const ConvArgs& a, cudaStream_t st) {
   e.y = (bf16*)a.y; e.ldy = a.ldy;
   e.fin_w = a.fin_w; e.fin_b = a.fin_b; e.fin_out = a.fin_out; e.fin_cout = a.fin_cout;
   e.debug = p.debug | ((getenv("LDM_EPI_DEBUG") ? atoi(getenv("LDM_EPI_DEBUG")) : 0) << 16);
+  e.dbg = nullptr;
+  if (p.debug & 4) LDM_CUDA(cudaGetSymbolAddress((void**)&e.dbg, g_halo_dbg));
   // ---- fused GroupNorm plan (conv_epilogue.cuh): a sample always spans tiles_per_image tiles -> packet exchange
   const ConvGn& g = a.gn;
   e.gn_mode = g.mode;

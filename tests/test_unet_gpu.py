@@ -157,3 +157,30 @@ def test_rejects_bad_shapes():
     with pytest.raises(Exception):
         m(torch.zeros(2, 3, 32, 32, device=dev()), torch.zeros(2, dtype=torch.long, device=dev()),
           torch.zeros(3, dtype=torch.long, device=dev()))               # label count neither 1 nor batch
+
+
+def test_groupnorm_applied_inside_the_consuming_conv_opt_in():
+    """LDM_CONV_XFORM=1 (read once per process, hence the subprocess): the ResNetBlocks' second GroupNorm + SiLU is applied by
+    conv_halo_kernel's transform warps on the slab in shared memory instead of by an apply kernel.  Same golden, same bar, and
+    batch-shared CFG prefix included (y_rows path of the sampler)."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import sys, numpy as np, torch; sys.path.insert(0, %r)\n"
+        "import ldm_b200, oracle\n"
+        "g = np.load(%r)\n"
+        "dev = torch.device('cuda:0')\n"
+        "m = ldm_b200.UNet(3, 3, 64, (1, 2, 4, 8), True, 10, dtype='bf16').to(dev)\n"
+        "m.load_state_dict(oracle.init_state_dict(0, 3, 3, 64, (1, 2, 4, 8), True, 10))\n"
+        "x, t, y = (torch.from_numpy(g[k]).to(dev) for k in ('x', 't', 'y'))\n"
+        "ref = torch.from_numpy(g['eps_cond'])\n"
+        "with torch.no_grad(): out = m(x, t, y).float().cpu()\n"
+        "print('REL', float((out - ref).norm() / ref.norm()))\n"
+    ) % (ROOT, os.path.join(ROOT, "tests", "golden", "g1_unet_cifar.npz"))
+    env = dict(os.environ, LDM_CONV_XFORM="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rel = float([l for l in r.stdout.splitlines() if l.startswith("REL")][-1].split()[1])
+    assert rel < BAR["bf16"], rel

@@ -34,8 +34,8 @@ if int(os.environ.get("LDM_HALO_DEBUG", "0")) & 4:
         dns = buf[it*16+3] - buf[it*16+2]; dcy = buf[512+it*16+3] - buf[512+it*16+2]
         print(f"tile {it}: issue span {dns} ns = {dcy} cycles -> {dcy/dns:.3f} GHz; per MMA {dcy/36:.1f} cycles")
     t0 = buf[0]
-    names = {0: "mma:pre_tempty", 1: "mma:got_tempty", 2: "mma:got_afull", 3: "mma:committed", 4: "epi:pre_tfull", 5: "epi:got_tfull", 6: "epi:arrived", 8: "prod:pre_aempty", 9: "prod:got_aempty"}
-    for it in range(12):
+    names = {0: "mma:pre_tempty", 1: "mma:got_tempty", 2: "mma:got_afull", 3: "mma:committed", 4: "epi:pre_tfull", 5: "epi:got_tfull", 6: "epi:released", 7: "epi:tile_end", 8: "prod:pre_aempty", 9: "prod:got_aempty"}
+    for it in range(8, 20):
         print(f"tile {it}: " + "  ".join(f"{names[k]}={buf[it*16+k]-t0}" for k in sorted(names)))
 
 if int(os.environ.get("LDM_TC_DEBUG", "0")):
