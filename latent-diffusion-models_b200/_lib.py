@@ -178,3 +178,42 @@ def ptr(t) -> Optional[int]:
 def stream_ptr():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+# ---- native handle destruction that is safe next to CUDA-graph capture
+# ldm_unet_destroy frees the packed-weight arena with cudaFree and ldm_sampler_destroy destroys graph executables: both are
+# "unsafe" calls while ANY stream of the process is capturing (global capture mode) -- they invalidate the capture.  Objects
+# die whenever Python's cyclic collector runs, e.g. in the middle of torch.cuda.make_graphed_callables of a later model, so a
+# destroy request that arrives during a capture is parked and carried out by the next request that arrives outside one.
+_graveyard: list = []
+
+
+def _capturing() -> bool:
+    try:
+        import torch
+        return bool(torch.cuda.is_available() and torch.cuda.is_current_stream_capturing())
+    except Exception:
+        return False
+
+
+def destroy_native(fn_name: str, handle) -> None:
+    """Call ``lib.<fn_name>(handle)`` now, or after the stream capture that is in progress on this thread."""
+    if handle is None:
+        return
+    _graveyard.append((fn_name, handle))
+    flush_graveyard()
+
+
+def flush_graveyard() -> None:
+    if not _graveyard or _capturing():
+        return
+    try:
+        lib = load()
+    except Exception:
+        return
+    while _graveyard:
+        name, h = _graveyard.pop()
+        try:
+            getattr(lib, name)(h)
+        except Exception:
+            pass

@@ -67,7 +67,7 @@ class Diffusion(nn.Module):
             ent = self._samplers[key]
             if dead_only and ent["unet"]() is not None:
                 continue
-            lib.ldm_sampler_destroy(ent["s"])
+            _lib.destroy_native("ldm_sampler_destroy", ent["s"])    # parked while a CUDA-graph capture is in progress
             del self._samplers[key]
 
     def __getstate__(self):

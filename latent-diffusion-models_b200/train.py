@@ -613,7 +613,18 @@ def make_graphed(model, x_noisy: torch.Tensor, t: torch.Tensor, y: Optional[torc
     outs = enc(*args_a)                               # eager, once: the shapes / dtypes of the boundary tensors
     args_b = tuple(torch.zeros_like(o).requires_grad_(o.requires_grad) for o in outs)
     del outs
-    g_enc, g_dec = torch.cuda.make_graphed_callables((enc, dec), (args_a, args_b), allow_unused_input=True)
+    # No cyclic garbage collection while a stream is capturing: graph objects, samplers and native UNet handles of models that
+    # died earlier are freed with cudaFree / cudaGraphExecDestroy, which invalidates a capture in progress (the collector runs
+    # whenever its allocation counters say so, e.g. in the middle of the second half's forward capture).
+    import gc
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        g_enc, g_dec = torch.cuda.make_graphed_callables((enc, dec), (args_a, args_b), allow_unused_input=True)
+    finally:
+        if was_enabled:
+            gc.enable()
 
     def forward(x_noisy, t, y=None):
         outs = g_enc(x_noisy, t, y) if y is not None else g_enc(x_noisy, t)

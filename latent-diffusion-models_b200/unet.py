@@ -135,9 +135,10 @@ class UNet(nn.Module):
 
     def _destroy_native(self) -> None:
         try:
-            lib = _lib.load()
             for h in getattr(self, "_handles", {}).values():
-                lib.ldm_unet_destroy(h)
+                _lib.destroy_native("ldm_unet_destroy", h)     # parked while a CUDA-graph capture is in progress (cudaFree)
+            if getattr(self, "_handles", None):
+                self._handles = {}
         except Exception:
             pass
 
@@ -168,6 +169,7 @@ class UNet(nn.Module):
         key = (image_size, device.index if device.index is not None else torch.cuda.current_device())
         h = self._handles.get(key)
         if h is None:
+            _lib.flush_graveyard()              # handles whose owners died during a stream capture
             lib = _lib.load()
             d = _lib.UNetDesc()
             d.in_channels, d.out_channels, d.channels = self.in_channels, self.out_channels, self.channels
