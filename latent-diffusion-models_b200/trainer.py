@@ -81,6 +81,10 @@ class FlatAdam:
             cuts.append(int(self.offsets[int(np.searchsorted(self.offsets, target))]))
         cuts.append(n)
         self.bucket_bounds = sorted(set(cuts))
+        # data parallel: every replica starts from rank 0's parameters (the reference has one process; nothing else would make
+        # the replicas agree unless every rank happened to seed torch identically)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.broadcast(self.flat_param, src=0)
         self.step_count = 0
         self.generation = 0                      # bumped by begin_step: a slot is handed out once per generation
         self._slot_gen: dict = {}
